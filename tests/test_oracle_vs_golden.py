@@ -1,0 +1,107 @@
+"""Pins the CPU oracle (oracle/in_oracle.py) against golden vectors produced by the
+reference's own classes (tests/golden/make_golden.py)."""
+import pytest
+import torch
+
+from oracle import in_oracle as O
+from tests.golden.common import case_inputs
+
+# fp32 CPU vs fp32 CPU through the same ATen ops: differences are summation-order
+# noise only.  Tolerance is relative to the output scale (SURVEY 8c guidance).
+RTOL = 2e-6
+
+
+def close(a, b, rtol=RTOL):
+    scale = max(float(b.abs().max()), 1.0)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    err = float((a - b).abs().max())
+    assert err <= rtol * scale, f"max|d|={err:.3e} scale={scale:.3e}"
+
+
+def _cases(kind):
+    from tests.golden.common import load
+
+    return [k for k, v in load("models").items() if v["kind"] == kind]
+
+
+@pytest.mark.parametrize("name", _cases("in"))
+def test_in_layer(name, golden_models, golden_graphs):
+    c = golden_models[name]
+    gd = case_inputs(c, golden_graphs)
+    xt, et = O.interaction_network(gd["x"], gd["edge_index"], gd["edge_attr"], c["state_dict"], "")
+    close(xt, c["outputs"]["x_tilde"])
+    close(et, c["outputs"]["e_tilde"])
+
+
+@pytest.mark.parametrize("name", _cases("resin"))
+def test_resin(name, golden_models, golden_graphs):
+    c = golden_models[name]
+    gd = case_inputs(c, golden_graphs)
+    kw = c["kwargs"]
+    rk = kw.get("residual_kwargs") or {}
+    x, e, es = O.resin(gd["x"], gd["edge_index"], gd["edge_attr"], c["state_dict"], "network.",
+                       alpha=kw["alpha"], residual_type=kw["residual_type"],
+                       collect=rk.get("collect_hidden_edge_embeds", False), connect_to=rk.get("connect_to", 1))
+    close(x, c["outputs"]["x"])
+    close(e, c["outputs"]["edge_attr"])
+    ref_es = c["outputs"]["edge_attrs"]
+    if ref_es is None:
+        assert es is None
+    else:
+        assert len(es) == len(ref_es)
+        for a, b in zip(es, ref_es):
+            close(a, b)
+
+
+@pytest.mark.parametrize("name", _cases("ec"))
+def test_ec(name, golden_models, golden_graphs):
+    c = golden_models[name]
+    gd = case_inputs(c, golden_graphs)
+    kw = c["kwargs"]
+    out = O.ec_forward(gd["x"], gd["edge_index"], gd["edge_attr"], c["state_dict"], "",
+                       alpha=kw.get("alpha", 0.5), residual_type=kw.get("residual_type", "skip1"),
+                       use_intermediate_edge_embeddings=kw.get("use_intermediate_edge_embeddings", True),
+                       use_node_embedding=kw.get("use_node_embedding", True),
+                       residual_kwargs=kw.get("residual_kwargs"))
+    for k in ("W", "node_embedding", "edge_embedding"):
+        close(out[k], c["outputs"][k])
+
+
+@pytest.mark.parametrize("name", _cases("tcn"))
+def test_tcn(name, golden_models, golden_graphs):
+    c = golden_models[name]
+    gd = case_inputs(c, golden_graphs)
+    kw = c["kwargs"]
+    out = O.graph_tcn_forward(
+        gd["x"], gd["edge_index"], gd["edge_attr"], c["state_dict"], "_gtcn.",
+        alpha_ec=kw.get("alpha_ec", 0.5), alpha_hc=kw.get("alpha_hc", 0.5),
+        ec_threshold=kw.get("ec_threshold", 0.5), mask_orphan_nodes=kw.get("mask_orphan_nodes", False),
+        use_ec_embeddings_for_hc=kw.get("use_ec_embeddings_for_hc", False),
+        feed_edge_weights=kw.get("feed_edge_weights", False), alpha_latent=kw.get("alpha_latent", 0.0),
+        n_embedding_coords=kw.get("n_embedding_coords", 0))
+    ref = c["outputs"]
+    assert torch.equal(out["ec_edge_mask"], ref["ec_edge_mask"])
+    assert torch.equal(out["ec_hit_mask"], ref["ec_hit_mask"])
+    close(out["W"], ref["W"])
+    close(out["H"], ref["H"], rtol=1e-5)
+    close(out["B"], ref["B"], rtol=1e-5)
+
+
+def test_survey_self_check_values(golden_models):
+    """SURVEY.md 8(c) self-check values of the reference on test_graph.pt."""
+    o = golden_models["in_testgraph_default"]["outputs"]
+    assert float(o["x_tilde"].sum()) == pytest.approx(1596.53578, rel=1e-6)
+    assert float(o["e_tilde"].sum()) == pytest.approx(-13142.87839, rel=1e-6)
+    assert float(golden_models["ec_yml_testgraph"]["outputs"]["W"].sum()) == pytest.approx(150.0467169, rel=1e-6)
+
+
+def test_plan_oracle_is_stable_sort(golden_graphs):
+    ei = golden_graphs["synthetic"]["edge_index"]
+    n = golden_graphs["synthetic"]["x"].size(0)
+    perm, rowptr, src_s, dst_s = O.plan(ei, n)
+    assert torch.all(dst_s[1:] >= dst_s[:-1])
+    same = dst_s[1:] == dst_s[:-1]
+    assert torch.all(perm[1:][same] > perm[:-1][same])  # stable within a destination
+    assert rowptr[-1] == ei.size(1) and rowptr[0] == 0
+    deg = rowptr[1:] - rowptr[:-1]
+    assert torch.equal(deg, torch.bincount(ei[1], minlength=n))
