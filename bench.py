@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""Benchmark of the Interaction-Network hot path (BASELINE.json metric:
+"edges/sec on 1M-edge TrackML-shape graph ...; % HBM roofline").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--dims wide|default]
+
+A *step* is one full ``ECForGraphTCN`` forward (encoders -> 3 x IN -> W head, hidden 64,
+fp32) over one synthetic TrackML-shaped graph of 100k nodes / 1M directed edges
+(BASELINE.json configs[1]), including the per-graph plan build (destination sort).
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+N_NODES, N_EDGES = 100_000, 1_000_000
+NODE_IN, EDGE_IN, HIDDEN, L_EC = 14, 4, 64, 3
+
+
+# ------------------------------------------------------------------ synthetic graph
+def make_graph(n_nodes: int, n_edges: int, seed: int = 0) -> dict:
+    """Seeded TrackML-shaped graph: hits on 10 concentric layers, candidate edges
+    between adjacent layers inside a phi window, doubled in both directions with
+    sign-flipped (dr, dphi, dz) and unchanged dR (reference graph_builder.py:371-378,
+    431-438); layer-pair block order, NOT destination sorted."""
+    gen = torch.Generator().manual_seed(seed)
+    n_layers = 10
+    per = n_nodes // n_layers
+    n_nodes = per * n_layers
+    layer = torch.arange(n_layers).repeat_interleave(per)
+    r = (layer.float() + 1.0) * 0.1 + torch.randn(n_nodes, generator=gen) * 1e-3
+    phi = (torch.rand(n_nodes, generator=gen) * 2 - 1) * math.pi
+    z = torch.randn(n_nodes, generator=gen) * 0.3
+    half = n_edges // 2
+    want_per_pair = half / (n_layers - 1) * 1.15
+    delta = want_per_pair / per * math.pi / per  # expected neighbours per hit = per * delta / pi
+    srcs, dsts = [], []
+    for l in range(n_layers - 1):
+        a = torch.arange(l * per, (l + 1) * per)
+        b = torch.arange((l + 1) * per, (l + 2) * per)
+        order = torch.argsort(phi[b])
+        pb = phi[b][order]
+        lo = torch.searchsorted(pb, phi[a] - delta)
+        hi = torch.searchsorted(pb, phi[a] + delta)
+        cnt = hi - lo
+        src = a.repeat_interleave(cnt)
+        start = torch.cumsum(cnt, 0) - cnt
+        off = torch.arange(int(cnt.sum())) - start.repeat_interleave(cnt)
+        dst = b[order][lo.repeat_interleave(cnt) + off]
+        srcs.append(src)
+        dsts.append(dst)
+    src, dst = torch.cat(srcs), torch.cat(dsts)
+    assert src.numel() >= half, (src.numel(), half)
+    keep = torch.randperm(src.numel(), generator=gen)[:half].sort().values
+    src, dst = src[keep], dst[keep]
+    dr, dphi, dz = r[dst] - r[src], phi[dst] - phi[src], z[dst] - z[src]
+    dR = torch.sqrt(dphi ** 2 + (dz * 0.5) ** 2)
+    fwd = torch.stack([dr, dphi, dz, dR], 1)
+    bwd = torch.stack([-dr, -dphi, -dz, dR], 1)
+    edge_index = torch.cat([torch.stack([src, dst]), torch.stack([dst, src])], 1).contiguous()
+    edge_attr = torch.cat([fwd, bwd], 0).contiguous()
+    eta = torch.asinh(z / r)
+    x = torch.cat([torch.stack([r, phi / math.pi, z, eta, r * torch.cos(phi), r * torch.sin(phi)], 1),
+                   torch.randn(n_nodes, 8, generator=gen)], 1).contiguous()
+    pid = torch.randint(0, n_nodes // 10, (n_nodes,), generator=gen)
+    y = (pid[edge_index[0]] == pid[edge_index[1]]) & (pid[edge_index[0]] > 0)
+    return {"x": x, "edge_index": edge_index, "edge_attr": edge_attr, "y": y, "n_nodes": n_nodes,
+            "n_edges": edge_index.size(1)}
+
+
+def model_kwargs(dims: str) -> dict:
+    kw = dict(node_indim=NODE_IN, edge_indim=EDGE_IN, hidden_dim=HIDDEN, L_ec=L_EC)
+    if dims == "wide":
+        kw.update(interaction_node_dim=HIDDEN, interaction_edge_dim=HIDDEN)
+    return kw
+
+
+def workload_name(dims: str, n: int, e: int) -> str:
+    d = "Dn=De=H=64 (wide)" if dims == "wide" else "Dn=5,De=4,H=64 (reference-default widths)"
+    return f"ECForGraphTCN forward, L_ec=3, {d}, fp32, TrackML-shaped synthetic graph {n} nodes / {e} edges, plan build per step"
+
+
+def layer_algorithmic_bytes(n: int, e: int, dn: int, de: int) -> float:
+    """B_layer = E*(2*idx + s*De_in + s*De_out) + N*s*(Dn_in + Dn_out), s = 4, idx = 8."""
+    return e * (16 + 4 * de + 4 * de) + n * 4 * (dn + dn)
+
+
+# ------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [s.strip() for s in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self) -> dict:
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------- CPU legs
+def cpu_forward_time(g: dict, dims: str, reps: int, warm: int) -> tuple[float, int]:
+    """The CPU restatement of the reference forward (oracle/in_oracle.py, pinned to the
+    reference's own classes) on all host threads; returns (median seconds, threads)."""
+    from oracle import in_oracle as O
+    from gnn_tracking_b200.models.edge_classifier import ECForGraphTCN
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    sd = {k: v.clone() for k, v in ECForGraphTCN(**model_kwargs(dims)).state_dict().items()}
+    ts = []
+    with torch.no_grad():
+        for i in range(warm + reps):
+            t0 = time.perf_counter()
+            O.ec_forward(g["x"], g["edge_index"], g["edge_attr"], sd)
+            if i >= warm:
+                ts.append(time.perf_counter() - t0)
+    return statistics.median(ts), threads
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n, e = N_NODES, N_EDGES
+    sample = "full graph per step"
+    if args.steps + args.warmup > 16:  # keep the whole run within a few minutes
+        n, e = N_NODES // 4, N_EDGES // 4
+        sample = "quarter-size graph (25k nodes / 250k edges) per step"
+    g = make_graph(n, e)
+    from oracle import in_oracle as O
+    from gnn_tracking_b200.models.edge_classifier import ECForGraphTCN
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    sd = {k: v.clone() for k, v in ECForGraphTCN(**model_kwargs(args.dims)).state_dict().items()}
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            O.ec_forward(g["x"], g["edge_index"], g["edge_attr"], sd)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            O.ec_forward(g["x"], g["edge_index"], g["edge_attr"], sd)
+        dt = time.perf_counter() - t0
+    val = g["n_edges"] * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "edges/sec", "value": val, "unit": "edges/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.dims, g["n_nodes"], g["n_edges"]),
+                   "note": "CPU restatement of the reference forward (oracle/in_oracle.py, op-for-op the PyG/ATen chain; "
+                           "the Python reference cannot travel to the GPU box)"},
+        "cpu_baseline": {"value": val, "unit": "edges/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# -------------------------------------------------------------------------- ours
+def run_ours(args) -> None:
+    import torch.distributed as dist
+    from gnn_tracking_b200 import ops
+    from gnn_tracking_b200.models.edge_classifier import ECForGraphTCN
+    from gnn_tracking_b200.plan import build_plan, clear_plan_cache
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # weak scaling: every rank owns one full graph per step (independent events, as the
+    # reference trains with batch_size=1 graph per step); no data-path collective.
+    g = make_graph(N_NODES, N_EDGES, seed=rank)
+    n, e = g["n_nodes"], g["n_edges"]
+    torch.manual_seed(0)
+    model = ECForGraphTCN(**model_kwargs(args.dims)).to(dev)
+    x, ei, ea = g["x"].to(dev), g["edge_index"].to(dev), g["edge_attr"].to(dev)
+    hx, hei, hea = g["x"].pin_memory(), g["edge_index"].pin_memory(), g["edge_attr"].pin_memory()
+    hw = torch.empty(e, dtype=torch.float32).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step_resident():
+        clear_plan_cache()
+        with torch.no_grad():
+            return model.forward_tensors(x, ei, ea)
+
+    def step_e2e():
+        clear_plan_cache()
+        dx, dei, dea = hx.to(dev, non_blocking=True), hei.to(dev, non_blocking=True), hea.to(dev, non_blocking=True)
+        with torch.no_grad():
+            out = model.forward_tensors(dx, dei, dea)
+        hw.copy_(out["W"], non_blocking=True)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        evs = []
+        l0 = ops.launch_count()
+        for _ in range(steps):
+            flush.zero_()  # L2 flush between timed iterations (outside the events)
+            s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn()
+            t.record()
+            evs.append((s, t))
+        barrier()
+        launches = ops.launch_count() - l0
+        ms = sum(s.elapsed_time(t) for s, t in evs)
+        if world > 1:
+            tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        return ms, launches
+
+    with ClockSampler(local) as clocks:
+        ms, launches = timed(step_resident, args.steps, args.warmup)
+        ms_e2e, _ = timed(step_e2e, args.steps, max(1, args.warmup))
+
+    # ---- dominant kernel (fused IN edge kernel of a middle layer: ReLU on load), timed alone
+    dn, de = (HIDDEN, HIDDEN) if args.dims == "wide" else (5, 4)
+    plan = build_plan(ei, n)
+    layer = model.ec_resin.network.layers[1]
+    xx = torch.randn(n, dn, device=dev)
+    ee = torch.randn(e, de, device=dev)
+    kt = []
+    for i in range(3 + args.steps):
+        flush.zero_()
+        s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        aggr = torch.zeros((n, de), device=dev)
+        out = torch.empty((e, de), device=dev)
+        s.record()
+        with torch.no_grad():
+            layer.relational_model.forward_blocks(
+                [ops.Block(xx, plan.dst_sorted, True), ops.Block(xx, plan.src_sorted, True),
+                 ops.Block(ee, plan.perm, True)], e, out=out, out_index=plan.perm, aggr=aggr,
+                seg_id=plan.dst_sorted, rowptr=plan.rowptr)
+        t.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            kt.append(s.elapsed_time(t))
+    k_ms = statistics.mean(kt)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks_file = ROOT / "MEASURED_PEAKS.json"
+    if peaks_file.exists():
+        peak, peak_src = float(json.loads(peaks_file.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+    alg = layer_algorithmic_bytes(n, e, dn, de)
+    achieved = alg / (k_ms * 1e-3) / 1e9
+    traffic = None
+    tf = ROOT / "profiles" / "roofline_traffic.json"
+    if tf.exists():
+        traffic = json.loads(tf.read_text()).get(args.dims)
+
+    value = e * world * args.steps / (ms * 1e-3)
+    e2e_val = e * world * args.steps / (ms_e2e * 1e-3)
+    line = {
+        "metric": "edges/sec", "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.dims, n, e), "l2": "flushed between timed iterations (256 MB write)",
+                   "multi_gpu": "one independent graph per rank per step, no data-path collective",
+                   "impl": os.environ.get("GTB_IMPL", "auto")},
+        "e2e": {"value": e2e_val, "unit": "edges/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": hx.numel() * 4 + hei.numel() * 8 + hea.numel() * 4, "d2h_bytes_per_step": e * 4},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": "fused IN edge kernel (gather + relational MLP + segmented sum), one layer",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "algorithmic_bytes_per_launch": alg, "kernel_ms": k_ms, "peak_source": peak_src},
+        "clocks": clocks.summary(),
+    }
+    if world == 1 and not args.no_cpu:
+        t_cpu, threads = cpu_forward_time(g, args.dims, reps=3, warm=1)
+        line["cpu_baseline"] = {"value": e / t_cpu, "unit": "edges/s", "cores": threads, "kind": "port",
+                                "sample": "same full graph, 1 warm-up + 3 forwards, median",
+                                "ms_per_step": t_cpu * 1e3}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dims", default="wide", choices=["wide", "default"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,77 @@
+"""Object-condensation loss "tiger" behind the reference interface (reference
+metrics/losses/oc.py:251-436) without the N x K planes (``gtb_oc_*``)."""
+from __future__ import annotations
+
+import torch
+from torch import Tensor
+
+from ... import ops
+from ..._hparams import HyperparametersMixin
+from ..._lib import check, lib
+from ...utils.graph_masks import get_good_node_mask_tensors
+from . import MultiLossFct, MultiLossFctReturn
+
+
+def condensation_loss_tiger(*, beta: Tensor, x: Tensor, object_id: Tensor, object_mask: Tensor, q_min: float,
+                            noise_threshold: int = 0, max_n_rep: int = 0):
+    """Same contract as the reference function (oc.py:251-347): returns
+    ``({"attractive", "repulsive", "coward", "noise"}, {"n_rep"})``."""
+    if max_n_rep:
+        raise NotImplementedError("max_n_rep sub-sampling uses the reference's fp16 torch RNG stream and is "
+                                  "not reproduced; the tiled kernel needs no sub-sampling to fit in memory")
+    dev = ops.require_cuda(beta, x, object_id, object_mask)
+    n, d = x.shape
+    st = ops.stream_ptr(dev)
+    beta = beta.reshape(-1).to(torch.float32).contiguous()
+    x = x.to(torch.float32).contiguous()
+    oid = object_id.to(torch.int64).contiguous()
+    mask = object_mask.to(torch.bool).contiguous().view(torch.uint8)
+    uniq = torch.empty(n, dtype=torch.int64, device=dev)
+    slot = torch.empty(n, dtype=torch.int32, device=dev)
+    n_uniq = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws_bytes = lib().gtb_oc_workspace_bytes(n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    check(lib().gtb_oc_prepare(oid.data_ptr(), mask.data_ptr(), n, uniq.data_ptr(), slot.data_ptr(),
+                               n_uniq.data_ptr(), ws.data_ptr(), ws_bytes, st))
+    k = int(n_uniq.item())  # the reference's torch.unique syncs at the same place
+    assert k > 0, "No hits left after masking"
+    scratch = torch.empty(k, dtype=torch.int64, device=dev)
+    alphas = torch.empty(k, dtype=torch.int32, device=dev)
+    check(lib().gtb_oc_alphas(beta.data_ptr(), slot.data_ptr(), n, float(q_min), k, scratch.data_ptr(),
+                              alphas.data_ptr(), st))
+    out = torch.zeros(8, dtype=torch.float64, device=dev)
+    check(lib().gtb_oc_potentials(beta.data_ptr(), x.data_ptr(), d, oid.data_ptr(), mask.data_ptr(),
+                                  slot.data_ptr(), n, alphas.data_ptr(), k, float(q_min), int(noise_threshold),
+                                  out.data_ptr(), st))
+    ops._count(9)
+    eps = 1e-9
+    v_att, v_rep, coward, noise, n_noise, n_oi, n_rep, _ = out.unbind(0)
+    losses = {
+        "attractive": (v_att / (eps + n_oi - k)).float(),
+        "repulsive": (v_rep / (eps + (k - 1) * n)).float(),
+        "coward": (coward / k).float(),
+        "noise": (noise / n_noise).float(),  # NaN without noise hits, as in the reference (oc.py:335-336)
+    }
+    return losses, {"n_rep": n_rep.to(torch.int64), "alphas": alphas, "unique_ids": uniq[:k]}
+
+
+class CondensationLossTiger(MultiLossFct, HyperparametersMixin):
+    def __init__(self, *, lw_repulsive: float = 1.0, lw_noise: float = 0.0, lw_coward: float = 0.0,
+                 q_min: float = 0.01, pt_thld: float = 0.9, max_eta: float = 4.0, max_n_rep: int = 0,
+                 sample_pids: float = 1.0):
+        super().__init__()
+        self.save_hyperparameters()
+
+    def forward(self, *, beta: Tensor, x: Tensor, particle_id: Tensor, reconstructable: Tensor, pt: Tensor,
+                ec_hit_mask: Tensor | None = None, eta: Tensor, **kwargs) -> MultiLossFctReturn:
+        hp = self.hparams
+        if ec_hit_mask is not None:  # model outputs are already pruned, the truth is not (oc.py:394-401)
+            particle_id, reconstructable, pt, eta = (t[ec_hit_mask] for t in (particle_id, reconstructable, pt, eta))
+        mask = get_good_node_mask_tensors(pt=pt, particle_id=particle_id, reconstructable=reconstructable,
+                                          eta=eta, pt_thld=hp.pt_thld, max_eta=hp.max_eta)
+        if hp.sample_pids < 1:
+            raise NotImplementedError("sample_pids < 1 draws from the reference's fp16 torch RNG stream")
+        losses, extra = condensation_loss_tiger(beta=beta, x=x, object_id=particle_id, object_mask=mask,
+                                                q_min=hp.q_min, noise_threshold=0, max_n_rep=hp.max_n_rep)
+        weights = {"attractive": 1.0, "repulsive": hp.lw_repulsive, "noise": hp.lw_noise, "coward": hp.lw_coward}
+        return MultiLossFctReturn(loss_dct=losses, weight_dct=weights, extra_metrics={"n_rep": extra["n_rep"]})

@@ -1,0 +1,65 @@
+"""Edge classifier of the Graph-TCN behind the reference interface (reference
+models/edge_classifier.py:15-121): encoders -> ResIN -> W head, each a fused
+kernel over the shared destination-sorted plan."""
+from __future__ import annotations
+
+from torch import Tensor, nn
+
+from .. import ops
+from .._hparams import HyperparametersMixin
+from ..ops import ACT_RELU, ACT_SIGMOID_AFFINE, Block
+from ..plan import GraphPlan, get_plan
+from ..utils.asserts import assert_feat_dim
+from .mlp import MLP
+from .resin import ResIN
+
+
+class ECForGraphTCN(nn.Module, HyperparametersMixin):
+    def __init__(self, *, node_indim: int, edge_indim: int, interaction_node_dim: int = 5,
+                 interaction_edge_dim: int = 4, hidden_dim: int | float | None = None, L_ec: int = 3,
+                 alpha: float = 0.5, residual_type="skip1", use_intermediate_edge_embeddings: bool = True,
+                 use_node_embedding: bool = True, residual_kwargs: dict | None = None):
+        """Same arguments, ``.hparams`` and parameter names as the reference
+        (``ec_node_encoder``, ``ec_edge_encoder``, ``ec_resin.network.layers.*``, ``W``)."""
+        super().__init__()
+        self.save_hyperparameters()
+        residual_kwargs = dict(residual_kwargs or {})
+        residual_kwargs["collect_hidden_edge_embeds"] = use_intermediate_edge_embeddings
+        self.relu = nn.ReLU()
+        self.ec_node_encoder = MLP(node_indim, interaction_node_dim, hidden_dim=hidden_dim, L=2, bias=False)
+        self.ec_edge_encoder = MLP(edge_indim, interaction_edge_dim, hidden_dim=hidden_dim, L=2, bias=False)
+        self.ec_resin = ResIN(node_dim=interaction_node_dim, edge_dim=interaction_edge_dim,
+                              object_hidden_dim=hidden_dim, relational_hidden_dim=hidden_dim, alpha=alpha,
+                              n_layers=L_ec, residual_type=residual_type, residual_kwargs=residual_kwargs)
+        w_in = interaction_edge_dim
+        if use_intermediate_edge_embeddings:
+            w_in = self.ec_resin.concat_edge_embeddings_length
+        if use_node_embedding:
+            w_in += 2 * interaction_node_dim
+        self.W = MLP(input_size=w_in, output_size=1, hidden_dim=hidden_dim, L=3)
+        self.latent_dim = (interaction_node_dim, interaction_edge_dim)
+
+    def forward(self, data) -> dict[str, Tensor]:
+        x, edge_index, edge_attr = data.x, data.edge_index, data.edge_attr
+        return self.forward_tensors(x, edge_index, edge_attr)
+
+    def forward_tensors(self, x: Tensor, edge_index: Tensor, edge_attr: Tensor,
+                        plan: GraphPlan | None = None) -> dict[str, Tensor]:
+        assert_feat_dim(x, self.hparams.node_indim)
+        assert_feat_dim(edge_attr, self.hparams.edge_indim)
+        ops.require_cuda(x, edge_index, edge_attr)
+        if plan is None:
+            plan = get_plan(edge_index, x.size(0))
+        n, e = x.size(0), edge_attr.size(0)
+        # encoders + the ReLU behind them (edge_classifier.py:102-103)
+        h = self.ec_node_encoder.forward_blocks([Block(x)], n, final_act=ACT_RELU)
+        ea = self.ec_edge_encoder.forward_blocks([Block(edge_attr)], e, final_act=ACT_RELU)
+        h, ea, eas = self.ec_resin.forward_planned(h, plan, ea)
+        # W head over cat[h[src], h[dst], e_0 .. e_L] (edge_classifier.py:108-117), walked in
+        # dst-sorted order (h[dst] rows repeat) and written back in the caller's edge order
+        blocks = []
+        if self.hparams.use_node_embedding:
+            blocks += [Block(h, plan.src_sorted), Block(h, plan.dst_sorted)]
+        blocks += [Block(t, plan.perm) for t in (eas if self.hparams.use_intermediate_edge_embeddings else [ea])]
+        w = self.W.forward_blocks(blocks, e, final_act=ACT_SIGMOID_AFFINE, act_eps=0.001, out_index=plan.perm)
+        return {"W": w.squeeze(), "node_embedding": h, "edge_embedding": ea}

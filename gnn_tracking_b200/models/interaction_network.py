@@ -1,0 +1,55 @@
+"""Interaction-Network layer behind the reference's module interface
+(reference models/interaction_network.py:12-103): same constructor arguments,
+``.hparams``, parameter names (``relational_model.layers.*``,
+``object_model.layers.*``) and ``forward(x, edge_index, edge_attr) -> (x_tilde,
+e_tilde)`` in the caller's edge order -- computed by two fused kernels over a
+destination-sorted plan instead of PyG's gather / cat / addmm / scatter_add chain."""
+from __future__ import annotations
+
+import torch
+from torch import Tensor, nn
+
+from .. import ops
+from .._hparams import HyperparametersMixin
+from ..ops import Block
+from ..plan import GraphPlan, get_plan
+from ..utils.asserts import assert_feat_dim
+from .mlp import MLP
+
+
+class InteractionNetwork(nn.Module, HyperparametersMixin):
+    def __init__(self, *, node_indim: int, edge_indim: int, node_outdim: int = 3, edge_outdim: int = 4,
+                 node_hidden_dim: int = 40, edge_hidden_dim: int = 40, aggr: str = "add"):
+        super().__init__()
+        self.save_hyperparameters()
+        if aggr != "add":
+            raise ValueError("only aggr='add' (the reference default, used by every model) is implemented")
+        self.relational_model = MLP(2 * node_indim + edge_indim, edge_outdim, edge_hidden_dim)
+        self.object_model = MLP(node_indim + edge_outdim, node_outdim, node_hidden_dim)
+
+    def forward(self, x: Tensor, edge_index: Tensor, edge_attr: Tensor) -> tuple[Tensor, Tensor]:
+        assert_feat_dim(x, self.hparams.node_indim)
+        assert_feat_dim(edge_attr, self.hparams.edge_indim)
+        plan = get_plan(edge_index, x.size(0))
+        return self.forward_planned(x, plan, edge_attr)
+
+    def forward_planned(self, x: Tensor, plan: GraphPlan, edge_attr: Tensor, *, relu_x: bool = False,
+                        relu_e: bool = False, res: Tensor | None = None, res_a: float = 0.0,
+                        res_b: float = 1.0) -> tuple[Tensor, Tensor]:
+        """One layer on a planned graph.  ``relu_*`` apply the activation on load (layers
+        > 0 of a residual stack see relu(x), reference models/resin.py:104-105); ``res``
+        fuses ``sqconvex_combination`` (resin.py:17-42) into the node kernel."""
+        dev = ops.require_cuda(x, edge_attr)
+        n, e = x.size(0), edge_attr.size(0)
+        e_out = self.hparams.edge_outdim
+        # zeroed: isolated nodes keep 0 (SumAggregation), partial runs are added atomically
+        aggr = torch.zeros((n, e_out), dtype=torch.float32, device=dev)
+        # message(): cat[x_i (target), x_j (source), edge_attr]  (interaction_network.py:75-89)
+        e_tilde = self.relational_model.forward_blocks(
+            [Block(x, plan.dst_sorted, relu_x), Block(x, plan.src_sorted, relu_x),
+             Block(edge_attr, plan.perm, relu_e)],
+            e, out_index=plan.perm, aggr=aggr, seg_id=plan.dst_sorted, rowptr=plan.rowptr)
+        # update(): cat[x, aggr]  (interaction_network.py:92-103)
+        x_tilde = self.object_model.forward_blocks([Block(x, None, relu_x), Block(aggr)], n,
+                                                   res=res, res_a=res_a, res_b=res_b)
+        return x_tilde, e_tilde

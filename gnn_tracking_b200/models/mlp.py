@@ -1,0 +1,141 @@
+"""``MLP`` / ``ResFCNN`` with the reference's constructor arguments and state_dict
+names (reference models/mlp.py:18-120), evaluated by the fused row-MLP kernel."""
+from __future__ import annotations
+
+import math
+from typing import Sequence
+
+import torch
+from torch import Tensor, nn
+
+from .. import ops
+from ..ops import ACT_NONE, ACT_RELU, Block, PackedMLP
+
+
+class PackedCache:
+    """Packed copies of a chain of ``nn.Linear`` layers, re-packed when a weight
+    changes (optimizer step, ``load_state_dict``, ``.to(device)``)."""
+
+    def __init__(self):
+        self._key = None
+        self._packed: list[PackedMLP] = []
+
+    def get(self, linears: Sequence[nn.Linear], impl: int | None = None) -> list[PackedMLP]:
+        impl = ops.default_impl() if impl is None else impl
+        key = (impl,) + tuple((p.data_ptr(), p._version) for lin in linears for p in lin.parameters())
+        if key != self._key:
+            groups = [list(linears[i:i + 3]) for i in range(0, len(linears), 3)]
+            self._packed = [ops.pack_linears([l.weight for l in g], [l.bias for l in g], impl) for g in groups]
+            self._key = key
+        return self._packed
+
+
+def run_linears(cache: PackedCache, linears: Sequence[nn.Linear], blocks: Sequence[Block], n_rows: int,
+                *, final_act: int = ACT_NONE, **epilogue) -> Tensor | None:
+    """Linear/ReLU chain over concatenated column blocks; <= 3 Linear layers per
+    fused launch, longer chains are split with the intermediate kept in HBM."""
+    if torch.is_grad_enabled() and (any(b.tensor.requires_grad for b in blocks)
+                                    or any(p.requires_grad for lin in linears for p in lin.parameters())):
+        raise NotImplementedError(
+            "gnn_tracking_b200 kernels are forward-only in this build: call the model under torch.no_grad() "
+            "(there is no silent autograd fallback)")
+    packed = cache.get(linears)
+    cur = list(blocks)
+    for i, p in enumerate(packed):
+        if i + 1 < len(packed):
+            h = ops.fused_mlp(cur, n_rows, p, final_act=ACT_RELU)
+            cur = [Block(h)]
+        else:
+            return ops.fused_mlp(cur, n_rows, p, final_act=final_act, **epilogue)
+    raise AssertionError("unreachable")
+
+
+class MLP(nn.Module):
+    def __init__(self, input_size: int, output_size: int, hidden_dim: int | None, L: int = 3, *,
+                 bias: bool = True, include_last_activation: bool = False):
+        """Linear/ReLU chain: 1 input layer, ``L - 2`` hidden layers, 1 output layer.
+        ``hidden_dim=None`` picks ``max(input_size, output_size)`` (reference
+        mlp.py:42-43).  Parameters live at ``layers.{0,2,4,...}`` as in the reference."""
+        super().__init__()
+        if hidden_dim is None:
+            hidden_dim = max(input_size, output_size)
+        widths = [input_size] + [hidden_dim] * max(L - 1, 1) + [output_size]
+        mods: list[nn.Module] = []
+        for i in range(len(widths) - 1):
+            if i:
+                mods.append(nn.ReLU())
+            mods.append(nn.Linear(widths[i], widths[i + 1], bias=bias))
+        if include_last_activation:
+            mods.append(nn.ReLU())
+        self.layers = nn.ModuleList(mods)
+        self._last_act = include_last_activation
+        self._cache = PackedCache()
+
+    @property
+    def linears(self) -> list[nn.Linear]:
+        return [m for m in self.layers if isinstance(m, nn.Linear)]
+
+    @property
+    def in_features(self) -> int:
+        return self.linears[0].in_features
+
+    @property
+    def out_features(self) -> int:
+        return self.linears[-1].out_features
+
+    def reset_parameters(self) -> None:
+        for m in self.layers:
+            if hasattr(m, "reset_parameters"):
+                m.reset_parameters()
+
+    def forward_blocks(self, blocks: Sequence[Block], n_rows: int, *, final_act: int | None = None,
+                       **epilogue) -> Tensor | None:
+        if final_act is None:
+            final_act = ACT_RELU if self._last_act else ACT_NONE
+        return run_linears(self._cache, self.linears, blocks, n_rows, final_act=final_act, **epilogue)
+
+    def forward(self, x: Tensor) -> Tensor:
+        return self.forward_blocks([Block(x)], x.size(0))
+
+
+class ResFCNN(nn.Module):
+    def __init__(self, *, in_dim: int, hidden_dim: int, out_dim: int, depth: int, alpha: float = 0.6,
+                 bias: bool = True):
+        """L2-normalise rows -> encoder -> (depth-1) residual hidden layers
+        ``sqrt(a) x + sqrt(1-a) layer(relu(x))`` -> decoder(relu(.)); parameter names
+        ``_encoder``, ``_layers.{i}``, ``_decoder`` and the normal initialisation of
+        reference mlp.py:95-113."""
+        super().__init__()
+        if depth < 1:
+            raise ValueError("Depth must be at least 1")
+        self._encoder = nn.Linear(in_dim, hidden_dim, bias=bias)
+        self._decoder = nn.Linear(hidden_dim, out_dim, bias=bias)
+        self._layers = nn.ModuleList([nn.Linear(hidden_dim, hidden_dim, bias=bias) for _ in range(depth - 1)])
+        self._init(self._encoder, 1 / in_dim)
+        for lay in self._layers:
+            self._init(lay, 2 / hidden_dim)
+        self._init(self._decoder, 2 / hidden_dim)
+        self._alpha = alpha
+        self._cache = PackedCache()
+        self._layer_caches = [PackedCache() for _ in range(depth)]
+
+    @staticmethod
+    def _init(layer: nn.Linear, var: float) -> None:
+        layer.reset_parameters()  # keeps the RNG stream aligned with the reference (mlp.py:108-111)
+        for p in layer.parameters():
+            nn.init.normal_(p.data, mean=0.0, std=math.sqrt(var))
+
+    def forward_blocks(self, blocks: Sequence[Block], n_rows: int, *, final_act: int = ACT_NONE) -> Tensor:
+        inv = ops.rows_inv_l2norm(blocks, n_rows, 1e-12)
+        if len(self._layers) == 0:
+            p = self._cache.get([self._encoder, self._decoder])[0]
+            return ops.fused_mlp(blocks, n_rows, p, row_scale=inv, final_act=final_act)
+        x = ops.fused_mlp(blocks, n_rows, self._layer_caches[0].get([self._encoder])[0], row_scale=inv)
+        a, b = math.sqrt(self._alpha), math.sqrt(1 - self._alpha)
+        for lay, cache in zip(self._layers, self._layer_caches[1:]):
+            x = ops.fused_mlp([Block(x, relu=True)], n_rows, cache.get([lay])[0], res=x, res_a=a, res_b=b)
+        return ops.fused_mlp([Block(x, relu=True)], n_rows, self._cache.get([self._decoder])[0],
+                             final_act=final_act)
+
+    def forward(self, x: Tensor, **ignore) -> Tensor:
+        return self.forward_blocks([Block(x)], x.size(0))

@@ -1,0 +1,146 @@
+"""Residual stacks of interaction networks (reference models/resin.py:45-295) over
+one shared graph plan.  The residual combination ``sqrt(a) x + sqrt(1-a) dx``
+(resin.py:17-42) and the ReLU in front of every layer but the first
+(resin.py:104-105) are fused into the layer kernels (epilogue / on-load
+activation), so a layer is exactly two launches and no elementwise pass."""
+from __future__ import annotations
+
+import math
+from abc import ABC, abstractmethod
+from itertools import pairwise
+
+from torch import Tensor, nn
+
+from .._hparams import HyperparametersMixin
+from ..plan import GraphPlan, get_plan
+from .interaction_network import InteractionNetwork
+
+
+def _res_coeffs(alpha: float) -> tuple[float, float] | None:
+    """None when the residual is skipped (alpha ~ 0, resin.py:38-39)."""
+    if math.isclose(alpha, 0.0):
+        return None
+    return math.sqrt(alpha), math.sqrt(1.0 - alpha)
+
+
+class ResidualNetwork(ABC, nn.Module):
+    def __init__(self, layers: list[nn.Module], *, alpha: float = 0.5, collect_hidden_edge_embeds: bool = False):
+        super().__init__()
+        self.layers = nn.ModuleList(layers)
+        self._alpha = alpha
+        self._collect_hidden_edge_embeds = collect_hidden_edge_embeds
+
+    def forward(self, x: Tensor, edge_index: Tensor, edge_attr: Tensor) -> tuple[Tensor, Tensor, list[Tensor] | None]:
+        return self._forward(x, get_plan(edge_index, x.size(0)), edge_attr)
+
+    def forward_planned(self, x: Tensor, plan: GraphPlan, edge_attr: Tensor):
+        return self._forward(x, plan, edge_attr)
+
+    def _layer(self, i: int, x: Tensor, plan: GraphPlan, e: Tensor, *, first: bool, residue: Tensor | None):
+        """IN layer i on (act(x), act(e)) with the residual onto the un-activated
+        ``residue`` fused in; act = identity for the very first layer, else ReLU."""
+        co = _res_coeffs(self._alpha) if residue is not None else None
+        kw = {} if co is None else dict(res=residue, res_a=co[0], res_b=co[1])
+        return self.layers[i].forward_planned(x, plan, e, relu_x=not first, relu_e=not first, **kw)
+
+    @abstractmethod
+    def _forward(self, x: Tensor, plan: GraphPlan, edge_attr: Tensor):
+        ...
+
+
+class Skip1ResidualNetwork(ResidualNetwork):
+    """Every layer has a residual connection to its input (resin.py:99-114)."""
+
+    def _forward(self, x, plan, edge_attr):
+        edge_attrs = [edge_attr] if self._collect_hidden_edge_embeds else None
+        for i in range(len(self.layers)):
+            x, edge_attr = self._layer(i, x, plan, edge_attr, first=i == 0, residue=x)
+            if edge_attrs is not None:
+                edge_attrs.append(edge_attr)
+        return x, edge_attr, edge_attrs
+
+
+class Skip2ResidualNetwork(ResidualNetwork):
+    """Blocks of two layers with a residual connection around each block
+    (resin.py:153-175).  The reference iterates ``pairwise(range(L))`` -- overlapping
+    pairs -- which is reproduced literally."""
+
+    def __init__(self, layers: list[nn.Module], *, node_dim: int, edge_dim: int, add_bn: bool = False, **kwargs):
+        if len(layers) % 2 != 0:
+            raise ValueError("Only even number of layers allowed at the moment")
+        if add_bn:
+            raise NotImplementedError("Skip2ResidualNetwork(add_bn=True): batch norm is not on the B200 path")
+        super().__init__(layers=layers, **kwargs)
+        # parameter-free placeholders keep the reference's module tree
+        self._node_batch_norms = nn.ModuleList([nn.Identity() for _ in layers])
+        self._edge_batch_norms = nn.ModuleList([nn.Identity() for _ in layers])
+
+    def _forward(self, x, plan, edge_attr):
+        edge_attrs = [edge_attr] if self._collect_hidden_edge_embeds else None
+        for i0, i1 in pairwise(range(len(self.layers))):
+            hx, he = self._layer(i0, x, plan, edge_attr, first=i0 == 0, residue=None)
+            x, edge_attr = self._layer(i1, hx, plan, he, first=False, residue=x)
+            if edge_attrs is not None:
+                edge_attrs.append(edge_attr)
+        return x, edge_attr, edge_attrs
+
+
+class SkipTopResidualNetwork(ResidualNetwork):
+    """Residual connections to one fixed early layer output (resin.py:197-216)."""
+
+    def __init__(self, layers: list[nn.Module], connect_to: int = 1, **kwargs):
+        assert connect_to <= len(layers)
+        super().__init__(layers=layers, **kwargs)
+        self._residual_layer = connect_to
+
+    def _forward(self, x, plan, edge_attr):
+        edge_attrs = [edge_attr] if self._collect_hidden_edge_embeds else None
+        x_residue = None
+        for i in range(len(self.layers)):
+            if i == self._residual_layer:
+                x_residue = x
+            x, edge_attr = self._layer(i, x, plan, edge_attr, first=i == 0, residue=x_residue)
+            if edge_attrs is not None:
+                edge_attrs.append(edge_attr)
+        return x, edge_attr, edge_attrs
+
+
+RESIDUAL_NETWORKS_BY_NAME = {
+    "skip1": Skip1ResidualNetwork,
+    "skip2": Skip2ResidualNetwork,
+    "skip_top": SkipTopResidualNetwork,
+}
+
+
+class ResIN(nn.Module, HyperparametersMixin):
+    def __init__(self, *, node_dim: int, edge_dim: int, object_hidden_dim=40, relational_hidden_dim=40,
+                 alpha: float = 0.5, n_layers=1, residual_type: str = "skip1",
+                 residual_kwargs: dict | None = None):
+        """``n_layers`` identical interaction networks inside the residual network named
+        by ``residual_type`` (reference resin.py:226-281; parameters under
+        ``network.layers.{i}.*``)."""
+        super().__init__()
+        self.save_hyperparameters()
+        residual_kwargs = dict(residual_kwargs or {})
+        layers = [InteractionNetwork(node_indim=node_dim, edge_indim=edge_dim, node_outdim=node_dim,
+                                     edge_outdim=edge_dim, node_hidden_dim=object_hidden_dim,
+                                     edge_hidden_dim=relational_hidden_dim) for _ in range(n_layers)]
+        if residual_type == "skip2":
+            residual_kwargs["node_dim"] = node_dim
+            residual_kwargs["edge_dim"] = edge_dim
+        self.network = RESIDUAL_NETWORKS_BY_NAME[residual_type](layers, alpha=alpha, **residual_kwargs)
+        self.node_dim = node_dim
+        self.edge_dim = edge_dim
+        self._residual_type = residual_type
+
+    @property
+    def concat_edge_embeddings_length(self) -> int:
+        """Width of the concatenated per-layer edge embeddings (resin.py:283-290)."""
+        n = len(self.network.layers)
+        return self.edge_dim * ((n // 2 if self._residual_type == "skip2" else n) + 1)
+
+    def forward(self, x: Tensor, edge_index: Tensor, edge_attr: Tensor):
+        return self.network.forward(x, edge_index, edge_attr)
+
+    def forward_planned(self, x: Tensor, plan: GraphPlan, edge_attr: Tensor):
+        return self.network.forward_planned(x, plan, edge_attr)

@@ -1,0 +1,187 @@
+"""Host-side wrappers of the C ABI: tensors in, tensors out.  PyTorch is used for
+device memory and streams only; all arithmetic happens in ``libgtb200.so``."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import Sequence
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import (ACT_NONE, ACT_RELU, ACT_SIGMOID_AFFINE, IMPL_AUTO, IMPL_FFMA, IMPL_TCGEN05, GtbError,
+                   MlpDesc, Src, check, lib)
+
+__all__ = ["ACT_NONE", "ACT_RELU", "ACT_SIGMOID_AFFINE", "IMPL_AUTO", "IMPL_FFMA", "IMPL_TCGEN05", "Block",
+           "PackedMLP", "fused_mlp", "pack_linears", "require_cuda", "default_impl", "launch_count"]
+
+_LAUNCHES = 0  # kernels launched through the C ABI by this process (bench.py reports it)
+
+
+def launch_count() -> int:
+    return _LAUNCHES
+
+
+def _count(n: int) -> None:
+    global _LAUNCHES
+    _LAUNCHES += n
+
+
+def require_cuda(*tensors: Tensor) -> torch.device:
+    """The product path is CUDA sm_100a only: there is no CPU / eager fallback."""
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError(
+                "gnn_tracking_b200 runs on a CUDA sm_100a (B200) device only; got a tensor on "
+                f"{t.device}.  There is no CPU fallback (use the reference package on CPU).")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"tensors on different devices: {dev} and {t.device}")
+    if dev is None:
+        raise RuntimeError("no tensor given")
+    _lib.require_device(dev.index if dev.index is not None else torch.cuda.current_device())
+    return dev
+
+
+def stream_ptr(dev: torch.device) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def default_impl() -> int:
+    """GTB_IMPL_AUTO unless ``GTB_IMPL`` = ffma | tcgen05 forces one."""
+    v = os.environ.get("GTB_IMPL", "auto").lower()
+    return {"auto": IMPL_AUTO, "ffma": IMPL_FFMA, "tcgen05": IMPL_TCGEN05}[v]
+
+
+def _f32c(t: Tensor) -> Tensor:
+    if t.dtype != torch.float32:
+        raise TypeError(f"gtb200 kernels are fp32; got {t.dtype}")
+    if t.dim() == 1:
+        t = t.unsqueeze(1)
+    if t.stride(-1) != 1 and t.size(-1) > 1:
+        t = t.contiguous()
+    return t
+
+
+@dataclass
+class Block:
+    """One column block of a concatenated MLP input: ``act(tensor[index])``."""
+    tensor: Tensor
+    index: Tensor | None = None  # int32 row index per output row
+    relu: bool = False
+
+
+@dataclass
+class PackedMLP:
+    buf: Tensor
+    dims: tuple[int, ...]
+    impl: int
+
+    @property
+    def n_layers(self) -> int:
+        return len(self.dims) - 1
+
+
+def resolve_impl(dims: Sequence[int], impl: int) -> int:
+    if impl != IMPL_AUTO:
+        return impl
+    arr = (C.c_int32 * len(dims))(*dims)
+    return IMPL_TCGEN05 if lib().gtb_mlp_packed_bytes(len(dims) - 1, arr, IMPL_TCGEN05) > 0 else IMPL_FFMA
+
+
+def pack_linears(weights: Sequence[Tensor], biases: Sequence[Tensor | None], impl: int = IMPL_AUTO) -> PackedMLP:
+    """Repack <= 3 ``nn.Linear`` layers ([out, in] weights) for the fused tiles."""
+    dev = require_cuda(*weights)
+    n = len(weights)
+    if not 1 <= n <= _lib.GTB_MAX_LAYERS:
+        raise ValueError(f"a fused MLP call takes 1..{_lib.GTB_MAX_LAYERS} Linear layers, got {n}")
+    dims = [weights[0].size(1)] + [w.size(0) for w in weights]
+    for i, w in enumerate(weights):
+        if w.size(1) != dims[i]:
+            raise ValueError("Linear layers do not chain")
+    impl = resolve_impl(dims, impl)
+    dims_c = (C.c_int32 * (n + 1))(*dims)
+    nbytes = lib().gtb_mlp_packed_bytes(n, dims_c, impl)
+    if nbytes == 0:
+        raise GtbError(-2, f"MLP widths {dims} are not supported by impl {impl}")
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    ws = [w.detach().to(torch.float32).contiguous() for w in weights]
+    bs = [None if b is None else b.detach().to(torch.float32).contiguous() for b in biases]
+    wp = (C.c_void_p * n)(*[w.data_ptr() for w in ws])
+    bp = (C.c_void_p * n)(*[(b.data_ptr() if b is not None else None) for b in bs])
+    check(lib().gtb_mlp_pack(n, dims_c, wp, bp, impl, buf.data_ptr(), stream_ptr(dev)))
+    _count(n)
+    return PackedMLP(buf, tuple(dims), impl)
+
+
+def _idx(t: Tensor | None) -> int | None:
+    if t is None:
+        return None
+    if t.dtype != torch.int32 or not t.is_contiguous():
+        raise TypeError("row indices must be contiguous int32")
+    return t.data_ptr()
+
+
+def fused_mlp(blocks: Sequence[Block], n_rows: int, packed: PackedMLP, *, final_act: int = ACT_NONE,
+              act_eps: float = 0.0, res: Tensor | None = None, res_a: float = 0.0, res_b: float = 1.0,
+              row_scale: Tensor | None = None, out_scale: Tensor | None = None, out: Tensor | None = None, out_index: Tensor | None = None,
+              want_out: bool = True, aggr: Tensor | None = None, seg_id: Tensor | None = None,
+              rowptr: Tensor | None = None, out_rows: int | None = None) -> Tensor | None:
+    """``out[orow(r)] = epilogue(MLP(cat_s act_s(block_s[irow_s(r)])))`` -- see
+    ``gtb_fused_mlp_f32`` in include/gtb200.h."""
+    tensors = [_f32c(b.tensor) for b in blocks]
+    dev = require_cuda(*tensors)
+    d = MlpDesc()
+    d.n_rows = n_rows
+    d.n_srcs = len(blocks)
+    d.n_layers = packed.n_layers
+    if len(blocks) > _lib.GTB_MAX_SRCS:
+        raise ValueError(f"at most {_lib.GTB_MAX_SRCS} column blocks")
+    for i, (b, t) in enumerate(zip(blocks, tensors)):
+        d.srcs[i] = Src(t.data_ptr(), _idx(b.index), t.size(1), t.stride(0), int(b.relu), 0)
+    for i, v in enumerate(packed.dims):
+        d.dims[i] = v
+    d.packed = packed.buf.data_ptr()
+    d.impl = packed.impl
+    d.final_act = final_act
+    d.act_eps = act_eps
+    n_out = packed.dims[-1]
+    keep = [tensors]
+    if res is not None:
+        res = _f32c(res)
+        d.res, d.res_ld, d.res_a, d.res_b = res.data_ptr(), res.stride(0), res_a, res_b
+    d.res_b = res_b
+    if row_scale is not None:
+        d.row_scale = row_scale.data_ptr()
+    if out_scale is not None:
+        d.out_scale = out_scale.data_ptr()
+    if want_out:
+        if out is None:
+            out = torch.empty((n_rows if out_rows is None else out_rows, n_out), dtype=torch.float32, device=dev)
+        d.out, d.out_ld = out.data_ptr(), out.stride(0)
+        d.out_index = _idx(out_index)
+    if aggr is not None:
+        d.aggr, d.aggr_ld = aggr.data_ptr(), aggr.stride(0)
+        d.seg_id, d.rowptr = _idx(seg_id), _idx(rowptr)
+    check(lib().gtb_fused_mlp_f32(C.byref(d), stream_ptr(dev)))
+    _count(1)
+    del keep
+    return out if want_out else None
+
+
+def rows_inv_l2norm(blocks: Sequence[Block], n_rows: int, eps: float = 1e-12) -> Tensor:
+    tensors = [_f32c(b.tensor) for b in blocks]
+    dev = require_cuda(*tensors)
+    arr = (Src * len(blocks))()
+    for i, (b, t) in enumerate(zip(blocks, tensors)):
+        arr[i] = Src(t.data_ptr(), _idx(b.index), t.size(1), t.stride(0), int(b.relu), 0)
+    out = torch.empty(n_rows, dtype=torch.float32, device=dev)
+    check(lib().gtb_rows_inv_l2norm_f32(arr, len(blocks), n_rows, eps, out.data_ptr(), stream_ptr(dev)))
+    _count(1)
+    return out

@@ -1,0 +1,230 @@
+/* gtb200 -- C ABI of the B200-native Interaction-Network hot path.
+ *
+ * Plain C, no torch types: raw DEVICE pointers, sizes, a cudaStream_t passed as
+ * void*.  The caller owns every buffer (inputs, outputs, workspace); no entry
+ * point allocates device memory or synchronises the stream.  Every function
+ * returns 0 on success or a negative GTB_ERR_* code; gtb_last_error() gives the
+ * thread-local message.
+ *
+ * Each entry point cites the reference code it replaces.  Citations are
+ * relative to /root/reference/src/gnn_tracking (gnn-tracking/gnn_tracking @ 23.12.1).
+ *
+ * The reference has no FFI of its own (pure Python over torch / PyG); the
+ * binding a maintainer would add is the ctypes stub shown in INTEGRATION.md and
+ * implemented in gnn_tracking_b200/_lib.py.
+ */
+#ifndef GTB200_H
+#define GTB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GTB_OK                    0
+#define GTB_ERR_BAD_ARG          -1
+#define GTB_ERR_UNSUPPORTED_DIM  -2
+#define GTB_ERR_WORKSPACE        -3
+#define GTB_ERR_CUDA             -4
+#define GTB_ERR_ARCH             -5
+
+#define GTB_MAX_SRCS   16   /* column blocks of a concatenated MLP input          */
+#define GTB_MAX_LAYERS 3    /* Linear layers of an MLP on the path (mlp.py:44-51) */
+#define GTB_MAX_WIDTH  128  /* max Linear output width of the FFMA path           */
+
+/* final activation of a fused MLP */
+#define GTB_ACT_NONE           0
+#define GTB_ACT_RELU           1
+#define GTB_ACT_SIGMOID_AFFINE 2 /* eps + (1-2 eps) * sigmoid(v): edge_classifier.py:115-117,
+                                    track_condensation_networks.py:284-288 */
+
+/* which implementation a fused-MLP call must use */
+#define GTB_IMPL_AUTO   0
+#define GTB_IMPL_FFMA   1 /* fp32 CUDA-core tiles (any width <= GTB_MAX_WIDTH)             */
+#define GTB_IMPL_TCGEN05 2 /* tcgen05 3xTF32 tiles (widths multiple of 16)  */
+
+int         gtb_version(void);
+const char* gtb_last_error(void);
+/* 0 when `device` is a compute-capability 10.x part; GTB_ERR_ARCH otherwise. */
+int gtb_arch_ok(int device);
+
+/* ------------------------------------------------------------------ graph plan
+ * Destination-sorted view of edge_index, built once per graph and shared by all
+ * layers.  Replaces what PyG's MessagePassing.propagate re-derives on every call
+ * (models/interaction_network.py:67 -> index_select on edge_index[0|1] and
+ * scatter_add_ over edge_index[1]).
+ *
+ *  edge_index : int64 [2, E] row-major as delivered by the reference API
+ *               (row 0 = source j, row 1 = target i).
+ *  perm       : int32 [E]   stable argsort of edge_index[1]  (bit-exact contract)
+ *  rowptr     : int32 [N+1] CSR offsets of the sorted list
+ *  src_sorted : int32 [E]   edge_index[0][perm]
+ *  dst_sorted : int32 [E]   edge_index[1][perm]
+ *  status     : int32 [1]   set to nonzero if an index is outside [0, N)
+ */
+size_t gtb_plan_workspace_bytes(int64_t n_nodes, int64_t n_edges);
+int gtb_plan_build(const int64_t* edge_index, int64_t n_nodes, int64_t n_edges,
+                   int32_t* perm, int32_t* rowptr, int32_t* src_sorted, int32_t* dst_sorted,
+                   int32_t* status, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Plan of an edge sub-graph (track_condensation_networks.py:251-252,
+ * Data.edge_subgraph(W > thr)): a dst-sorted list stays sorted under filtering, so
+ * this is a stream compaction of the parent plan.  keep: uint8 [E] in ORIGINAL
+ * edge order.  new_id: int32 [E] scratch, receives the position of every kept edge
+ * in the compacted original order (-1 for dropped); kept_ids: int32 [E], the
+ * inverse map (original id of compacted edge j) in its first n_kept entries.
+ * n_kept_out: int32 [1]. */
+size_t gtb_plan_filter_workspace_bytes(int64_t n_nodes, int64_t n_edges);
+int gtb_plan_filter(const uint8_t* keep, int64_t n_nodes, int64_t n_edges,
+                    const int32_t* perm, const int32_t* src_sorted, const int32_t* dst_sorted,
+                    int32_t* new_id, int32_t* kept_ids, int32_t* perm_out, int32_t* rowptr_out,
+                    int32_t* src_sorted_out, int32_t* dst_sorted_out, int32_t* n_kept_out,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------ packed MLP weights
+ * An MLP of the path (models/mlp.py:18-62: Linear/ReLU chain, nn.Linear weights
+ * [out, in] row-major, optional bias) is repacked once per weight version into the
+ * K-major, zero-padded layout the tiles consume.  `impl` selects the layout
+ * (GTB_IMPL_FFMA or GTB_IMPL_TCGEN05).  dims = {K0, N0, N1, N2} (true widths). */
+size_t gtb_mlp_packed_bytes(int n_layers, const int32_t* dims, int impl);
+int gtb_mlp_pack(int n_layers, const int32_t* dims, const float* const* weights,
+                 const float* const* biases /* entries may be NULL */, int impl,
+                 void* packed, void* stream);
+
+/* --------------------------------------------------------------- fused row MLP
+ * out[orow(r), :] = epilogue( MLP( cat_s( act_s( src_s[irow_s(r), 0:width_s] ) ) ) )
+ * for r in [0, n_rows): the one building block behind every dense op of the path:
+ *   - relational model  interaction_network.py:75-89  (3 gathered column blocks)
+ *   - object model      interaction_network.py:92-103 (+ residual, resin.py:17-42)
+ *   - encoders          edge_classifier.py:102-103, track_condensation_networks.py:279-280
+ *   - W head            edge_classifier.py:108-117
+ *   - beta / H heads    track_condensation_networks.py:284-298
+ * The concatenation is never materialised. */
+typedef struct {
+  const float*   ptr;    /* [*, ld] fp32 rows                                           */
+  const int32_t* index;  /* row gather index per output row, or NULL for identity        */
+  int32_t        width;  /* columns taken (from column 0)                                */
+  int32_t        ld;     /* row stride in elements                                       */
+  int32_t        relu;   /* 1: relu on load (resin.py:104-105: layers > 0 see relu(x))   */
+  int32_t        reserved;
+} gtb_src_t;
+
+typedef struct {
+  int64_t   n_rows;
+  int32_t   n_srcs;
+  int32_t   n_layers;               /* 1..GTB_MAX_LAYERS                                  */
+  gtb_src_t srcs[GTB_MAX_SRCS];
+  int32_t   dims[GTB_MAX_LAYERS + 1]; /* K0 (= sum of src widths), N0, N1, N2              */
+  const void* packed;               /* from gtb_mlp_pack (same impl)                      */
+  int32_t   impl;                   /* GTB_IMPL_*                                         */
+  int32_t   final_act;              /* GTB_ACT_*                                          */
+  float     act_eps;
+  /* out = res_b * value (+ res_a * res[r, :] when res != NULL), then * (*out_scale) when
+   * out_scale != NULL.  sqconvex_combination resin.py:17-42: res_a = sqrt(alpha),
+   * res_b = sqrt(1-alpha); out_scale: the learnable _latent_normalization scalar kept on
+   * the device (track_condensation_networks.py:298).  res_b must be 1 for "no scaling". */
+  float     res_a, res_b;
+  int32_t   res_ld;
+  const float* res;
+  /* optional per-row scale applied to every source block on load, used for the L2 row
+   * normalisation in front of ResFCNN (mlp.py:115-116); NULL = none */
+  const float* row_scale;
+  const float* out_scale;
+  /* output rows (out may be NULL when only the aggregate is wanted) */
+  float*    out;
+  const int32_t* out_index;         /* row scatter index or NULL                          */
+  int32_t   out_ld;
+  /* optional per-destination sum of the output rows (PyG SumAggregation,
+   * interaction_network.py:22,36): rows must be ordered so that seg_id is
+   * non-decreasing (the plan's dst_sorted); aggr [n_segments, aggr_ld] must be
+   * zero-filled by the caller. */
+  int32_t   aggr_ld;
+  float*    aggr;
+  const int32_t* seg_id;
+  const int32_t* rowptr;
+} gtb_mlp_desc_t;
+
+int gtb_fused_mlp_f32(const gtb_mlp_desc_t* desc, void* stream);
+
+/* ------------------------------------------------------------- IN layer wrappers
+ * One Interaction-Network layer (interaction_network.py:54-103) on a planned graph.
+ * edge_attr / e_tilde stay in the caller's edge order; kernels walk them in
+ * dst-sorted order through `perm`.
+ *   gtb_in_edge_forward_f32 : e_tilde = MLP_rel(cat[x[dst], x[src], edge_attr]) and
+ *                             aggr[i] = sum_{dst(e)=i} e_tilde[e]      (aggr zeroed inside)
+ *   gtb_in_node_forward_f32 : x_out = res_a * x + res_b * MLP_obj(cat[act(x), aggr])
+ *                             (res_a = 0, res_b = 1 for a bare IN layer)
+ */
+int gtb_in_edge_forward_f32(const float* x, int32_t x_ld, int32_t relu_x,
+                            const float* edge_attr, int32_t e_ld, int32_t relu_e,
+                            int64_t n_nodes, int64_t n_edges,
+                            const int32_t* perm, const int32_t* rowptr,
+                            const int32_t* src_sorted, const int32_t* dst_sorted,
+                            int32_t node_dim, int32_t edge_dim, int32_t hidden, int32_t edge_outdim,
+                            const void* packed_rel, int impl,
+                            float* e_tilde, int32_t eo_ld, float* aggr, void* stream);
+int gtb_in_node_forward_f32(const float* x, int32_t x_ld, int32_t relu_x,
+                            const float* aggr, int64_t n_nodes,
+                            int32_t node_dim, int32_t aggr_dim, int32_t hidden, int32_t node_outdim,
+                            const void* packed_obj, int impl,
+                            float res_a, float res_b, const float* res, int32_t res_ld,
+                            float* x_out, int32_t xo_ld, void* stream);
+
+/* ------------------------------------------------------------------- EC losses
+ * metrics/losses/ec.py.  y_true may be NULL-free uint8 or float labels:
+ *   label_kind 0: float [E], 1: uint8/bool [E].
+ * If pt != NULL, labels are falsified: y &= pt[src[e]] > pt_thld (ec.py:71-92;
+ * only edge_index[0] is looked at).  src: int64 [E] (edge_index row 0).
+ * out: float [2] = {sum, n}; the mean is sum / n (finished on the host side of the
+ * boundary so that the kernel stays allocation- and sync-free).  out must be zeroed.
+ *   mode 0: BCE (ec.py:116-121, log clamped at -100 as torch does)
+ *   mode 1: focal (ec.py:12-29) with alpha, gamma, scalar pos_weight
+ *   mode 2: haughty focal (ec.py:153-178): falsified labels are pos_weight,
+ *           the raw labels the target. */
+int gtb_ec_loss_f32(const float* w, const void* y, int label_kind, int64_t n_edges,
+                    const int64_t* src, const float* pt, float pt_thld,
+                    int mode, float alpha, float gamma, float pos_weight,
+                    double* out /* [2] */, void* stream);
+
+/* ------------------------------------------------------- condensation loss (tiger)
+ * metrics/losses/oc.py:251-347 without the N x K planes.
+ *   beta [N], x [N, d] (ld = d), object_id int64 [N], object_mask uint8 [N]
+ *   (object_mask from get_good_node_mask_tensors, utils/graph_masks.py:19-28).
+ * Step 1 (host side picks K = #unique masked ids; ids are compacted on the device):
+ *   gtb_oc_prepare   : sorts / uniques the masked object ids -> uniq [K<=N] int64,
+ *                      obj_slot int32 [N] (slot of the hit's object or -1), n_uniq [1]
+ *   gtb_oc_alphas    : alpha_k = argmax_j q_j [id_j == uniq_k]  (first index on ties)
+ *   gtb_oc_potentials: the four sums; out double[8] =
+ *                      {V_att_sum, V_rep_sum, coward_sum, noise_sum, n_noise, n_hits_oi, n_rep, K}
+ */
+size_t gtb_oc_workspace_bytes(int64_t n_nodes);
+int gtb_oc_prepare(const int64_t* object_id, const uint8_t* object_mask, int64_t n_nodes,
+                   int64_t* uniq, int32_t* obj_slot, int32_t* n_uniq,
+                   void* workspace, size_t workspace_bytes, void* stream);
+int gtb_oc_alphas(const float* beta, const int32_t* obj_slot, int64_t n_nodes, float q_min,
+                  int32_t k, unsigned long long* packed_scratch /* [k] */, int32_t* alphas /* [k] */,
+                  void* stream);
+int gtb_oc_potentials(const float* beta, const float* x, int32_t d, const int64_t* object_id,
+                      const uint8_t* object_mask, const int32_t* obj_slot, int64_t n_nodes,
+                      const int32_t* alphas, int32_t k, float q_min, int64_t noise_threshold,
+                      double* out /* [8], zeroed by caller */, void* stream);
+
+/* inv_norm[r] = 1 / max(||cat_s src_s[r]||_2, eps): torch.nn.functional.normalize(x, p=2, dim=1,
+ * eps) as used by ResFCNN.forward (mlp.py:115-116); feed the result as row_scale. */
+int gtb_rows_inv_l2norm_f32(const gtb_src_t* srcs, int32_t n_srcs, int64_t n_rows, float eps,
+                            float* inv_norm, void* stream);
+
+/* --------------------------------------------------------------------- row ops
+ * Row gather / scatter used by the halo exchange of the node-partitioned
+ * multi-GPU path (no reference equivalent: the reference is single-process). */
+int gtb_rows_gather_f32(const float* src, int32_t src_ld, const int32_t* index, int64_t n_rows,
+                        int32_t width, float* dst, int32_t dst_ld, void* stream);
+int gtb_rows_scatter_f32(const float* src, int32_t src_ld, const int32_t* index, int64_t n_rows,
+                         int32_t width, float* dst, int32_t dst_ld, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GTB200_H */

@@ -1,0 +1,97 @@
+"""Host-side checks that need no GPU: the C-ABI library loads and exports every symbol
+include/gtb200.h declares, the modules keep the reference's constructor / hparams /
+state_dict contract, and CPU tensors are refused (no fallback)."""
+import re
+from pathlib import Path
+
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_library_exports_every_declared_symbol():
+    from gnn_tracking_b200 import _lib
+    header = (ROOT / "include" / "gtb200.h").read_text()
+    declared = set(re.findall(r"\b(gtb_[a-z0-9_]+)\s*\(", header))
+    declared -= {"gtb_src_t", "gtb_mlp_desc_t"}
+    assert declared, "no declarations found"
+    handle = _lib.lib()
+    for name in sorted(declared):
+        assert hasattr(handle, name), f"{name} declared in gtb200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert handle.gtb_version() >= 100
+
+
+def test_desc_struct_matches_header_layout():
+    from gnn_tracking_b200 import _lib
+    assert _lib.C.sizeof(_lib.Src) == 32
+    assert _lib.MlpDesc.srcs.offset == 16
+    assert _lib.MlpDesc.dims.offset == 16 + 32 * 16
+    assert _lib.MlpDesc.packed.offset == 544
+    assert _lib.C.sizeof(_lib.MlpDesc) == 648
+
+
+def test_packed_bytes_host_logic():
+    from gnn_tracking_b200 import _lib
+    import ctypes as C
+    dims = (C.c_int32 * 4)(192, 64, 64, 64)
+    n = _lib.lib().gtb_mlp_packed_bytes(3, dims, _lib.IMPL_FFMA)
+    assert n == 4 * (192 * 64 + 64 + 64 * 64 + 64 + 64 * 64 + 64)
+    dims = (C.c_int32 * 4)(14, 64, 64, 4)  # narrow last layer padded to 8 columns, K0 to 32
+    n = _lib.lib().gtb_mlp_packed_bytes(3, dims, _lib.IMPL_FFMA)
+    assert n == 4 * (32 * 64 + 64 + 64 * 64 + 64 + 64 * 8 + 8)
+    dims = (C.c_int32 * 4)(14, 300, 64, 4)
+    assert _lib.lib().gtb_mlp_packed_bytes(3, dims, _lib.IMPL_FFMA) == 0  # unsupported width
+
+
+@pytest.mark.parametrize("kind", ["in", "resin", "ec", "tcn"])
+def test_state_dict_and_hparams_contract(kind, golden_models):
+    """Reference checkpoints load with strict=True: same parameter names and shapes."""
+    from gnn_tracking_b200.models.edge_classifier import ECForGraphTCN
+    from gnn_tracking_b200.models.interaction_network import InteractionNetwork
+    from gnn_tracking_b200.models.resin import ResIN
+    from gnn_tracking_b200.models.track_condensation_networks import GraphTCN
+    cls = {"in": InteractionNetwork, "resin": ResIN, "ec": ECForGraphTCN, "tcn": GraphTCN}[kind]
+    n = 0
+    for name, c in golden_models.items():
+        if c["kind"] != kind:
+            continue
+        kw = {k: (dict(v) if isinstance(v, dict) else v) for k, v in c["kwargs"].items()}
+        m = cls(**kw)
+        missing, unexpected = m.load_state_dict(c["state_dict"], strict=True)
+        assert not missing and not unexpected
+        assert list(m.state_dict().keys()) == list(c["state_dict"].keys()), name
+        for k, v in c["kwargs"].items():
+            assert m.hparams[k] == v or kind == "tcn"
+        n += 1
+    assert n > 0
+
+
+def test_hparams_attribute_dict_is_deepcopy_safe():
+    import copy
+    from gnn_tracking_b200.models.interaction_network import InteractionNetwork
+    m = InteractionNetwork(node_indim=3, edge_indim=2)
+    assert m.hparams.node_indim == 3 and m.hparams.edge_outdim == 4 and m.hparams.aggr == "add"
+    m2 = copy.deepcopy(m)
+    assert m2.hparams.node_hidden_dim == 40
+
+
+def test_no_cpu_fallback():
+    from gnn_tracking_b200.models.edge_classifier import ECForGraphTCN
+    m = ECForGraphTCN(node_indim=3, edge_indim=2, L_ec=1)
+
+    class D:
+        x = torch.zeros(4, 3)
+        edge_index = torch.zeros(2, 2, dtype=torch.long)
+        edge_attr = torch.zeros(2, 2)
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(D())
+
+
+def test_width_mismatch_is_an_assertion_error():
+    from gnn_tracking_b200.models.interaction_network import InteractionNetwork
+    m = InteractionNetwork(node_indim=3, edge_indim=2)
+    with pytest.raises(AssertionError):
+        m(torch.zeros(4, 5), torch.zeros(2, 2, dtype=torch.long), torch.zeros(2, 2))

@@ -1,0 +1,198 @@
+"""GPU parity of the CUDA path against (a) the golden vectors produced by the
+reference's own classes and (b) the CPU oracle on the same seeded inputs.
+
+Tolerance (BASELINE north_star): 1e-5 in fp32, relative to the output scale (SURVEY
+8c: the bundled test_graph has unscaled inputs so outputs reach O(1e3)); integer /
+index outputs bit-exact."""
+import pytest
+import torch
+
+from tests.golden.common import case_inputs
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def close(a, b, tol=TOL, what=""):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    scale = max(float(b.abs().max()), 1.0)
+    err = float((a - b).abs().max()) if a.numel() else 0.0
+    assert err <= tol * scale, f"{what}: max|d|={err:.3e} scale={scale:.3e}"
+
+
+def _cases(kind):
+    from tests.golden.common import load
+    return [k for k, v in load("models").items() if v["kind"] == kind]
+
+
+def _dev(gd):
+    return {k: v.cuda() for k, v in gd.items()}
+
+
+@pytest.fixture(scope="module", params=["ffma", "auto"])
+def impl(request, monkeypatch_module):
+    monkeypatch_module.setenv("GTB_IMPL", request.param)
+    return request.param
+
+
+@pytest.fixture(scope="module")
+def monkeypatch_module():
+    mp = pytest.MonkeyPatch()
+    yield mp
+    mp.undo()
+
+
+def test_plan_bit_exact(golden_graphs):
+    from gnn_tracking_b200.plan import build_plan
+    from oracle import in_oracle as O
+    for name, gd in golden_graphs.items():
+        ei = gd["edge_index"]
+        n = gd["x"].size(0)
+        plan = build_plan(ei.cuda(), n)
+        plan.validate()
+        perm, rowptr, src_s, dst_s = O.plan(ei, n)
+        assert torch.equal(plan.perm.cpu().long(), perm), name
+        assert torch.equal(plan.rowptr.cpu().long(), rowptr), name
+        assert torch.equal(plan.src_sorted.cpu().long(), src_s), name
+        assert torch.equal(plan.dst_sorted.cpu().long(), dst_s), name
+
+
+def test_plan_edge_cases():
+    from gnn_tracking_b200.plan import build_plan
+    from oracle import in_oracle as O
+    # no edges; one edge; all edges into the last node; out-of-range index flagged
+    for n, ei in [(5, torch.zeros(2, 0, dtype=torch.long)), (3, torch.tensor([[0], [2]])),
+                  (4, torch.tensor([[0, 1, 2, 3], [3, 3, 3, 3]]))]:
+        plan = build_plan(ei.cuda(), n)
+        plan.validate()
+        perm, rowptr, _, _ = O.plan(ei, n)
+        assert torch.equal(plan.rowptr.cpu().long(), rowptr)
+        assert torch.equal(plan.perm.cpu().long(), perm)
+    bad = build_plan(torch.tensor([[0, 1], [1, 7]]).cuda(), 4)
+    with pytest.raises(IndexError):
+        bad.validate()
+
+
+def test_plan_filter_matches_rebuild(golden_graphs):
+    from gnn_tracking_b200.plan import build_plan
+    gd = golden_graphs["synthetic"]
+    ei = gd["edge_index"].cuda()
+    n = gd["x"].size(0)
+    plan = build_plan(ei, n)
+    gen = torch.Generator().manual_seed(5)
+    for frac in (0.0, 0.37, 1.0):
+        keep = (torch.rand(ei.size(1), generator=gen) < frac).cuda()
+        sub, new_id, kept = plan.filtered(keep)
+        ref = build_plan(ei[:, keep].contiguous(), n)
+        assert sub.n_edges == ref.n_edges == int(keep.sum())
+        for f in ("perm", "rowptr", "src_sorted", "dst_sorted"):
+            assert torch.equal(getattr(sub, f), getattr(ref, f)), (frac, f)
+        exp = torch.full((ei.size(1),), -1, dtype=torch.int32, device="cuda")
+        exp[keep] = torch.arange(int(keep.sum()), dtype=torch.int32, device="cuda")
+        assert torch.equal(new_id, exp)
+        assert torch.equal(kept.long(), torch.nonzero(keep).flatten())
+
+
+@pytest.mark.parametrize("name", _cases("in"))
+def test_in_layer_vs_reference_golden(name, golden_models, golden_graphs, impl):
+    from gnn_tracking_b200.models.interaction_network import InteractionNetwork
+    c = golden_models[name]
+    gd = _dev(case_inputs(c, golden_graphs))
+    m = InteractionNetwork(**c["kwargs"]).cuda()
+    m.load_state_dict(c["state_dict"])
+    with torch.no_grad():
+        xt, et = m(gd["x"], gd["edge_index"], gd["edge_attr"])
+    close(xt, c["outputs"]["x_tilde"], what="x_tilde")
+    close(et, c["outputs"]["e_tilde"], what="e_tilde")
+
+
+@pytest.mark.parametrize("name", _cases("resin"))
+def test_resin_vs_reference_golden(name, golden_models, golden_graphs, impl):
+    from gnn_tracking_b200.models.resin import ResIN
+    c = golden_models[name]
+    gd = _dev(case_inputs(c, golden_graphs))
+    kw = {k: (dict(v) if isinstance(v, dict) else v) for k, v in c["kwargs"].items()}
+    m = ResIN(**kw).cuda()
+    m.load_state_dict(c["state_dict"])
+    with torch.no_grad():
+        x, e, es = m(gd["x"], gd["edge_index"], gd["edge_attr"])
+    close(x, c["outputs"]["x"], what="x")
+    close(e, c["outputs"]["edge_attr"], what="edge_attr")
+    ref_es = c["outputs"]["edge_attrs"]
+    if ref_es is None:
+        assert es is None
+    else:
+        assert len(es) == len(ref_es)
+        for i, (a, b) in enumerate(zip(es, ref_es)):
+            close(a, b, what=f"edge_attrs[{i}]")
+
+
+class _Data:
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+@pytest.mark.parametrize("name", _cases("ec"))
+def test_ec_vs_reference_golden(name, golden_models, golden_graphs, impl):
+    from gnn_tracking_b200.models.edge_classifier import ECForGraphTCN
+    c = golden_models[name]
+    gd = _dev(case_inputs(c, golden_graphs))
+    kw = {k: (dict(v) if isinstance(v, dict) else v) for k, v in c["kwargs"].items()}
+    m = ECForGraphTCN(**kw).cuda()
+    m.load_state_dict(c["state_dict"])
+    with torch.no_grad():
+        out = m(_Data(**gd))
+    for k in ("W", "node_embedding", "edge_embedding"):
+        close(out[k], c["outputs"][k], what=k)
+
+
+@pytest.mark.parametrize("dims", [(64, 64, 64), (5, 4, 64), (128, 128, 128), (16, 8, 40)])
+def test_in_layer_vs_oracle_seeded(dims, impl):
+    """Seeded uniform-random graph (worst locality) with high-degree nodes: CUDA vs the
+    CPU oracle on identical inputs and weights."""
+    from gnn_tracking_b200.models.interaction_network import InteractionNetwork
+    from oracle import in_oracle as O
+    dn, de, h = dims
+    gen = torch.Generator().manual_seed(42)
+    n, e = 3000, 40000
+    ei = torch.randint(0, n, (2, e), generator=gen)
+    ei[1, :1500] = 17  # a destination spanning many tiles
+    x = torch.randn(n, dn, generator=gen)
+    ea = torch.randn(e, de, generator=gen)
+    torch.manual_seed(1)
+    m = InteractionNetwork(node_indim=dn, edge_indim=de, node_outdim=dn, edge_outdim=de,
+                           node_hidden_dim=h, edge_hidden_dim=h)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    xt_ref, et_ref = O.interaction_network(x, ei, ea, sd, "")
+    m = m.cuda()
+    with torch.no_grad():
+        xt, et = m(x.cuda(), ei.cuda(), ea.cuda())
+    close(et, et_ref, what="e_tilde")
+    close(xt, xt_ref, what="x_tilde")
+
+
+def test_in_layer_empty_and_tiny(impl):
+    from gnn_tracking_b200.models.interaction_network import InteractionNetwork
+    from oracle import in_oracle as O
+    torch.manual_seed(3)
+    m = InteractionNetwork(node_indim=6, edge_indim=3, node_outdim=6, edge_outdim=3, node_hidden_dim=16, edge_hidden_dim=16)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    m = m.cuda()
+    for n, e in [(4, 0), (1, 1), (130, 129)]:
+        gen = torch.Generator().manual_seed(n + e)
+        x = torch.randn(n, 6, generator=gen)
+        ei = torch.randint(0, n, (2, e), generator=gen)
+        ea = torch.randn(e, 3, generator=gen)
+        xt_ref, et_ref = O.interaction_network(x, ei, ea, sd, "")
+        with torch.no_grad():
+            xt, et = m(x.cuda(), ei.cuda(), ea.cuda())
+        close(xt, xt_ref, what=f"x_tilde n={n} e={e}")
+        close(et, et_ref, what=f"e_tilde n={n} e={e}")
+
+
+def test_cpu_tensors_are_refused():
+    from gnn_tracking_b200.models.interaction_network import InteractionNetwork
+    m = InteractionNetwork(node_indim=2, edge_indim=2, node_outdim=2, edge_outdim=2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(3, 2), torch.zeros(2, 1, dtype=torch.long), torch.zeros(1, 2))
