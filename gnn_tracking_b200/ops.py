@@ -169,8 +169,9 @@ def fused_mlp(blocks: Sequence[Block], n_rows: int, packed: PackedMLP, *, final_
     if aggr is not None:
         d.aggr, d.aggr_ld = aggr.data_ptr(), aggr.stride(0)
         d.seg_id, d.rowptr = _idx(seg_id), _idx(rowptr)
-    check(lib().gtb_fused_mlp_f32(C.byref(d), stream_ptr(dev)))
-    _count(1)
+    if n_rows > 0:  # an empty edge set (E = 0) launches nothing; `out` is empty, `aggr` stays zero
+        check(lib().gtb_fused_mlp_f32(C.byref(d), stream_ptr(dev)))
+        _count(1)
     del keep
     return out if want_out else None
 

@@ -16,6 +16,8 @@ TOL = 1e-5
 def close(a, b, tol=TOL, what=""):
     a, b = a.detach().cpu().double(), b.detach().cpu().double()
     assert a.shape == b.shape, (what, a.shape, b.shape)
+    if b.numel() == 0:
+        return
     scale = max(float(b.abs().max()), 1.0)
     err = float((a - b).abs().max()) if a.numel() else 0.0
     assert err <= tol * scale, f"{what}: max|d|={err:.3e} scale={scale:.3e}"
