@@ -17,6 +17,7 @@ GTB_MAX_LAYERS = 3
 GTB_MAX_WIDTH = 128
 ACT_NONE, ACT_RELU, ACT_SIGMOID_AFFINE = 0, 1, 2
 IMPL_AUTO, IMPL_FFMA, IMPL_TCGEN05 = 0, 1, 2
+SRC_PROJECTED, SRC_SORTED = 1, 2
 
 _ERR_NAMES = {-1: "BAD_ARG", -2: "UNSUPPORTED_DIM", -3: "WORKSPACE", -4: "CUDA", -5: "ARCH"}
 
@@ -33,7 +34,7 @@ class GtbError(RuntimeError):
 
 class Src(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("index", C.c_void_p), ("width", C.c_int32), ("ld", C.c_int32),
-                ("relu", C.c_int32), ("reserved", C.c_int32)]
+                ("relu", C.c_int32), ("flags", C.c_int32)]
 
 
 class MlpDesc(C.Structure):
@@ -59,9 +60,11 @@ SIGNATURES = {
     "gtb_plan_build": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gtb_plan_filter_workspace_bytes": (_sz, [_i64, _i64]),
     "gtb_plan_filter": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "gtb_mlp_packed_bytes": (_sz, [C.c_int, C.POINTER(_i32), C.c_int]),
-    "gtb_mlp_pack": (C.c_int, [C.c_int, C.POINTER(_i32), C.POINTER(_vp), C.POINTER(_vp), C.c_int, _vp, _vp]),
+    "gtb_mlp_packed_bytes": (_sz, [C.c_int, C.POINTER(_i32), C.c_int, C.POINTER(_i32), C.c_int]),
+    "gtb_mlp_pack": (C.c_int, [C.c_int, C.POINTER(_i32), C.c_int, C.POINTER(_i32), C.POINTER(_vp), C.POINTER(_vp),
+                               C.c_int, _vp, _vp]),
     "gtb_fused_mlp_f32": (C.c_int, [C.POINTER(MlpDesc), _vp]),
+    "gtb_debug_tc_timeout": (C.c_int, [C.POINTER(C.c_int)]),
     "gtb_in_edge_forward_f32": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _i64, _i64, _vp, _vp, _vp, _vp,
                                           _i32, _i32, _i32, _i32, _vp, C.c_int, _vp, _i32, _vp, _vp]),
     "gtb_in_node_forward_f32": (C.c_int, [_vp, _i32, _i32, _vp, _i64, _i32, _i32, _i32, _i32, _vp, C.c_int,

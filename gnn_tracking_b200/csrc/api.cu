@@ -25,10 +25,10 @@ int rows_inv_l2norm(const gtb_src_t*, int, int64_t, float, float*, cudaStream_t)
 int rows_move(const float*, int, const int32_t*, int64_t, int, float*, int, bool, cudaStream_t);
 int pack_ffma(int, const int32_t*, const float* const*, const float* const*, void*, cudaStream_t);
 int fused_mlp_ffma(const gtb_mlp_desc_t&, cudaStream_t);
-size_t tc_packed_bytes(int, const int32_t*);
-bool tc_supported(int, const int32_t*);
-int pack_tc(int, const int32_t*, const float* const*, const float* const*, void*, cudaStream_t);
+size_t tc_packed_bytes(int, const int32_t*, int, const int32_t*);
+int pack_tc(int, const int32_t*, int, const int32_t*, const float* const*, const float* const*, void*, cudaStream_t);
 int fused_mlp_tc(const gtb_mlp_desc_t&, cudaStream_t);
+int tc_timeout_flag(int*);
 int ec_loss(const float*, const void*, int, int64_t, const int64_t*, const float*, float, int, float, float, float,
             double*, cudaStream_t);
 size_t oc_workspace_bytes(int64_t);
@@ -48,7 +48,13 @@ static int validate_desc(const gtb_mlp_desc_t* d) {
   for (int s = 0; s < d->n_srcs; ++s) {
     GTB_REQUIRE(d->srcs[s].ptr != nullptr && d->srcs[s].width >= 0 && d->srcs[s].ld >= d->srcs[s].width,
                 GTB_ERR_BAD_ARG, "gtb_fused_mlp_f32: bad source block %d", s);
-    k += d->srcs[s].width;
+    if (d->srcs[s].flags & GTB_SRC_PROJECTED) {
+      GTB_REQUIRE(d->n_layers >= 2 && d->srcs[s].width == d->dims[1] && !d->srcs[s].relu, GTB_ERR_BAD_ARG,
+                  "gtb_fused_mlp_f32: pre-projected block %d must be %d wide, un-activated, in front of a hidden layer",
+                  s, d->dims[1]);
+    } else {
+      k += d->srcs[s].width;
+    }
   }
   // the reference asserts the feature widths at the same place (utils/asserts.py:4-7)
   GTB_REQUIRE(k == d->dims[0], GTB_ERR_BAD_ARG, "gtb_fused_mlp_f32: source widths sum to %d, first Linear expects %d",
@@ -70,6 +76,8 @@ extern "C" {
 
 int gtb_version(void) { return 100; }
 const char* gtb_last_error(void) { return g_err; }
+
+int gtb_debug_tc_timeout(int* flag) { return tc_timeout_flag(flag); }
 
 int gtb_arch_ok(int device) {
   cudaDeviceProp p;
@@ -102,19 +110,20 @@ int gtb_plan_filter(const uint8_t* keep, int64_t n_nodes, int64_t n_edges, const
                      static_cast<cudaStream_t>(stream));
 }
 
-size_t gtb_mlp_packed_bytes(int n_layers, const int32_t* dims, int impl) {
+size_t gtb_mlp_packed_bytes(int n_layers, const int32_t* dims, int n_blocks, const int32_t* block_widths, int impl) {
   if (n_layers < 1 || n_layers > GTB_MAX_LAYERS || dims == nullptr) return 0;
-  if (impl == GTB_IMPL_TCGEN05) return tc_packed_bytes(n_layers, dims);
+  if (impl == GTB_IMPL_TCGEN05) return tc_packed_bytes(n_layers, dims, n_blocks, block_widths);
   FfmaLayout L;
   if (!ffma_layout(n_layers, dims, &L)) return 0;
   return L.total_floats * sizeof(float);
 }
 
-int gtb_mlp_pack(int n_layers, const int32_t* dims, const float* const* weights, const float* const* biases,
-                 int impl, void* packed, void* stream) {
+int gtb_mlp_pack(int n_layers, const int32_t* dims, int n_blocks, const int32_t* block_widths,
+                 const float* const* weights, const float* const* biases, int impl, void* packed, void* stream) {
   GTB_REQUIRE(n_layers >= 1 && n_layers <= GTB_MAX_LAYERS && dims && weights && packed, GTB_ERR_BAD_ARG,
               "gtb_mlp_pack: bad arguments");
-  if (impl == GTB_IMPL_TCGEN05) return pack_tc(n_layers, dims, weights, biases, packed, static_cast<cudaStream_t>(stream));
+  if (impl == GTB_IMPL_TCGEN05)
+    return pack_tc(n_layers, dims, n_blocks, block_widths, weights, biases, packed, static_cast<cudaStream_t>(stream));
   GTB_REQUIRE(impl == GTB_IMPL_FFMA, GTB_ERR_BAD_ARG, "gtb_mlp_pack: impl must be GTB_IMPL_FFMA or GTB_IMPL_TCGEN05");
   return pack_ffma(n_layers, dims, weights, biases, packed, static_cast<cudaStream_t>(stream));
 }

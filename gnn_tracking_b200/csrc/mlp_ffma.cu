@@ -18,6 +18,7 @@ struct SrcS {
   int width;
   int ld;
   int relu;
+  int sidx;   // position of the block in the descriptor (row index table)
 };
 
 template <int NC>
@@ -28,7 +29,7 @@ struct Smem {
   static constexpr size_t w_floats = (size_t)KC * NW;
   static constexpr size_t h_floats = (size_t)TM * HS;
   static size_t bytes(int n_srcs) {
-    return (a_floats + w_floats + h_floats) * 4 + (size_t)(n_srcs + 2) * TM * 4 + GTB_MAX_SRCS * sizeof(SrcS);
+    return (a_floats + w_floats + h_floats) * 4 + (size_t)(n_srcs + 2) * TM * 4 + GTB_MAX_SRCS * sizeof(SrcS) + 16;
   }
 };
 
@@ -96,7 +97,8 @@ fused_mlp_ffma_kernel(const __grid_constant__ gtb_mlp_desc_t d, const __grid_con
   int32_t* ridx = reinterpret_cast<int32_t*>(Hs + S::h_floats);  // [n_srcs][TM]
   int32_t* orow = ridx + d.n_srcs * TM;                          // [TM]
   int32_t* segs = orow + TM;                                     // [TM]
-  SrcS* srcs = reinterpret_cast<SrcS*>(segs + TM);               // [n_srcs]
+  SrcS* srcs = reinterpret_cast<SrcS*>(segs + TM);               // [n_stream] concatenated (non-projected) blocks
+  int* n_stream_p = reinterpret_cast<int*>(srcs + GTB_MAX_SRCS);
 
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -105,10 +107,14 @@ fused_mlp_ffma_kernel(const __grid_constant__ gtb_mlp_desc_t d, const __grid_con
   const int rows_here = (int)min((int64_t)TM, d.n_rows - row0);
   const float* __restrict__ packed = static_cast<const float*>(d.packed);
 
-  if (tid < d.n_srcs) {
-    int off = 0;
-    for (int s = 0; s < tid; ++s) off += d.srcs[s].width;
-    srcs[tid] = SrcS{d.srcs[tid].ptr, off, d.srcs[tid].width, d.srcs[tid].ld, d.srcs[tid].relu};
+  if (tid == 0) {
+    int off = 0, n = 0;
+    for (int s = 0; s < d.n_srcs; ++s) {
+      if (d.srcs[s].flags & GTB_SRC_PROJECTED) continue;
+      srcs[n++] = SrcS{d.srcs[s].ptr, off, d.srcs[s].width, d.srcs[s].ld, d.srcs[s].relu, s};
+      off += d.srcs[s].width;
+    }
+    *n_stream_p = n;
   }
   for (int i = tid; i < d.n_srcs * TM; i += NTHREADS) {
     const int s = i / TM, r = i - s * TM;
@@ -128,6 +134,7 @@ fused_mlp_ffma_kernel(const __grid_constant__ gtb_mlp_desc_t d, const __grid_con
   __syncthreads();
 
   const int last = d.n_layers - 1;
+  const int n_stream = *n_stream_p;
   for (int l = 0; l <= last; ++l) {
     const bool narrow = (l == last) && L.narrow_last;
     const int Kp = L.kp[l];
@@ -155,12 +162,12 @@ fused_mlp_ffma_kernel(const __grid_constant__ gtb_mlp_desc_t d, const __grid_con
         int s = -1;
         if (k < d.dims[0]) {
           s = 0;
-          while (s + 1 < d.n_srcs && k >= srcs[s + 1].off) ++s;
+          while (s + 1 < n_stream && k >= srcs[s + 1].off) ++s;
         }
         if (s >= 0) {
           const SrcS sd = srcs[s];
           const int col = k - sd.off;
-          const int32_t* ri = ridx + s * TM;
+          const int32_t* ri = ridx + sd.sidx * TM;
 #pragma unroll 4
           for (int r = warp; r < TM; r += NTHREADS / 32) {
             float v = 0.f;
@@ -197,6 +204,17 @@ fused_mlp_ffma_kernel(const __grid_constant__ gtb_mlp_desc_t d, const __grid_con
         for (int i = 0; i < 8; ++i) {
           float4 v = make_float4(acc[i][c * 4 + 0] + b.x, acc[i][c * 4 + 1] + b.y,
                                  acc[i][c * 4 + 2] + b.z, acc[i][c * 4 + 3] + b.w);
+          if (l == 0 && n_stream != d.n_srcs) {  // gathered rows of the pre-projected blocks
+            const int col = c * 64 + tx * 4, n0 = d.dims[1];
+            for (int s = 0; s < d.n_srcs; ++s) {
+              if (!(d.srcs[s].flags & GTB_SRC_PROJECTED)) continue;
+              const float* pr = d.srcs[s].ptr + (size_t)ridx[s * TM + ty + 16 * i] * d.srcs[s].ld + col;
+              if (col + 0 < n0) v.x += __ldg(pr + 0);
+              if (col + 1 < n0) v.y += __ldg(pr + 1);
+              if (col + 2 < n0) v.z += __ldg(pr + 2);
+              if (col + 3 < n0) v.w += __ldg(pr + 3);
+            }
+          }
           if (l != last) {
             v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
           }

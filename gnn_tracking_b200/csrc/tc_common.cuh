@@ -80,6 +80,45 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// 32 lanes x 8 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+// 32 lanes x 32 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// ------------------------------------------------------------------------- cp.async
+// 16-byte global -> shared copy that bypasses L1 (streamed / gathered rows are used once)
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// wait until at most `n` of this thread's most recent groups are pending (n clamped to [0, 3])
+__device__ __forceinline__ void cp_async_wait_pending(int n) {
+  if (n <= 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
+  else if (n == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
+  else if (n == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
+  else asm volatile("cp.async.wait_group 3;" ::: "memory");
+}
+
 // ------------------------------------------------------------------------ descriptors
 // Shared-memory matrix descriptor, K-major operand stored as [rows][32 fp32] tiles with the
 // 128-byte swizzle: 8-row groups of 1024 B (SBO), 16-byte chunk c of row r stored at chunk
@@ -134,10 +173,19 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
                : "memory");
 }
 
-// split an fp32 value into a tf32-exact high part and the fp32 remainder (3xTF32 scheme)
+// split an fp32 value into two tf32-exact parts (3xTF32 scheme): hi = rn_tf32(v), lo = rn_tf32(v - hi).
+// Both parts are rounded to nearest HERE because the tensor core truncates its fp32 operands to
+// tf32 (profiles/r1_tc_unit_probe.log): handing it a truncated hi and an unrounded lo leaves a
+// one-sided 2^-21 error per product that adds up coherently over K; with both parts pre-rounded
+// the representation error is <= 2^-23 |v| and unbiased.
+__device__ __forceinline__ float rn_tf32(float v) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  return __uint_as_float(u);
+}
 __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
-  hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-  lo = v - hi;
+  hi = rn_tf32(v);
+  lo = rn_tf32(v - hi);
 }
 
 }  // namespace tc

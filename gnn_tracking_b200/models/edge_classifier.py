@@ -59,7 +59,7 @@ class ECForGraphTCN(nn.Module, HyperparametersMixin):
         # dst-sorted order (h[dst] rows repeat) and written back in the caller's edge order
         blocks = []
         if self.hparams.use_node_embedding:
-            blocks += [Block(h, plan.src_sorted), Block(h, plan.dst_sorted)]
+            blocks += [Block(h, plan.src_sorted), Block(h, plan.dst_sorted, sorted_index=True)]
         blocks += [Block(t, plan.perm) for t in (eas if self.hparams.use_intermediate_edge_embeddings else [ea])]
         w = self.W.forward_blocks(blocks, e, final_act=ACT_SIGMOID_AFFINE, act_eps=0.001, out_index=plan.perm)
         return {"W": w.squeeze(), "node_embedding": h, "edge_embedding": ea}

@@ -46,7 +46,7 @@ class InteractionNetwork(nn.Module, HyperparametersMixin):
         aggr = torch.zeros((n, e_out), dtype=torch.float32, device=dev)
         # message(): cat[x_i (target), x_j (source), edge_attr]  (interaction_network.py:75-89)
         e_tilde = self.relational_model.forward_blocks(
-            [Block(x, plan.dst_sorted, relu_x), Block(x, plan.src_sorted, relu_x),
+            [Block(x, plan.dst_sorted, relu_x, sorted_index=True), Block(x, plan.src_sorted, relu_x),
              Block(edge_attr, plan.perm, relu_e)],
             e, out_index=plan.perm, aggr=aggr, seg_id=plan.dst_sorted, rowptr=plan.rowptr)
         # update(): cat[x, aggr]  (interaction_network.py:92-103)

@@ -11,8 +11,8 @@ import torch
 from torch import Tensor
 
 from . import _lib
-from ._lib import (ACT_NONE, ACT_RELU, ACT_SIGMOID_AFFINE, IMPL_AUTO, IMPL_FFMA, IMPL_TCGEN05, GtbError,
-                   MlpDesc, Src, check, lib)
+from ._lib import (ACT_NONE, ACT_RELU, ACT_SIGMOID_AFFINE, IMPL_AUTO, IMPL_FFMA, IMPL_TCGEN05, SRC_PROJECTED,
+                   SRC_SORTED, GtbError, MlpDesc, Src, check, lib)
 
 __all__ = ["ACT_NONE", "ACT_RELU", "ACT_SIGMOID_AFFINE", "IMPL_AUTO", "IMPL_FFMA", "IMPL_TCGEN05", "Block",
            "PackedMLP", "fused_mlp", "pack_linears", "require_cuda", "default_impl", "launch_count"]
@@ -71,10 +71,21 @@ def _f32c(t: Tensor) -> Tensor:
 
 @dataclass
 class Block:
-    """One column block of a concatenated MLP input: ``act(tensor[index])``."""
+    """One column block of a concatenated MLP input: ``act(tensor[index])``.
+
+    ``projected``: ``tensor`` already holds the block multiplied by its columns of the first
+    Linear (a ``[*, N0]`` table); its gathered rows are added behind the first Linear instead
+    of being concatenated in front of it (GTB_SRC_PROJECTED in include/gtb200.h).
+    ``sorted_index``: hint that ``index`` is non-decreasing (the plan's ``dst_sorted``)."""
     tensor: Tensor
     index: Tensor | None = None  # int32 row index per output row
     relu: bool = False
+    projected: bool = False
+    sorted_index: bool = False
+
+    @property
+    def flags(self) -> int:
+        return (SRC_PROJECTED if self.projected else 0) | (SRC_SORTED if self.sorted_index else 0)
 
 
 @dataclass
@@ -82,21 +93,30 @@ class PackedMLP:
     buf: Tensor
     dims: tuple[int, ...]
     impl: int
+    block_widths: tuple[int, ...] = ()
 
     @property
     def n_layers(self) -> int:
         return len(self.dims) - 1
 
 
-def resolve_impl(dims: Sequence[int], impl: int) -> int:
+def _i32arr(vals: Sequence[int]):
+    return (C.c_int32 * len(vals))(*vals)
+
+
+def resolve_impl(dims: Sequence[int], impl: int, block_widths: Sequence[int] | None = None) -> int:
+    """GTB_IMPL_AUTO -> the tcgen05 tiles when they support the widths, else the FFMA tiles."""
     if impl != IMPL_AUTO:
         return impl
-    arr = (C.c_int32 * len(dims))(*dims)
-    return IMPL_TCGEN05 if lib().gtb_mlp_packed_bytes(len(dims) - 1, arr, IMPL_TCGEN05) > 0 else IMPL_FFMA
+    bw = list(block_widths) if block_widths else [dims[0]]
+    ok = lib().gtb_mlp_packed_bytes(len(dims) - 1, _i32arr(dims), len(bw), _i32arr(bw), IMPL_TCGEN05) > 0
+    return IMPL_TCGEN05 if ok else IMPL_FFMA
 
 
-def pack_linears(weights: Sequence[Tensor], biases: Sequence[Tensor | None], impl: int = IMPL_AUTO) -> PackedMLP:
-    """Repack <= 3 ``nn.Linear`` layers ([out, in] weights) for the fused tiles."""
+def pack_linears(weights: Sequence[Tensor], biases: Sequence[Tensor | None], impl: int = IMPL_AUTO,
+                 block_widths: Sequence[int] | None = None) -> PackedMLP:
+    """Repack <= 3 ``nn.Linear`` layers ([out, in] weights) for the fused tiles.
+    ``block_widths``: widths of the concatenated source blocks the MLP is called with."""
     dev = require_cuda(*weights)
     n = len(weights)
     if not 1 <= n <= _lib.GTB_MAX_LAYERS:
@@ -105,19 +125,23 @@ def pack_linears(weights: Sequence[Tensor], biases: Sequence[Tensor | None], imp
     for i, w in enumerate(weights):
         if w.size(1) != dims[i]:
             raise ValueError("Linear layers do not chain")
-    impl = resolve_impl(dims, impl)
-    dims_c = (C.c_int32 * (n + 1))(*dims)
-    nbytes = lib().gtb_mlp_packed_bytes(n, dims_c, impl)
+    bw = list(block_widths) if block_widths else [dims[0]]
+    if sum(bw) != dims[0]:
+        raise ValueError(f"block widths {bw} do not sum to the input width {dims[0]}")
+    impl = resolve_impl(dims, impl, bw)
+    dims_c = _i32arr(dims)
+    bw_c = _i32arr(bw)
+    nbytes = lib().gtb_mlp_packed_bytes(n, dims_c, len(bw), bw_c, impl)
     if nbytes == 0:
-        raise GtbError(-2, f"MLP widths {dims} are not supported by impl {impl}")
+        raise GtbError(-2, f"MLP widths {dims} (blocks {bw}) are not supported by impl {impl}")
     buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     ws = [w.detach().to(torch.float32).contiguous() for w in weights]
     bs = [None if b is None else b.detach().to(torch.float32).contiguous() for b in biases]
     wp = (C.c_void_p * n)(*[w.data_ptr() for w in ws])
     bp = (C.c_void_p * n)(*[(b.data_ptr() if b is not None else None) for b in bs])
-    check(lib().gtb_mlp_pack(n, dims_c, wp, bp, impl, buf.data_ptr(), stream_ptr(dev)))
-    _count(n)
-    return PackedMLP(buf, tuple(dims), impl)
+    check(lib().gtb_mlp_pack(n, dims_c, len(bw), bw_c, wp, bp, impl, buf.data_ptr(), stream_ptr(dev)))
+    _count(n if impl == IMPL_FFMA else 1)
+    return PackedMLP(buf, tuple(dims), impl, tuple(bw))
 
 
 def _idx(t: Tensor | None) -> int | None:
@@ -144,7 +168,10 @@ def fused_mlp(blocks: Sequence[Block], n_rows: int, packed: PackedMLP, *, final_
     if len(blocks) > _lib.GTB_MAX_SRCS:
         raise ValueError(f"at most {_lib.GTB_MAX_SRCS} column blocks")
     for i, (b, t) in enumerate(zip(blocks, tensors)):
-        d.srcs[i] = Src(t.data_ptr(), _idx(b.index), t.size(1), t.stride(0), int(b.relu), 0)
+        d.srcs[i] = Src(t.data_ptr(), _idx(b.index), t.size(1), t.stride(0), int(b.relu), b.flags)
+    stream = tuple(t.size(1) for b, t in zip(blocks, tensors) if not b.projected)
+    if packed.impl == IMPL_TCGEN05 and stream != packed.block_widths:
+        raise ValueError(f"weights were packed for source blocks {packed.block_widths}, called with {stream}")
     for i, v in enumerate(packed.dims):
         d.dims[i] = v
     d.packed = packed.buf.data_ptr()

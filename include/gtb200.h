@@ -43,7 +43,7 @@ extern "C" {
 /* which implementation a fused-MLP call must use */
 #define GTB_IMPL_AUTO   0
 #define GTB_IMPL_FFMA   1 /* fp32 CUDA-core tiles (any width <= GTB_MAX_WIDTH)             */
-#define GTB_IMPL_TCGEN05 2 /* tcgen05 3xTF32 tiles (widths multiple of 16)  */
+#define GTB_IMPL_TCGEN05 2 /* tcgen05 3xTF32 tiles (Linear widths <= 64)     */
 
 int         gtb_version(void);
 const char* gtb_last_error(void);
@@ -87,11 +87,26 @@ int gtb_plan_filter(const uint8_t* keep, int64_t n_nodes, int64_t n_edges,
  * An MLP of the path (models/mlp.py:18-62: Linear/ReLU chain, nn.Linear weights
  * [out, in] row-major, optional bias) is repacked once per weight version into the
  * K-major, zero-padded layout the tiles consume.  `impl` selects the layout
- * (GTB_IMPL_FFMA or GTB_IMPL_TCGEN05).  dims = {K0, N0, N1, N2} (true widths). */
-size_t gtb_mlp_packed_bytes(int n_layers, const int32_t* dims, int impl);
-int gtb_mlp_pack(int n_layers, const int32_t* dims, const float* const* weights,
-                 const float* const* biases /* entries may be NULL */, int impl,
-                 void* packed, void* stream);
+ * (GTB_IMPL_FFMA or GTB_IMPL_TCGEN05).  dims = {K0, N0, N1, N2} (true widths).
+ * block_widths[n_blocks] are the widths of the concatenated (non-projected) source blocks the
+ * MLP will be called with (they sum to K0; NULL = one block): the tcgen05 layout pads every
+ * block to a multiple of 8 columns.  gtb_mlp_packed_bytes returns 0 when `impl` does not
+ * support the widths. */
+size_t gtb_mlp_packed_bytes(int n_layers, const int32_t* dims, int n_blocks, const int32_t* block_widths,
+                            int impl);
+int gtb_mlp_pack(int n_layers, const int32_t* dims, int n_blocks, const int32_t* block_widths,
+                 const float* const* weights, const float* const* biases /* entries may be NULL */,
+                 int impl, void* packed, void* stream);
+
+/* flags of a source block.
+ * GTB_SRC_PROJECTED: the block was already multiplied by its column block of the first Linear
+ *   (a per-node table [*, N0], N0 = dims[1]); the gathered rows are ADDED to the output of
+ *   the first Linear instead of being concatenated in front of it.  With E >> N this moves
+ *   2*Dn*H of the (2*Dn + De)*H multiply-adds per edge of the relational model
+ *   (interaction_network.py:86-87) to a per-node launch.  Such blocks do not count in dims[0].
+ * GTB_SRC_SORTED: hint, `index` is non-decreasing (neighbouring rows repeat). */
+#define GTB_SRC_PROJECTED 1
+#define GTB_SRC_SORTED    2
 
 /* --------------------------------------------------------------- fused row MLP
  * out[orow(r), :] = epilogue( MLP( cat_s( act_s( src_s[irow_s(r), 0:width_s] ) ) ) )
@@ -108,7 +123,7 @@ typedef struct {
   int32_t        width;  /* columns taken (from column 0)                                */
   int32_t        ld;     /* row stride in elements                                       */
   int32_t        relu;   /* 1: relu on load (resin.py:104-105: layers > 0 see relu(x))   */
-  int32_t        reserved;
+  int32_t        flags;  /* GTB_SRC_*                                                    */
 } gtb_src_t;
 
 typedef struct {
@@ -147,6 +162,10 @@ typedef struct {
 } gtb_mlp_desc_t;
 
 int gtb_fused_mlp_f32(const gtb_mlp_desc_t* desc, void* stream);
+
+/* Test hook (synchronises): *flag != 0 if a tcgen05 kernel ever gave up waiting for its MMA
+ * barrier -- such a kernel traps, so the CUDA error is sticky as well. */
+int gtb_debug_tc_timeout(int* flag);
 
 /* ------------------------------------------------------------- IN layer wrappers
  * One Interaction-Network layer (interaction_network.py:54-103) on a planned graph.

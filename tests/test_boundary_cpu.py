@@ -35,14 +35,26 @@ def test_desc_struct_matches_header_layout():
 def test_packed_bytes_host_logic():
     from gnn_tracking_b200 import _lib
     import ctypes as C
-    dims = (C.c_int32 * 4)(192, 64, 64, 64)
-    n = _lib.lib().gtb_mlp_packed_bytes(3, dims, _lib.IMPL_FFMA)
-    assert n == 4 * (192 * 64 + 64 + 64 * 64 + 64 + 64 * 64 + 64)
-    dims = (C.c_int32 * 4)(14, 64, 64, 4)  # narrow last layer padded to 8 columns, K0 to 32
-    n = _lib.lib().gtb_mlp_packed_bytes(3, dims, _lib.IMPL_FFMA)
-    assert n == 4 * (32 * 64 + 64 + 64 * 64 + 64 + 64 * 8 + 8)
-    dims = (C.c_int32 * 4)(14, 300, 64, 4)
-    assert _lib.lib().gtb_mlp_packed_bytes(3, dims, _lib.IMPL_FFMA) == 0  # unsupported width
+    L = _lib.lib()
+
+    def nbytes(dims, impl, blocks=None):
+        d = (C.c_int32 * len(dims))(*dims)
+        b = (C.c_int32 * len(blocks))(*blocks) if blocks else None
+        return L.gtb_mlp_packed_bytes(len(dims) - 1, d, len(blocks) if blocks else 0, b, impl)
+
+    assert nbytes((192, 64, 64, 64), _lib.IMPL_FFMA) == 4 * (192 * 64 + 64 + 64 * 64 + 64 + 64 * 64 + 64)
+    # narrow last layer padded to 8 columns, K0 to 32
+    assert nbytes((14, 64, 64, 4), _lib.IMPL_FFMA) == 4 * (32 * 64 + 64 + 64 * 64 + 64 + 64 * 8 + 8)
+    assert nbytes((14, 300, 64, 4), _lib.IMPL_FFMA) == 0  # unsupported width
+    # tcgen05 layout: per layer hi + lo K-major tiles [npad][32] fp32 per 32-wide K tile, + 64-float bias rows
+    assert nbytes((64, 64, 64, 64), _lib.IMPL_TCGEN05) == 3 * 2 * (2 * 64 * 128) + 3 * 256
+    # blocks are padded to 8 columns each (5 -> 8, 4 -> 8: K0 = 16 -> one K tile); N = 5 -> 16 rows
+    assert nbytes((9, 64, 64, 5), _lib.IMPL_TCGEN05, (5, 4)) == 2 * (64 * 128) + 2 * (2 * 64 * 128) + 2 * (2 * 16 * 128) + 3 * 256
+    assert nbytes((9, 64, 64, 5), _lib.IMPL_TCGEN05, (5, 5)) == 0      # blocks do not sum to K0
+    assert nbytes((64, 128, 128, 64), _lib.IMPL_TCGEN05) == 0          # Linear wider than 64: FFMA path
+    assert nbytes((18, 64, 64, 1), _lib.IMPL_TCGEN05, (18,)) == 0      # neither 16-byte rows nor narrow
+    assert nbytes((384, 64, 64, 1), _lib.IMPL_TCGEN05, (64,) * 6) == 0  # weights + one staging slot exceed 227 KB
+    assert nbytes((256, 64, 64, 1), _lib.IMPL_TCGEN05, (64,) * 4) > 0
 
 
 @pytest.mark.parametrize("kind", ["in", "resin", "ec", "tcn"])
