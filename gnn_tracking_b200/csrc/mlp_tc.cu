@@ -30,9 +30,9 @@ constexpr int TC_SLOT = TC_TM * 256;       // one staging slot: [128 rows][64 fp
 constexpr int TC_MAXCH = 8;                // streamed sub-blocks (<= 64 columns each) of the first Linear
 constexpr int TC_MAXITEMS = TC_MAXCH + 3;
 constexpr int TC_SMEM_MAX = 232448;        // 227 KB opt-in shared memory per CTA
-constexpr int TC_HEAD = 1040;              // row indices (2 x 128 int32), MMA barrier, TMEM slot
+constexpr int TC_HEAD = 1056;              // per team: 128 segment ids + MMA barrier; TMEM slot
 constexpr int TC_MISC = TC_HEAD + 1023;    // + slack to align the weight tiles to 1024 bytes
-constexpr uint32_t TM_A_HI = 0, TM_A_LO = 64, TM_D = 128;  // TMEM column map of one tile context
+constexpr uint32_t TM_A_HI = 0, TM_A_LO = 64, TM_D = 128, TM_CTX = 192;  // TMEM column map of one team
 
 __device__ int g_tc_timeout = 0;
 
@@ -58,7 +58,7 @@ struct TcAdd {
 };
 struct TcParams {
   int64_t n_rows;
-  int32_t n_tiles, n_chunks, n_adds, n_layers, ring, ipt;
+  int32_t n_tiles, n_chunks, n_adds, n_layers, ring, ipt, n_teams;
   int8_t items[TC_MAXITEMS + 1];  // per tile, in consumption order: chunk c -> c, add a -> 64 + a, output tile -> -1
   TcChunk ch[TC_MAXCH];
   TcAdd add[2];
@@ -192,6 +192,16 @@ int pack_tc(int n_layers, const int32_t* dims, int n_chunks, const int32_t* chun
 }
 
 // ------------------------------------------------------------------------------ kernel
+// A CTA runs one or two TEAMS of 256 threads.  A team owns its tiles (alternating with the other
+// team), its ring of staging slots, its TMEM columns and its MMA barrier, and synchronises on a
+// named barrier only -- so one team's MMA chain and load latency overlap the other team's
+// epilogue / conversion work on the same SM, with the packed weights shared.
+constexpr int TC_TEAM = 256;
+
+__device__ __forceinline__ void team_sync(int team) {
+  asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(TC_TEAM) : "memory");
+}
+
 __device__ __forceinline__ uint32_t slot_off(int r, int c4) {  // 16-byte chunk c4 of row r
   return (uint32_t)(r * 256 + ((c4 ^ (r & 7)) << 4));
 }
@@ -203,11 +213,15 @@ __device__ __forceinline__ void wait_or_trap(uint64_t* bar, uint32_t parity) {
   }
 }
 
-// gather one staged item (a streamed column block or a pre-projected row block) of sequence
-// number g into its ring slot; every thread commits exactly one cp.async group per call
-__device__ __forceinline__ void tc_issue_item(const TcParams& p, int g, unsigned char* slots, int tid) {
+__device__ __forceinline__ int64_t team_tile(const TcParams& p, int team, int t) {
+  return (int64_t)blockIdx.x + (int64_t)gridDim.x * ((int64_t)t * p.n_teams + team);
+}
+
+// gather one staged item (a streamed column block or a pre-projected row block) of the team's
+// sequence number g into its ring slot; every thread commits exactly one cp.async group per call
+__device__ __forceinline__ void tc_issue_item(const TcParams& p, int g, int team, unsigned char* slots, int tt) {
   const int t = g / p.ipt, k = g - t * p.ipt;
-  const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
+  const int64_t tile = team_tile(p, team, t);
   const int kind = p.items[k];
   if (tile < p.n_tiles && kind >= 0) {
     const float* ptr;
@@ -222,31 +236,54 @@ __device__ __forceinline__ void tc_issue_item(const TcParams& p, int g, unsigned
     const int rows_here = (int)min((int64_t)TC_TM, p.n_rows - row0);
     const uint32_t sbase = smem_u32(slots + (size_t)(g % p.ring) * TC_SLOT);
     const int c4n = width >> 2;
-    const int total = rows_here * c4n;
-    for (int i = tid; i < total; i += TC_NT) {
-      const int r = i / c4n, c = i - r * c4n;
-      const int64_t row = index ? (int64_t)__ldg(index + row0 + r) : row0 + r;
-      cp_async16(sbase + slot_off(r, c), ptr + (size_t)row * ld + (c << 2));
+    const int total = rows_here * c4n;  // <= 8 copies per thread
+    const bool pow2 = (c4n & (c4n - 1)) == 0;
+    const int sh = __ffs(c4n) - 1;
+    int64_t rows[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {  // row indices first: independent loads, one latency
+      const int i = tt + j * TC_TEAM;
+      rows[j] = 0;
+      if (i < total) {
+        const int r = pow2 ? (i >> sh) : (i / c4n);
+        rows[j] = index ? (int64_t)__ldg(index + row0 + r) : row0 + r;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int i = tt + j * TC_TEAM;
+      if (i < total) {
+        const int r = pow2 ? (i >> sh) : (i / c4n);
+        const int c = i - r * c4n;
+        cp_async16(sbase + slot_off(r, c), ptr + (size_t)rows[j] * ld + (c << 2));
+      }
     }
   }
   cp_async_commit();
 }
 
-__device__ __forceinline__ void tc_issue_mmas(uint32_t tm, uint32_t wbase, const TcParams& p, int l, int koff,
-                                              int ksteps, bool first) {
-  const uint32_t idesc = make_idesc_tf32(TC_TM, p.npad[l]);
-  const uint32_t tile_bytes = (uint32_t)p.npad[l] * 128u;
+// three passes (small terms first: lo*hi, hi*lo, hi*hi) over `ksteps` K = 8 steps of one streamed
+// block (first Linear) or of a whole hidden Linear; descriptors advance by plain adds
+__device__ __forceinline__ void tc_issue_mmas(uint32_t tmc, uint64_t bd_hi, uint64_t bd_lo, uint32_t idesc,
+                                              uint32_t tile16, int koff, int ksteps, bool first) {
   bool acc = !first;
+  const uint32_t boff = (uint32_t)(koff >> 5) * tile16 + (uint32_t)((koff & 31) >> 3) * 2u;
 #pragma unroll 1
-  for (int pass = 0; pass < 3; ++pass) {  // small terms first: lo*hi, hi*lo, hi*hi
-    const uint32_t a_col = (pass == 0) ? TM_A_LO : TM_A_HI;
-    const uint32_t b_base = wbase + p.w_off[l][pass == 1 ? 1 : 0];
+  for (int pass = 0; pass < 3; ++pass) {
+    uint32_t a = tmc + ((pass == 0) ? TM_A_LO : TM_A_HI);
+    uint64_t bd = ((pass == 1) ? bd_lo : bd_hi) + boff;
+    int sub = (koff & 31) >> 3;
 #pragma unroll 1
     for (int ks = 0; ks < ksteps; ++ks) {
-      const int kg = koff + 8 * ks;
-      const uint64_t bd = make_smem_desc_sw128(b_base + (uint32_t)(kg >> 5) * tile_bytes + (uint32_t)((kg & 31) >> 3) * 32u);
-      mma_tf32_ts(tm + TM_D, tm + a_col + 8 * ks, bd, idesc, acc);
+      mma_tf32_ts(tmc + TM_D, a, bd, idesc, acc);
       acc = true;
+      a += 8;
+      if (++sub == 4) {
+        sub = 0;
+        bd += tile16 - 6;  // next 32-wide K tile
+      } else {
+        bd += 2;           // +32 bytes inside the swizzled tile
+      }
     }
   }
 }
@@ -264,57 +301,76 @@ __device__ __forceinline__ void split_store8(uint32_t taddr_hi, uint32_t taddr_l
   tmem_st8(taddr_lo, lo);
 }
 
-__global__ void __launch_bounds__(TC_NT, 1) fused_mlp_tc_kernel(const __grid_constant__ TcParams p) {
+__device__ __forceinline__ void split_store16(uint32_t taddr_hi, uint32_t taddr_lo, const float (&v)[16]) {
+  uint32_t hi[16], lo[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float h, l;
+    split_tf32(v[j], h, l);
+    hi[j] = __float_as_uint(h);
+    lo[j] = __float_as_uint(l);
+  }
+  tmem_st16(taddr_hi, hi);
+  tmem_st16(taddr_lo, lo);
+}
+
+__global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  int32_t* orow = reinterpret_cast<int32_t*>(smem_raw);
-  int32_t* segs = orow + TC_TM;
-  uint64_t* mma_bar = reinterpret_cast<uint64_t*>(segs + TC_TM);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
+  int32_t* segs_all = reinterpret_cast<int32_t*>(smem_raw);                  // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(segs_all + 2 * TC_TM);         // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
   unsigned char* wsm = smem_raw + TC_HEAD;                     // packed weights + biases (1024-aligned tiles)
   wsm += (1024u - (smem_u32(wsm) & 1023u)) & 1023u;
-  unsigned char* slots = wsm + ((p.w_bytes + 15u) & ~15u);     // ring of staging slots
+  unsigned char* slots_all = wsm + ((p.w_bytes + 15u) & ~15u);  // rings of staging slots, one per team
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int r = tid & (TC_TM - 1), h = tid >> 7;
+  const int team = tid >> 8, tt = tid & (TC_TEAM - 1);
+  const int r = tt & (TC_TM - 1), h = tt >> 7;
+  unsigned char* slots = slots_all + (size_t)team * p.ring * TC_SLOT;
+  int32_t* segs = segs_all + team * TC_TM;
+  uint64_t* mma_bar = bars + team;
 
-  // ---- prologue: first items in flight, weights into shared memory, barrier + TMEM set-up
+  // ---- prologue: first items in flight, weights into shared memory, barriers + TMEM set-up
   int issued = 0;
-  for (; issued < p.ring; ++issued) tc_issue_item(p, issued, slots, tid);
+  for (; issued < p.ring; ++issued) tc_issue_item(p, issued, team, slots, tt);
   {
     const float4* g4 = reinterpret_cast<const float4*>(p.packed);
     float4* s4 = reinterpret_cast<float4*>(wsm);
-    for (int i = tid; i < (int)(p.w_bytes >> 4); i += TC_NT) s4[i] = __ldg(g4 + i);
+    for (int i = tid; i < (int)(p.w_bytes >> 4); i += blockDim.x) s4[i] = __ldg(g4 + i);
   }
-  if (tid == 0) {
+  if (tt == 0) {
     mbar_init(mma_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  const uint32_t tmem_cols = p.n_teams == 2 ? 512u : 256u;
+  if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
   fence_proxy_async_smem();  // weights were written through the generic proxy, the MMA reads them through the async proxy
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tm = *tmem_slot;
-  const uint32_t tm_lane = tm + ((uint32_t)((warp & 3) * 32) << 16);
+  const uint32_t tmc = tm + (uint32_t)team * TM_CTX;                        // this team's TMEM columns
+  const uint32_t tm_lane = tmc + ((uint32_t)((warp & 3) * 32) << 16);      // + this warp's 32 lanes
   const uint32_t wbase = smem_u32(wsm);
+  uint64_t bd_hi[GTB_MAX_LAYERS], bd_lo[GTB_MAX_LAYERS];
+  uint32_t idesc[GTB_MAX_LAYERS];
+#pragma unroll
+  for (int l = 0; l < GTB_MAX_LAYERS; ++l) {
+    bd_hi[l] = make_smem_desc_sw128(wbase + p.w_off[l][0]);
+    bd_lo[l] = make_smem_desc_sw128(wbase + p.w_off[l][1]);
+    idesc[l] = make_idesc_tf32(TC_TM, p.npad[l] > 0 ? p.npad[l] : 16);
+  }
   uint32_t mma_phase = 0;
   const int last = p.n_layers - 1;
 
-  int t = 0;
-  for (int64_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++t) {
+  for (int t = 0;; ++t) {
+    const int64_t tile = team_tile(p, team, t);
+    if (tile >= p.n_tiles) break;
     const int64_t row0 = tile * TC_TM;
     const int rows_here = (int)min((int64_t)TC_TM, p.n_rows - row0);
     const bool live = r < rows_here;
     int g = t * p.ipt;  // sequence number of this tile's next staged item
-    if (tid < TC_TM) {
-      int o = 0, sg = -1;
-      if (live) {
-        o = p.out_index ? __ldg(p.out_index + row0 + r) : (int)(row0 + r);
-        if (p.seg_id) sg = __ldg(p.seg_id + row0 + r);
-      }
-      orow[tid] = o;
-      segs[tid] = sg;
-    }
+    if (tt < TC_TM) segs[tt] = (live && p.seg_id) ? __ldg(p.seg_id + row0 + r) : -1;
     const float rscale = (p.row_scale && live) ? __ldg(p.row_scale + row0 + r) : 1.f;
 
     // ---------------- first Linear: one streamed block at a time through the TMEM A buffer
@@ -323,7 +379,7 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_mlp_tc_kernel(const __grid_con
       const int groups = ch.kpad >> 3;
       if (ch.staged) {
         cp_async_wait_pending(issued - g - 1);
-        __syncthreads();
+        team_sync(team);
       }
       if (c > 0) {  // the previous block's MMAs still read the A buffer
         wait_or_trap(mma_bar, mma_phase);
@@ -332,19 +388,27 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_mlp_tc_kernel(const __grid_con
       }
       if (ch.staged) {
         const unsigned char* sl = slots + (size_t)(g % p.ring) * TC_SLOT;
-        for (int g8 = h; g8 < groups; g8 += 2) {
-          float v[8];
-          const int c4 = 2 * g8;
-          float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-          if (c4 * 4 < ch.width) a = *reinterpret_cast<const float4*>(sl + slot_off(r, c4));
-          if ((c4 + 1) * 4 < ch.width) b = *reinterpret_cast<const float4*>(sl + slot_off(r, c4 + 1));
-          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        float4 a[4], b[4];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (ch.relu) v[j] = fmaxf(v[j], 0.f);
-            v[j] *= rscale;
+        for (int q = 0; q < 4; ++q) {
+          const int c4 = 2 * (h + 2 * q);
+          a[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          b[q] = a[q];
+          if (c4 * 4 < ch.width) a[q] = *reinterpret_cast<const float4*>(sl + slot_off(r, c4));
+          if ((c4 + 1) * 4 < ch.width) b[q] = *reinterpret_cast<const float4*>(sl + slot_off(r, c4 + 1));
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int g8 = h + 2 * q;
+          if (g8 < groups) {
+            float v[8] = {a[q].x, a[q].y, a[q].z, a[q].w, b[q].x, b[q].y, b[q].z, b[q].w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (ch.relu) v[j] = fmaxf(v[j], 0.f);
+              v[j] *= rscale;
+            }
+            split_store8(tm_lane + TM_A_HI + 8 * g8, tm_lane + TM_A_LO + 8 * g8, v);
           }
-          split_store8(tm_lane + TM_A_HI + 8 * g8, tm_lane + TM_A_LO + 8 * g8, v);
         }
       } else if (h == 0) {  // narrow block: the row owner reads its own elements
         const int64_t row = live ? (ch.index ? (int64_t)__ldg(ch.index + row0 + r) : row0 + r) : 0;
@@ -363,85 +427,104 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_mlp_tc_kernel(const __grid_con
       }
       tmem_st_wait();
       tc_fence_before_sync();
-      __syncthreads();
+      team_sync(team);
+      if (tt == 0) {
+        tc_fence_after_sync();
+        tc_issue_mmas(tmc, bd_hi[0], bd_lo[0], idesc[0], (uint32_t)p.npad[0] * 8u, ch.koff, groups, c == 0);
+        mma_commit(mma_bar);
+      }
       if (ch.staged) {  // the slot is free: keep the ring full
-        tc_issue_item(p, issued, slots, tid);
+        tc_issue_item(p, issued, team, slots, tt);
         ++issued;
         ++g;
-      }
-      if (tid == 0) {
-        tc_fence_after_sync();
-        tc_issue_mmas(tm, wbase, p, 0, ch.koff, groups, c == 0);
-        mma_commit(mma_bar);
       }
     }
 
     // ---------------- hidden layers: accumulator -> bias (+ gathered rows) -> ReLU -> next A operand
     for (int l = 0; l < last; ++l) {
-      wait_or_trap(mma_bar, mma_phase);
-      mma_phase ^= 1;
-      tc_fence_after_sync();
       const float* bias = reinterpret_cast<const float*>(wsm + p.b_off[l]);
-      const int groups = p.npad[l] >> 3, half = groups >> 1;
+      const int nb = p.npad[l] >> 4, per = (nb + 1) >> 1;
+      const int b0 = h * per, b1 = min(nb, b0 + per);
       const unsigned char* add_sl[2] = {nullptr, nullptr};
       const float* add_row[2] = {nullptr, nullptr};
+      float4 pre[8];  // the row owner's columns of the first directly read block, fetched under the MMA
+#pragma unroll
+      for (int q = 0; q < 8; ++q) pre[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      int gg = g;
       if (l == 0) {
-        int gg = g;
+        bool have_pre = false;
         for (int a = 0; a < p.n_adds; ++a) {
           if (p.add[a].staged) {
             add_sl[a] = slots + (size_t)(gg % p.ring) * TC_SLOT;
             ++gg;
           } else if (live) {
             const int64_t row = p.add[a].index ? (int64_t)__ldg(p.add[a].index + row0 + r) : row0 + r;
-            add_row[a] = p.add[a].ptr + (size_t)row * p.add[a].ld;
+            const float* rowp = p.add[a].ptr + (size_t)row * p.add[a].ld;
+            if (!have_pre) {
+              have_pre = true;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const int c4 = 4 * b0 + q;
+                if (q < 4 * (b1 - b0) && c4 * 4 < p.ntrue[0]) pre[q] = __ldg(reinterpret_cast<const float4*>(rowp) + c4);
+              }
+            } else {
+              add_row[a] = rowp;
+            }
           }
-        }
-        if (gg > g) {
-          cp_async_wait_pending(issued - gg);
-          __syncthreads();
         }
       }
-      for (int g8 = h * half; g8 < (h + 1) * half; ++g8) {
-        uint32_t acc[8];
-        tmem_ld8(tm_lane + TM_D + 8 * g8, acc);
-        tmem_ld_wait();
-        float v[8];
+      wait_or_trap(mma_bar, mma_phase);
+      mma_phase ^= 1;
+      tc_fence_after_sync();
+      if (gg > g) {
+        cp_async_wait_pending(issued - gg);
+        team_sync(team);
+      }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[j]) + bias[8 * g8 + j];
+      for (int bi = 0; bi < 2; ++bi) {  // at most two 16-column blocks per thread
+        const int b = b0 + bi;
+        if (b >= b1) break;
+        uint32_t acc[16];
+        tmem_ld16(tm_lane + TM_D + 16 * b, acc);
+        tmem_ld_wait();
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]) + bias[16 * b + j];
         if (l == 0) {
 #pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 x = pre[bi * 4 + q];
+            v[4 * q + 0] += x.x; v[4 * q + 1] += x.y; v[4 * q + 2] += x.z; v[4 * q + 3] += x.w;
+          }
+#pragma unroll
           for (int a = 0; a < 2; ++a) {
-            float4 x = make_float4(0.f, 0.f, 0.f, 0.f), y = x;
-            const int c4 = 2 * g8;
-            if (add_sl[a]) {
-              if (c4 * 4 < p.ntrue[0]) x = *reinterpret_cast<const float4*>(add_sl[a] + slot_off(r, c4));
-              if ((c4 + 1) * 4 < p.ntrue[0]) y = *reinterpret_cast<const float4*>(add_sl[a] + slot_off(r, c4 + 1));
-            } else if (add_row[a]) {
-              if (c4 * 4 < p.ntrue[0]) x = __ldg(reinterpret_cast<const float4*>(add_row[a]) + c4);
-              if ((c4 + 1) * 4 < p.ntrue[0]) y = __ldg(reinterpret_cast<const float4*>(add_row[a]) + c4 + 1);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int c4 = 4 * b + q;
+              float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (c4 * 4 < p.ntrue[0]) {
+                if (add_sl[a]) x = *reinterpret_cast<const float4*>(add_sl[a] + slot_off(r, c4));
+                else if (add_row[a]) x = __ldg(reinterpret_cast<const float4*>(add_row[a]) + c4);
+              }
+              v[4 * q + 0] += x.x; v[4 * q + 1] += x.y; v[4 * q + 2] += x.z; v[4 * q + 3] += x.w;
             }
-            v[0] += x.x; v[1] += x.y; v[2] += x.z; v[3] += x.w; v[4] += y.x; v[5] += y.y; v[6] += y.z; v[7] += y.w;
           }
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
-        split_store8(tm_lane + TM_A_HI + 8 * g8, tm_lane + TM_A_LO + 8 * g8, v);
+        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+        split_store16(tm_lane + TM_A_HI + 16 * b, tm_lane + TM_A_LO + 16 * b, v);
       }
       tmem_st_wait();
       tc_fence_before_sync();
-      __syncthreads();
-      if (l == 0) {
-        for (int a = 0; a < p.n_adds; ++a)
-          if (p.add[a].staged) {
-            tc_issue_item(p, issued, slots, tid);
-            ++issued;
-            ++g;
-          }
-      }
-      if (tid == 0) {
+      team_sync(team);
+      if (tt == 0) {
         tc_fence_after_sync();
-        tc_issue_mmas(tm, wbase, p, l + 1, 0, p.kpad[l + 1] >> 3, true);
+        tc_issue_mmas(tmc, bd_hi[l + 1], bd_lo[l + 1], idesc[l + 1], (uint32_t)p.npad[l + 1] * 8u, 0, p.kpad[l + 1] >> 3, true);
         mma_commit(mma_bar);
+      }
+      for (; g < gg; ++g) {  // the slots of the staged pre-projected blocks are free
+        tc_issue_item(p, issued, team, slots, tt);
+        ++issued;
       }
     }
 
@@ -449,28 +532,31 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_mlp_tc_kernel(const __grid_con
     wait_or_trap(mma_bar, mma_phase);
     mma_phase ^= 1;
     tc_fence_after_sync();
-    unsigned char* osl = slots + (size_t)(g % p.ring) * TC_SLOT;  // this item's slot was released R items ago
+    unsigned char* osl = slots + (size_t)(g % p.ring) * TC_SLOT;  // this item's slot was released `ring` items ago
     {
       const float* bias = reinterpret_cast<const float*>(wsm + p.b_off[last]);
-      const int groups = p.npad[last] >> 3, half = groups >> 1;
-      for (int g8 = h * half; g8 < (h + 1) * half; ++g8) {
-        uint32_t acc[8];
-        tmem_ld8(tm_lane + TM_D + 8 * g8, acc);
+      const int nb = p.npad[last] >> 4, per = (nb + 1) >> 1;
+      const int b0 = h * per, b1 = min(nb, b0 + per);
+      for (int b = b0; b < b1; ++b) {
+        uint32_t acc[16];
+        tmem_ld16(tm_lane + TM_D + 16 * b, acc);
         tmem_ld_wait();
-        float v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float x = __uint_as_float(acc[j]) + bias[8 * g8 + j];
-          if (p.final_act == GTB_ACT_RELU) x = fmaxf(x, 0.f);
-          else if (p.final_act == GTB_ACT_SIGMOID_AFFINE) x = p.act_eps + (1.f - 2.f * p.act_eps) * (1.f / (1.f + expf(-x)));
-          v[j] = x;
+        for (int q = 0; q < 4; ++q) {
+          float v[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float x = __uint_as_float(acc[4 * q + j]) + bias[16 * b + 4 * q + j];
+            if (p.final_act == GTB_ACT_RELU) x = fmaxf(x, 0.f);
+            else if (p.final_act == GTB_ACT_SIGMOID_AFFINE) x = p.act_eps + (1.f - 2.f * p.act_eps) * (1.f / (1.f + expf(-x)));
+            v[j] = x;
+          }
+          *reinterpret_cast<float4*>(osl + slot_off(r, 4 * b + q)) = make_float4(v[0], v[1], v[2], v[3]);
         }
-        *reinterpret_cast<float4*>(osl + slot_off(r, 2 * g8)) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4*>(osl + slot_off(r, 2 * g8 + 1)) = make_float4(v[4], v[5], v[6], v[7]);
       }
     }
     tc_fence_before_sync();
-    __syncthreads();
+    team_sync(team);
 
     // ---------------- residual / scale, coalesced (scattered) row stores
     const int N = p.ntrue[last];
@@ -482,8 +568,10 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_mlp_tc_kernel(const __grid_con
     if (p.out != nullptr || touch) {
       if (vec) {
         const int c4n = N >> 2;
-        for (int i = tid; i < rows_here * c4n; i += TC_NT) {
-          const int rr = i / c4n, c = i - rr * c4n;
+        const bool pow2 = (c4n & (c4n - 1)) == 0;
+        const int sh = __ffs(c4n) - 1;
+        for (int i = tt; i < rows_here * c4n; i += TC_TEAM) {
+          const int rr = pow2 ? (i >> sh) : (i / c4n), c = i - rr * c4n;
           float4* sp = reinterpret_cast<float4*>(osl + slot_off(rr, c));
           float4 v = *sp;
           if (touch) {
@@ -496,10 +584,13 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_mlp_tc_kernel(const __grid_con
             v.x *= oscale; v.y *= oscale; v.z *= oscale; v.w *= oscale;
             if (want_aggr) *sp = v;
           }
-          if (p.out) *(reinterpret_cast<float4*>(p.out + (size_t)orow[rr] * p.out_ld) + c) = v;
+          if (p.out) {
+            const int64_t orow = p.out_index ? (int64_t)__ldg(p.out_index + row0 + rr) : row0 + rr;
+            *(reinterpret_cast<float4*>(p.out + (size_t)orow * p.out_ld) + c) = v;
+          }
         }
       } else {
-        for (int i = tid; i < rows_here * N; i += TC_NT) {
+        for (int i = tt; i < rows_here * N; i += TC_TEAM) {
           const int rr = i / N, n = i - rr * N;
           float* sp = reinterpret_cast<float*>(osl + slot_off(rr, n >> 2)) + (n & 3);
           float v = *sp;
@@ -509,48 +600,44 @@ __global__ void __launch_bounds__(TC_NT, 1) fused_mlp_tc_kernel(const __grid_con
             v *= oscale;
             if (want_aggr) *sp = v;
           }
-          if (p.out) p.out[(size_t)orow[rr] * p.out_ld + n] = v;
+          if (p.out) {
+            const int64_t orow = p.out_index ? (int64_t)__ldg(p.out_index + row0 + rr) : row0 + rr;
+            p.out[(size_t)orow * p.out_ld + n] = v;
+          }
         }
       }
     }
 
-    // ---------------- in-tile segmented sum by destination (rows are destination-sorted): a run
-    // covering a node's whole CSR range is stored, partial runs (tile / part boundaries) are
-    // added atomically
+    // ---------------- in-tile segmented sum by destination (rows are destination-sorted): thread =
+    // (column, 32-row quarter); a warp shares its quarter, so the run boundaries are warp-uniform
+    // branches.  One fire-and-forget reduction per (run, column) onto the zero-filled aggregate.
     if (want_aggr) {
-      if (touch) __syncthreads();
-      constexpr int RP = 16;
-      const int n_parts = (rows_here + RP - 1) / RP;
-      for (int it = tid; it < N * n_parts; it += TC_NT) {
-        const int part = it / N, c = it - part * N;
-        const int r_beg = part * RP, r_end = min(r_beg + RP, rows_here);
-        int cur = segs[r_beg];
-        int g_start = r_beg;
+      if (touch) team_sync(team);
+      const int c = tt & 63, r0 = (tt >> 6) * 32, r1 = min(r0 + 32, rows_here);
+      if (c < N && r0 < r1) {
+        int cur = segs[r0];
         float sum = 0.f;
-        for (int rr = r_beg; rr <= r_end; ++rr) {
-          const int sg = (rr < r_end) ? segs[rr] : -2;
+        for (int rr = r0; rr < r1; ++rr) {
+          const int sg = segs[rr];
           if (sg != cur) {
-            const int64_t gs = row0 + g_start, ge = row0 + rr;
-            float* dst = p.aggr + (size_t)cur * p.aggr_ld + c;
-            if (__ldg(p.rowptr + cur) == gs && __ldg(p.rowptr + cur + 1) == ge) *dst = sum;
-            else atomicAdd(dst, sum);
+            atomicAdd(p.aggr + (size_t)cur * p.aggr_ld + c, sum);
             cur = sg;
-            g_start = rr;
             sum = 0.f;
           }
-          if (rr < r_end) sum += *(reinterpret_cast<const float*>(osl + slot_off(rr, c >> 2)) + (c & 3));
+          sum += *(reinterpret_cast<const float*>(osl + slot_off(rr, c >> 2)) + (c & 3));
         }
+        atomicAdd(p.aggr + (size_t)cur * p.aggr_ld + c, sum);
       }
     }
-    __syncthreads();
-    tc_issue_item(p, issued, slots, tid);  // the output slot is free again
+    team_sync(team);
+    tc_issue_item(p, issued, team, slots, tt);  // the output slot is free again
     ++issued;
   }
 
   cp_async_wait_pending(0);
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tm, 256);
+  if (warp == 0) tmem_dealloc(tm, tmem_cols);
 }
 
 // ------------------------------------------------------------------------------ host side
@@ -643,12 +730,14 @@ int fused_mlp_tc(const gtb_mlp_desc_t& d, cudaStream_t st) {
   p.seg_id = d.seg_id;
   p.rowptr = d.rowptr;
   const size_t fixed = ((size_t)L.total_bytes + 15) / 16 * 16 + TC_MISC;
-  int ring = (int)((TC_SMEM_MAX - fixed) / TC_SLOT);
-  if (ring > 4) ring = 4;
-  GTB_REQUIRE(ring >= 1, GTB_ERR_UNSUPPORTED_DIM, "gtb_fused_mlp_f32 (tcgen05): weights do not fit in shared memory");
-  p.ring = ring;
+  const int n_slots = (int)((TC_SMEM_MAX - fixed) / TC_SLOT);
+  GTB_REQUIRE(n_slots >= 1, GTB_ERR_UNSUPPORTED_DIM, "gtb_fused_mlp_f32 (tcgen05): weights do not fit in shared memory");
+  // two teams when every team still gets two slots (one item in flight while one is consumed)
+  p.n_teams = (n_slots >= 4 && p.n_tiles > kNumSMs) ? 2 : 1;
+  p.ring = n_slots / p.n_teams;
+  if (p.ring > 4) p.ring = 4;
   if (d.n_rows == 0) return GTB_OK;
-  const size_t smem = fixed + (size_t)ring * TC_SLOT;
+  const size_t smem = fixed + (size_t)p.ring * p.n_teams * TC_SLOT;
   static bool configured = false;  // one process drives one GPU (one rank per device)
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(fused_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
@@ -656,7 +745,7 @@ int fused_mlp_tc(const gtb_mlp_desc_t& d, cudaStream_t st) {
     configured = true;
   }
   const int grid = p.n_tiles < kNumSMs ? p.n_tiles : kNumSMs;
-  fused_mlp_tc_kernel<<<grid, TC_NT, smem, st>>>(p);
+  fused_mlp_tc_kernel<<<grid, TC_TEAM * p.n_teams, smem, st>>>(p);
   GTB_CHECK_LAUNCH("fused_mlp_tc_kernel");
   return GTB_OK;
 }
