@@ -65,6 +65,7 @@ SIGNATURES = {
                                C.c_int, _vp, _vp]),
     "gtb_fused_mlp_f32": (C.c_int, [C.POINTER(MlpDesc), _vp]),
     "gtb_debug_tc_timeout": (C.c_int, [C.POINTER(C.c_int)]),
+    "gtb_debug_tc_profile": (C.c_int, [C.c_int, C.POINTER(C.c_longlong)]),
     "gtb_in_edge_forward_f32": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _i64, _i64, _vp, _vp, _vp, _vp,
                                           _i32, _i32, _i32, _i32, _vp, C.c_int, _vp, _i32, _vp, _vp]),
     "gtb_in_node_forward_f32": (C.c_int, [_vp, _i32, _i32, _vp, _i64, _i32, _i32, _i32, _i32, _vp, C.c_int,

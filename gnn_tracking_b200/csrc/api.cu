@@ -29,6 +29,7 @@ size_t tc_packed_bytes(int, const int32_t*, int, const int32_t*);
 int pack_tc(int, const int32_t*, int, const int32_t*, const float* const*, const float* const*, void*, cudaStream_t);
 int fused_mlp_tc(const gtb_mlp_desc_t&, cudaStream_t);
 int tc_timeout_flag(int*);
+int tc_profile(int, long long*);
 int ec_loss(const float*, const void*, int, int64_t, const int64_t*, const float*, float, int, float, float, float,
             double*, cudaStream_t);
 size_t oc_workspace_bytes(int64_t);
@@ -78,6 +79,7 @@ int gtb_version(void) { return 100; }
 const char* gtb_last_error(void) { return g_err; }
 
 int gtb_debug_tc_timeout(int* flag) { return tc_timeout_flag(flag); }
+int gtb_debug_tc_profile(int enable, long long* out32) { return tc_profile(enable, out32); }
 
 int gtb_arch_ok(int device) {
   cudaDeviceProp p;

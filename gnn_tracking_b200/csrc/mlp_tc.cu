@@ -34,7 +34,11 @@ constexpr int TC_HEAD = 1056;              // per team: 128 segment ids + MMA ba
 constexpr int TC_MISC = TC_HEAD + 1023;    // + slack to align the weight tiles to 1024 bytes
 constexpr uint32_t TM_A_HI = 0, TM_A_LO = 64, TM_D = 128, TM_CTX = 192;  // TMEM column map of one team
 
+constexpr int TC_IDX_IDENTITY = -1, TC_IDX_GLOBAL = -2;
+
 __device__ int g_tc_timeout = 0;
+__device__ long long g_tc_prof[32];
+static int g_prof_enabled = 0;
 
 // packed weights of one MLP: per layer the tf32 hi and lo parts as K-major [npad][32] fp32 tiles
 // (128-byte swizzle), then one 64-float bias row per layer.  Layer 0 keeps each streamed column
@@ -60,6 +64,14 @@ struct TcParams {
   int64_t n_rows;
   int32_t n_tiles, n_chunks, n_adds, n_layers, ring, ipt, n_teams;
   int8_t items[TC_MAXITEMS + 1];  // per tile, in consumption order: chunk c -> c, add a -> 64 + a, output tile -> -1
+  // row indices of the gather copies travel in registers, fetched one tile ahead by the lanes that
+  // will use them (no exposed index latency, no shared memory): per item the register slot
+  // (TC_IDX_IDENTITY: rows are the tile's own rows, TC_IDX_GLOBAL: irregular width, read on use)
+  int8_t item_ireg[TC_MAXITEMS + 1];
+  int32_t n_iregs, ireg_c4n[4];
+  const int32_t* ireg_ptr[4];
+  int32_t out_mode, out_c4n;      // same for the output rows (out_index)
+  int32_t prof;                   // debug: per-stage clock accumulation by one thread
   TcChunk ch[TC_MAXCH];
   TcAdd add[2];
   int32_t kpad[GTB_MAX_LAYERS], npad[GTB_MAX_LAYERS], ntrue[GTB_MAX_LAYERS];
@@ -217,9 +229,25 @@ __device__ __forceinline__ int64_t team_tile(const TcParams& p, int team, int t)
   return (int64_t)blockIdx.x + (int64_t)gridDim.x * ((int64_t)t * p.n_teams + team);
 }
 
+// Row index of copy slot `lane` of a warp for a block of c4n = 2^sh 16-byte pieces per row: thread
+// tt = 32 * wteam + lane issues the copies i = tt + 256 j (row i >> sh), so a warp touches the
+// rows ((32 wteam + 256 j) >> sh) + q, q < m = 32 >> sh, j < J = max(1, c4n / 2): 16 rows (32 for
+// c4n = 1).  Lane s = j * m + q fetches the index of that row; the users get it by shuffle.
+__device__ __forceinline__ int32_t tc_load_copy_index(const int32_t* arr, int c4n, int64_t row0, int rows_here,
+                                                      int wteam, int lane) {
+  const int sh = __ffs(c4n) - 1;
+  const int m = 32 >> sh;
+  const int J = c4n >= 2 ? (c4n >> 1) : 1;
+  const int j = lane >> (5 - sh), q = lane & (m - 1);
+  const int row = ((32 * wteam + 256 * j) >> sh) + q;
+  return (j < J && row < rows_here) ? __ldg(arr + row0 + row) : 0;
+}
+
 // gather one staged item (a streamed column block or a pre-projected row block) of the team's
-// sequence number g into its ring slot; every thread commits exactly one cp.async group per call
-__device__ __forceinline__ void tc_issue_item(const TcParams& p, int g, int team, unsigned char* slots, int tt) {
+// sequence number g into its ring slot; every thread commits exactly one cp.async group per call.
+// idxv: this warp's row-index register for the item's tile (see tc_load_copy_index).
+__device__ __forceinline__ void tc_issue_item(const TcParams& p, int g, int team, unsigned char* slots, int tt,
+                                              int32_t idxv) {
   const int t = g / p.ipt, k = g - t * p.ipt;
   const int64_t tile = team_tile(p, team, t);
   const int kind = p.items[k];
@@ -232,6 +260,7 @@ __device__ __forceinline__ void tc_issue_item(const TcParams& p, int g, int team
     } else {
       ptr = p.add[kind - 64].ptr; index = p.add[kind - 64].index; ld = p.add[kind - 64].ld; width = p.ntrue[0];
     }
+    const int mode = p.item_ireg[k];
     const int64_t row0 = tile * TC_TM;
     const int rows_here = (int)min((int64_t)TC_TM, p.n_rows - row0);
     const uint32_t sbase = smem_u32(slots + (size_t)(g % p.ring) * TC_SLOT);
@@ -239,23 +268,17 @@ __device__ __forceinline__ void tc_issue_item(const TcParams& p, int g, int team
     const int total = rows_here * c4n;  // <= 8 copies per thread
     const bool pow2 = (c4n & (c4n - 1)) == 0;
     const int sh = __ffs(c4n) - 1;
-    int64_t rows[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {  // row indices first: independent loads, one latency
-      const int i = tt + j * TC_TEAM;
-      rows[j] = 0;
-      if (i < total) {
-        const int r = pow2 ? (i >> sh) : (i / c4n);
-        rows[j] = index ? (int64_t)__ldg(index + row0 + r) : row0 + r;
-      }
-    }
+    const int lane = tt & 31;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int i = tt + j * TC_TEAM;
+      const int r = pow2 ? (i >> sh) : (i / c4n);
+      int64_t row = row0 + r;
+      if (mode >= 0) row = __shfl_sync(0xffffffffu, idxv, (j * (32 >> sh) + (lane >> sh)) & 31);
+      else if (mode == TC_IDX_GLOBAL && i < total) row = __ldg(index + row0 + r);
       if (i < total) {
-        const int r = pow2 ? (i >> sh) : (i / c4n);
         const int c = i - r * c4n;
-        cp_async16(sbase + slot_off(r, c), ptr + (size_t)rows[j] * ld + (c << 2));
+        cp_async16(sbase + slot_off(r, c), ptr + (size_t)row * ld + (c << 2));
       }
     }
   }
@@ -314,6 +337,15 @@ __device__ __forceinline__ void split_store16(uint32_t taddr_hi, uint32_t taddr_
   tmem_st16(taddr_lo, lo);
 }
 
+#define TC_PROF(id)                                   \
+  do {                                                \
+    if (prof_on) {                                    \
+      const long long now_ = clock64();               \
+      g_tc_prof[id] += now_ - prof_t;                 \
+      prof_t = now_;                                  \
+    }                                                 \
+  } while (0)
+
 __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   int32_t* segs_all = reinterpret_cast<int32_t*>(smem_raw);                  // [2][128]
@@ -323,16 +355,46 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
   wsm += (1024u - (smem_u32(wsm) & 1023u)) & 1023u;
   unsigned char* slots_all = wsm + ((p.w_bytes + 15u) & ~15u);  // rings of staging slots, one per team
 
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int team = tid >> 8, tt = tid & (TC_TEAM - 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int team = tid >> 8, tt = tid & (TC_TEAM - 1), wteam = tt >> 5;
   const int r = tt & (TC_TM - 1), h = tt >> 7;
   unsigned char* slots = slots_all + (size_t)team * p.ring * TC_SLOT;
   int32_t* segs = segs_all + team * TC_TM;
   uint64_t* mma_bar = bars + team;
+  const bool prof_on = p.prof != 0 && blockIdx.x == 0 && tid == 0;
+  long long prof_t = prof_on ? clock64() : 0;
+
+  // ---- row indices of the first tile: copy-type (per warp slot) and row-type (per row owner)
+  // row-type arrays: 0 = segment ids, 1 / 2 = directly read pre-projected blocks
+  const int32_t* rarr[3] = {p.seg_id, (p.n_adds > 0 && !p.add[0].staged) ? p.add[0].index : nullptr,
+                            (p.n_adds > 1 && !p.add[1].staged) ? p.add[1].index : nullptr};
+  int32_t ccur[4] = {0, 0, 0, 0}, cnext[4] = {0, 0, 0, 0};
+  int32_t rcur[3] = {0, 0, 0}, rnext[3] = {0, 0, 0};
+  {
+    const int64_t tile0 = team_tile(p, team, 0);
+    if (tile0 < p.n_tiles) {
+      const int64_t row0 = tile0 * TC_TM;
+      const int rows_here = (int)min((int64_t)TC_TM, p.n_rows - row0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (q < p.n_iregs) ccur[q] = tc_load_copy_index(p.ireg_ptr[q], p.ireg_c4n[q], row0, rows_here, wteam, lane);
+#pragma unroll
+      for (int q = 0; q < 3; ++q)
+        if (rarr[q] && r < rows_here) rcur[q] = __ldg(rarr[q] + row0 + r);
+    }
+  }
+  auto item_index = [&](int g, int t_now) -> int32_t {  // register of item g: current or next tile's
+    const int t = g / p.ipt, ir = p.item_ireg[g - t * p.ipt];
+    if (ir < 0) return 0;
+    const bool nx = t != t_now;
+    const int32_t a0 = nx ? cnext[0] : ccur[0], a1 = nx ? cnext[1] : ccur[1];
+    const int32_t a2 = nx ? cnext[2] : ccur[2], a3 = nx ? cnext[3] : ccur[3];
+    return ir == 0 ? a0 : ir == 1 ? a1 : ir == 2 ? a2 : a3;
+  };
 
   // ---- prologue: first items in flight, weights into shared memory, barriers + TMEM set-up
   int issued = 0;
-  for (; issued < p.ring; ++issued) tc_issue_item(p, issued, team, slots, tt);
+  for (; issued < p.ring; ++issued) tc_issue_item(p, issued, team, slots, tt, item_index(issued, 0));
   {
     const float4* g4 = reinterpret_cast<const float4*>(p.packed);
     float4* s4 = reinterpret_cast<float4*>(wsm);
@@ -362,6 +424,7 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
   }
   uint32_t mma_phase = 0;
   const int last = p.n_layers - 1;
+  TC_PROF(0);
 
   for (int t = 0;; ++t) {
     const int64_t tile = team_tile(p, team, t);
@@ -370,7 +433,23 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
     const int rows_here = (int)min((int64_t)TC_TM, p.n_rows - row0);
     const bool live = r < rows_here;
     int g = t * p.ipt;  // sequence number of this tile's next staged item
-    if (tt < TC_TM) segs[tt] = (live && p.seg_id) ? __ldg(p.seg_id + row0 + r) : -1;
+    if (tt < TC_TM) segs[tt] = (live && p.seg_id) ? rcur[0] : -1;
+    // indices of the NEXT tile (consumed from the end of this tile on) and of this tile's output rows
+    int32_t ocur = 0;
+    {
+      const int64_t tile_n = team_tile(p, team, t + 1);
+      if (tile_n < p.n_tiles) {
+        const int64_t row0n = tile_n * TC_TM;
+        const int rows_n = (int)min((int64_t)TC_TM, p.n_rows - row0n);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (q < p.n_iregs) cnext[q] = tc_load_copy_index(p.ireg_ptr[q], p.ireg_c4n[q], row0n, rows_n, wteam, lane);
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+          if (rarr[q] && r < rows_n) rnext[q] = __ldg(rarr[q] + row0n + r);
+      }
+      if (p.out_mode == 1) ocur = tc_load_copy_index(p.out_index, p.out_c4n, row0, rows_here, wteam, lane);
+    }
     const float rscale = (p.row_scale && live) ? __ldg(p.row_scale + row0 + r) : 1.f;
 
     // ---------------- first Linear: one streamed block at a time through the TMEM A buffer
@@ -386,6 +465,7 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
         mma_phase ^= 1;
         tc_fence_after_sync();
       }
+      TC_PROF(1);
       if (ch.staged) {
         const unsigned char* sl = slots + (size_t)(g % p.ring) * TC_SLOT;
         float4 a[4], b[4];
@@ -428,16 +508,19 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
       tmem_st_wait();
       tc_fence_before_sync();
       team_sync(team);
+      TC_PROF(2);
       if (tt == 0) {
         tc_fence_after_sync();
         tc_issue_mmas(tmc, bd_hi[0], bd_lo[0], idesc[0], (uint32_t)p.npad[0] * 8u, ch.koff, groups, c == 0);
         mma_commit(mma_bar);
       }
+      TC_PROF(3);
       if (ch.staged) {  // the slot is free: keep the ring full
-        tc_issue_item(p, issued, team, slots, tt);
+        tc_issue_item(p, issued, team, slots, tt, item_index(issued, t));
         ++issued;
         ++g;
       }
+      TC_PROF(4);
     }
 
     // ---------------- hidden layers: accumulator -> bias (+ gathered rows) -> ReLU -> next A operand
@@ -453,12 +536,14 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
       int gg = g;
       if (l == 0) {
         bool have_pre = false;
-        for (int a = 0; a < p.n_adds; ++a) {
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          if (a >= p.n_adds) break;
           if (p.add[a].staged) {
             add_sl[a] = slots + (size_t)(gg % p.ring) * TC_SLOT;
             ++gg;
           } else if (live) {
-            const int64_t row = p.add[a].index ? (int64_t)__ldg(p.add[a].index + row0 + r) : row0 + r;
+            const int64_t row = p.add[a].index ? (int64_t)rcur[1 + a] : row0 + r;
             const float* rowp = p.add[a].ptr + (size_t)row * p.add[a].ld;
             if (!have_pre) {
               have_pre = true;
@@ -473,13 +558,16 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
           }
         }
       }
+      TC_PROF(5);
       wait_or_trap(mma_bar, mma_phase);
       mma_phase ^= 1;
       tc_fence_after_sync();
+      TC_PROF(l == 0 ? 6 : 11);
       if (gg > g) {
         cp_async_wait_pending(issued - gg);
         team_sync(team);
       }
+      TC_PROF(7);
 #pragma unroll
       for (int bi = 0; bi < 2; ++bi) {  // at most two 16-column blocks per thread
         const int b = b0 + bi;
@@ -517,21 +605,25 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
       tmem_st_wait();
       tc_fence_before_sync();
       team_sync(team);
+      TC_PROF(l == 0 ? 8 : 12);
       if (tt == 0) {
         tc_fence_after_sync();
         tc_issue_mmas(tmc, bd_hi[l + 1], bd_lo[l + 1], idesc[l + 1], (uint32_t)p.npad[l + 1] * 8u, 0, p.kpad[l + 1] >> 3, true);
         mma_commit(mma_bar);
       }
+      TC_PROF(9);
       for (; g < gg; ++g) {  // the slots of the staged pre-projected blocks are free
-        tc_issue_item(p, issued, team, slots, tt);
+        tc_issue_item(p, issued, team, slots, tt, item_index(issued, t));
         ++issued;
       }
+      TC_PROF(10);
     }
 
     // ---------------- output: accumulator -> bias -> activation -> staged tile
     wait_or_trap(mma_bar, mma_phase);
     mma_phase ^= 1;
     tc_fence_after_sync();
+    TC_PROF(13);
     unsigned char* osl = slots + (size_t)(g % p.ring) * TC_SLOT;  // this item's slot was released `ring` items ago
     {
       const float* bias = reinterpret_cast<const float*>(wsm + p.b_off[last]);
@@ -557,6 +649,7 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
     }
     tc_fence_before_sync();
     team_sync(team);
+    TC_PROF(14);
 
     // ---------------- residual / scale, coalesced (scattered) row stores
     const int N = p.ntrue[last];
@@ -566,28 +659,45 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
     const bool vec = (N & 3) == 0 && (p.out == nullptr || ((p.out_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0)) &&
                      (p.res == nullptr || ((p.res_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.res) & 15) == 0));
     if (p.out != nullptr || touch) {
-      if (vec) {
-        const int c4n = N >> 2;
-        const bool pow2 = (c4n & (c4n - 1)) == 0;
+      if (vec && p.out_mode != 2) {
+        const int c4n = N >> 2;  // a power of two here (out_mode 0 / 1)
         const int sh = __ffs(c4n) - 1;
-        for (int i = tt; i < rows_here * c4n; i += TC_TEAM) {
-          const int rr = pow2 ? (i >> sh) : (i / c4n), c = i - rr * c4n;
-          float4* sp = reinterpret_cast<float4*>(osl + slot_off(rr, c));
-          float4 v = *sp;
-          if (touch) {
-            v.x *= p.res_b; v.y *= p.res_b; v.z *= p.res_b; v.w *= p.res_b;
-            if (p.res) {
-              const float4 q = __ldg(reinterpret_cast<const float4*>(p.res + (size_t)(row0 + rr) * p.res_ld) + c);
-              v.x = fmaf(p.res_a, q.x, v.x); v.y = fmaf(p.res_a, q.y, v.y);
-              v.z = fmaf(p.res_a, q.z, v.z); v.w = fmaf(p.res_a, q.w, v.w);
+        const int total = rows_here * c4n;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int i = tt + j * TC_TEAM;
+          const int rr = i >> sh, c = i & (c4n - 1);
+          int64_t orow = row0 + rr;
+          if (p.out_mode == 1) orow = __shfl_sync(0xffffffffu, ocur, (j * (32 >> sh) + (lane >> sh)) & 31);
+          if (i < total) {
+            float4* sp = reinterpret_cast<float4*>(osl + slot_off(rr, c));
+            float4 v = *sp;
+            if (touch) {
+              v.x *= p.res_b; v.y *= p.res_b; v.z *= p.res_b; v.w *= p.res_b;
+              if (p.res) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(p.res + (size_t)(row0 + rr) * p.res_ld) + c);
+                v.x = fmaf(p.res_a, q.x, v.x); v.y = fmaf(p.res_a, q.y, v.y);
+                v.z = fmaf(p.res_a, q.z, v.z); v.w = fmaf(p.res_a, q.w, v.w);
+              }
+              v.x *= oscale; v.y *= oscale; v.z *= oscale; v.w *= oscale;
+              if (want_aggr) *sp = v;
             }
-            v.x *= oscale; v.y *= oscale; v.z *= oscale; v.w *= oscale;
+            if (p.out) *(reinterpret_cast<float4*>(p.out + (size_t)orow * p.out_ld) + c) = v;
+          }
+        }
+      } else if (N == 1 && p.out_mode != 2) {  // one value per row (edge weights): thread = row
+        int64_t orow = row0 + tt;
+        if (p.out_mode == 1) orow = ocur;  // c4n = 1: every lane holds its own row
+        if (tt < rows_here) {
+          float* sp = reinterpret_cast<float*>(osl + slot_off(tt, 0));
+          float v = *sp;
+          if (touch) {
+            v *= p.res_b;
+            if (p.res) v = fmaf(p.res_a, __ldg(p.res + (size_t)(row0 + tt) * p.res_ld), v);
+            v *= oscale;
             if (want_aggr) *sp = v;
           }
-          if (p.out) {
-            const int64_t orow = p.out_index ? (int64_t)__ldg(p.out_index + row0 + rr) : row0 + rr;
-            *(reinterpret_cast<float4*>(p.out + (size_t)orow * p.out_ld) + c) = v;
-          }
+          if (p.out) p.out[(size_t)orow * p.out_ld] = v;
         }
       } else {
         for (int i = tt; i < rows_here * N; i += TC_TEAM) {
@@ -607,6 +717,7 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
         }
       }
     }
+    TC_PROF(15);
 
     // ---------------- in-tile segmented sum by destination (rows are destination-sorted): thread =
     // (column, 32-row quarter); a warp shares its quarter, so the run boundaries are warp-uniform
@@ -629,9 +740,16 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
         atomicAdd(p.aggr + (size_t)cur * p.aggr_ld + c, sum);
       }
     }
+    TC_PROF(16);
     team_sync(team);
-    tc_issue_item(p, issued, team, slots, tt);  // the output slot is free again
+    tc_issue_item(p, issued, team, slots, tt, item_index(issued, t));  // the output slot is free again
     ++issued;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) ccur[q] = cnext[q];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) rcur[q] = rnext[q];
+    TC_PROF(17);
+    if (prof_on) g_tc_prof[31] += 1;
   }
 
   cp_async_wait_pending(0);
@@ -703,6 +821,34 @@ int fused_mlp_tc(const gtb_mlp_desc_t& d, cudaStream_t st) {
   }
   p.items[n_items++] = -1;  // the output tile
   p.ipt = n_items;
+  // row-index registers of the gather copies: one per distinct (index array, pieces per row)
+  for (int k = 0; k < n_items; ++k) {
+    const int kind = p.items[k];
+    p.item_ireg[k] = TC_IDX_IDENTITY;
+    if (kind < 0) continue;
+    const int32_t* index = kind < 64 ? p.ch[kind].index : p.add[kind - 64].index;
+    const int c4n = (kind < 64 ? p.ch[kind].width : d.dims[1]) >> 2;
+    if (index == nullptr) continue;
+    p.item_ireg[k] = TC_IDX_GLOBAL;
+    if ((c4n & (c4n - 1)) != 0) continue;
+    int q = 0;
+    while (q < p.n_iregs && !(p.ireg_ptr[q] == index && p.ireg_c4n[q] == c4n)) ++q;
+    if (q == p.n_iregs) {
+      if (q == 4) continue;
+      p.ireg_ptr[q] = index;
+      p.ireg_c4n[q] = c4n;
+      ++p.n_iregs;
+    }
+    p.item_ireg[k] = (int8_t)q;
+  }
+  {
+    const int n_out = d.dims[d.n_layers];
+    const int c4n = (n_out & 3) == 0 ? n_out >> 2 : (n_out == 1 ? 1 : 0);
+    const bool regular = c4n > 0 && (c4n & (c4n - 1)) == 0;
+    p.out_c4n = regular ? c4n : 1;
+    p.out_mode = regular ? (d.out_index ? 1 : 0) : 2;
+  }
+  p.prof = g_prof_enabled;
   for (int l = 0; l < d.n_layers; ++l) {
     p.kpad[l] = L.kpad[l];
     p.npad[l] = L.npad[l];
@@ -736,6 +882,7 @@ int fused_mlp_tc(const gtb_mlp_desc_t& d, cudaStream_t st) {
   p.n_teams = (n_slots >= 4 && p.n_tiles > kNumSMs) ? 2 : 1;
   p.ring = n_slots / p.n_teams;
   if (p.ring > 4) p.ring = 4;
+  if (p.ring > p.ipt) p.ring = p.ipt;  // at most one tile of look-ahead: the index registers hold one tile
   if (d.n_rows == 0) return GTB_OK;
   const size_t smem = fixed + (size_t)p.ring * p.n_teams * TC_SLOT;
   static bool configured = false;  // one process drives one GPU (one rank per device)
@@ -748,6 +895,15 @@ int fused_mlp_tc(const gtb_mlp_desc_t& d, cudaStream_t st) {
   fused_mlp_tc_kernel<<<grid, TC_TEAM * p.n_teams, smem, st>>>(p);
   GTB_CHECK_LAUNCH("fused_mlp_tc_kernel");
   return GTB_OK;
+}
+
+int tc_profile(int enable, long long* out32) {
+  g_prof_enabled = enable;
+  if (out32 == nullptr) {
+    long long zero[32] = {0};
+    return check_cuda(cudaMemcpyToSymbol(g_tc_prof, zero, sizeof(zero)), "cudaMemcpyToSymbol(g_tc_prof)");
+  }
+  return check_cuda(cudaMemcpyFromSymbol(out32, g_tc_prof, 32 * sizeof(long long)), "cudaMemcpyFromSymbol(g_tc_prof)");
 }
 
 int tc_timeout_flag(int* out) {

@@ -166,6 +166,10 @@ int gtb_fused_mlp_f32(const gtb_mlp_desc_t* desc, void* stream);
 /* Test hook (synchronises): *flag != 0 if a tcgen05 kernel ever gave up waiting for its MMA
  * barrier -- such a kernel traps, so the CUDA error is sticky as well. */
 int gtb_debug_tc_timeout(int* flag);
+/* Test hook (synchronises): per-stage clock accumulation of the tcgen05 kernel by thread 0 of CTA 0.
+ * out32 == NULL: set the enable flag for later launches and zero the counters; else copy the 32
+ * counters out (see tests/cuda/tc_diag.py for the stage names). */
+int gtb_debug_tc_profile(int enable, long long* out32);
 
 /* ------------------------------------------------------------- IN layer wrappers
  * One Interaction-Network layer (interaction_network.py:54-103) on a planned graph.

@@ -8,6 +8,7 @@ does not hide the cases behind it:
 """
 from __future__ import annotations
 
+import os
 import subprocess
 import sys
 from pathlib import Path
@@ -130,6 +131,20 @@ def run_case(i: int) -> None:
                 ev1.record()
                 torch.cuda.synchronize()
                 msg += f" {ev0.elapsed_time(ev1) / 5 * 1e3:.0f}us"
+                if os.environ.get("TC_PROF"):
+                    L = _lib.lib()
+                    L.gtb_debug_tc_profile(1, None)
+                    ops.fused_mlp(blocks, n, packed, **kw)
+                    torch.cuda.synchronize()
+                    buf = (_lib.C.c_longlong * 32)()
+                    L.gtb_debug_tc_profile(0, buf)
+                    tiles = max(1, buf[31])
+                    names = ["prologue", "wait chunk", "convert", "mma issue", "issue item", "pre loads", "mma wait l0",
+                             "wait add", "epilogue l0", "mma issue", "issue add", "mma wait l>0", "epilogue l>0",
+                             "mma wait out", "epilogue out", "store", "aggregate", "tail"]
+                    msg += "\n    prof (cycles per tile of team 0 / CTA 0, %d tiles): " % tiles + ", ".join(
+                        f"{nm} {buf[i] / (1 if i == 0 else tiles):.0f}" for i, nm in enumerate(names))
+                    msg += f" | total/tile {sum(buf[1:18]) / tiles:.0f}"
             line.append(msg)
         except Exception as e:  # noqa: BLE001
             line.append(f"{iname}: EXC {type(e).__name__}: {str(e)[:150]}")
