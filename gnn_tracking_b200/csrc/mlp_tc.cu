@@ -25,7 +25,6 @@ namespace gtb {
 using namespace tc;
 
 constexpr int TC_TM = 128;                 // rows per tile = UMMA M
-constexpr int TC_NT = 256;                 // threads: (row = tid & 127, column half = tid >> 7)
 constexpr int TC_SLOT = TC_TM * 256;       // one staging slot: [128 rows][64 fp32], 16-byte chunks ^ (row & 7)
 constexpr int TC_MAXCH = 8;                // streamed sub-blocks (<= 64 columns each) of the first Linear
 constexpr int TC_MAXITEMS = TC_MAXCH + 3;
@@ -208,107 +207,207 @@ int pack_tc(int n_layers, const int32_t* dims, int n_chunks, const int32_t* chun
 // team), its ring of staging slots, its TMEM columns and its MMA barrier, and synchronises on a
 // named barrier only -- so one team's MMA chain and load latency overlap the other team's
 // epilogue / conversion work on the same SM, with the packed weights shared.
+//
+// Code-generation notes (measured with ncu, profiles/README.md): the tile loop is issue-bound, so
+// shared memory is addressed with 32-bit shared-window addresses (no generic-pointer arithmetic),
+// ring positions are counted, never divided, and row offsets are 32 x 32 -> 64-bit multiplies.
 constexpr int TC_TEAM = 256;
 
 __device__ __forceinline__ void team_sync(int team) {
   asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(TC_TEAM) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float lds32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ int32_t lds_i32(uint32_t a) {
+  int32_t v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_i32(uint32_t a, int32_t v) {
+  asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+// row `row` of a table with a row pitch of ld4 BYTES: one 32 x 32 -> 64-bit multiply-add
+__device__ __forceinline__ const float* row_ptr(const float* base, uint32_t row, uint32_t ld4) {
+  return reinterpret_cast<const float*>(reinterpret_cast<const char*>(base) + (uint64_t)row * ld4);
 }
 
 __device__ __forceinline__ uint32_t slot_off(int r, int c4) {  // 16-byte chunk c4 of row r
   return (uint32_t)(r * 256 + ((c4 ^ (r & 7)) << 4));
 }
 
-__device__ __forceinline__ void wait_or_trap(uint64_t* bar, uint32_t parity) {
-  if (!mbar_wait(bar, parity, 20000000u)) {
-    atomicExch(&g_tc_timeout, 1);
-    __trap();  // a wrong descriptor must fail loudly, never hang the GPU or return garbage
+__device__ __forceinline__ void wait_or_trap(uint32_t bar_addr, uint32_t parity) {
+  for (uint32_t i = 0; i < 20000000u; ++i) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar_addr), "r"(parity)
+        : "memory");
+    if (ok) return;
   }
+  atomicExch(&g_tc_timeout, 1);
+  __trap();  // a wrong descriptor must fail loudly, never hang the GPU or return garbage
 }
 
-__device__ __forceinline__ int64_t team_tile(const TcParams& p, int team, int t) {
-  return (int64_t)blockIdx.x + (int64_t)gridDim.x * ((int64_t)t * p.n_teams + team);
+__device__ __forceinline__ int team_tile(const TcParams& p, int team, int t) {
+  return (int)blockIdx.x + (int)gridDim.x * (t * p.n_teams + team);
 }
 
-// Row index of copy slot `lane` of a warp for a block of c4n = 2^sh 16-byte pieces per row: thread
-// tt = 32 * wteam + lane issues the copies i = tt + 256 j (row i >> sh), so a warp touches the
-// rows ((32 wteam + 256 j) >> sh) + q, q < m = 32 >> sh, j < J = max(1, c4n / 2): 16 rows (32 for
-// c4n = 1).  Lane s = j * m + q fetches the index of that row; the users get it by shuffle.
-__device__ __forceinline__ int32_t tc_load_copy_index(const int32_t* arr, int c4n, int64_t row0, int rows_here,
-                                                      int wteam, int lane) {
+// Row (inside the tile) whose index copy slot `lane` of warp `wteam` holds, for a block of
+// c4n = 2^sh 16-byte pieces per row, or -1: thread tt = 32 wteam + lane issues the copies
+// i = tt + 256 j (row i >> sh), so a warp touches the rows ((32 wteam + 256 j) >> sh) + q,
+// q < m = 32 >> sh, j < J = max(1, c4n / 2): 16 rows (32 for c4n = 1); lane s = j m + q.
+__device__ __forceinline__ int tc_copy_slot_row(int c4n, int wteam, int lane) {
   const int sh = __ffs(c4n) - 1;
   const int m = 32 >> sh;
   const int J = c4n >= 2 ? (c4n >> 1) : 1;
   const int j = lane >> (5 - sh), q = lane & (m - 1);
-  const int row = ((32 * wteam + 256 * j) >> sh) + q;
-  return (j < J && row < rows_here) ? __ldg(arr + row0 + row) : 0;
+  return j < J ? ((32 * wteam + 256 * j) >> sh) + q : -1;
 }
 
-// gather one staged item (a streamed column block or a pre-projected row block) of the team's
-// sequence number g into its ring slot; every thread commits exactly one cp.async group per call.
-// idxv: this warp's row-index register for the item's tile (see tc_load_copy_index).
-__device__ __forceinline__ void tc_issue_item(const TcParams& p, int g, int team, unsigned char* slots, int tt,
-                                              int32_t idxv) {
-  const int t = g / p.ipt, k = g - t * p.ipt;
-  const int64_t tile = team_tile(p, team, t);
+// gather one staged item (kind: streamed block c -> c, pre-projected block a -> 64 + a, output
+// tile -> -1) of team tile `tile` into the slot at shared address `sdst`; every thread commits
+// exactly one cp.async group per call.  idxv: this warp's row-index register for that tile.
+// W64: the block is 64 columns wide: thread tt copies piece (tt & 15) of the rows (tt >> 4) + 16 j,
+// whose slot addresses differ by a constant 4096 bytes.
+template <bool W64>
+__device__ __forceinline__ void tc_issue_item(const TcParams& p, int tile, int k, uint32_t sdst, int tt, int32_t idxv) {
   const int kind = p.items[k];
   if (tile < p.n_tiles && kind >= 0) {
     const float* ptr;
     const int32_t* index;
-    int ld, width;
+    uint32_t ld4;
+    int width;
     if (kind < 64) {
-      ptr = p.ch[kind].ptr; index = p.ch[kind].index; ld = p.ch[kind].ld; width = p.ch[kind].width;
+      ptr = p.ch[kind].ptr; index = p.ch[kind].index; ld4 = (uint32_t)p.ch[kind].ld * 4u; width = p.ch[kind].width;
     } else {
-      ptr = p.add[kind - 64].ptr; index = p.add[kind - 64].index; ld = p.add[kind - 64].ld; width = p.ntrue[0];
+      ptr = p.add[kind - 64].ptr; index = p.add[kind - 64].index; ld4 = (uint32_t)p.add[kind - 64].ld * 4u; width = p.ntrue[0];
     }
     const int mode = p.item_ireg[k];
-    const int64_t row0 = tile * TC_TM;
-    const int rows_here = (int)min((int64_t)TC_TM, p.n_rows - row0);
-    const uint32_t sbase = smem_u32(slots + (size_t)(g % p.ring) * TC_SLOT);
-    const int c4n = width >> 2;
-    const int total = rows_here * c4n;  // <= 8 copies per thread
-    const bool pow2 = (c4n & (c4n - 1)) == 0;
-    const int sh = __ffs(c4n) - 1;
+    const uint32_t row0 = (uint32_t)tile * TC_TM;
+    const int rows_here = (int)min((int64_t)TC_TM, p.n_rows - (int64_t)row0);
     const int lane = tt & 31;
+    if (W64) {
+      const int rb = tt >> 4, c = tt & 15;
+      const uint32_t d0 = sdst + slot_off(rb, c);  // rows rb + 16 j share (row & 7): same swizzle
+      const float* src0 = ptr + (c << 2);
+      if (mode >= 0) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int i = tt + j * TC_TEAM;
-      const int r = pow2 ? (i >> sh) : (i / c4n);
-      int64_t row = row0 + r;
-      if (mode >= 0) row = __shfl_sync(0xffffffffu, idxv, (j * (32 >> sh) + (lane >> sh)) & 31);
-      else if (mode == TC_IDX_GLOBAL && i < total) row = __ldg(index + row0 + r);
-      if (i < total) {
-        const int c = i - r * c4n;
-        cp_async16(sbase + slot_off(r, c), ptr + (size_t)row * ld + (c << 2));
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t row = (uint32_t)__shfl_sync(0xffffffffu, idxv, 2 * j + (lane >> 4));
+          if (rb + 16 * j < rows_here) cp_async16(d0 + j * 4096, row_ptr(src0, row, ld4));
+        }
+      } else if (mode == TC_IDX_IDENTITY) {
+        const float* s = row_ptr(src0, row0 + rb, ld4);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (rb + 16 * j < rows_here) cp_async16(d0 + j * 4096, reinterpret_cast<const char*>(s) + (uint64_t)(16 * j) * ld4);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (rb + 16 * j < rows_here)
+            cp_async16(d0 + j * 4096, row_ptr(src0, (uint32_t)__ldg(index + row0 + rb + 16 * j), ld4));
+      }
+    } else {
+      const int c4n = width >> 2;
+      const int total = rows_here * c4n;  // <= 8 copies per thread
+      const bool pow2 = (c4n & (c4n - 1)) == 0;
+      const int sh = __ffs(c4n) - 1;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int i = tt + j * TC_TEAM;
+        const int r = pow2 ? (i >> sh) : (i / c4n);
+        uint32_t row = row0 + r;
+        if (mode >= 0) row = (uint32_t)__shfl_sync(0xffffffffu, idxv, (j * (32 >> sh) + (lane >> sh)) & 31);
+        else if (mode == TC_IDX_GLOBAL && i < total) row = (uint32_t)__ldg(index + row0 + r);
+        if (i < total) {
+          const int c = i - r * c4n;
+          cp_async16(sdst + slot_off(r, c), row_ptr(ptr + (c << 2), row, ld4));
+        }
       }
     }
   }
   cp_async_commit();
 }
 
+// Issued by the WHOLE first warp of a team with warp-uniform operands (kernel parameters, loop
+// counters, the team number as a template constant, TMEM base 0): ptxas then keeps descriptors and
+// addresses in uniform registers and emits one UTCHMMA per step.  Issued from a divergent branch
+// (`if (tid == 0)`) the same code becomes an ELECT / 6 x R2UR / UTCHMMA / BRA.U.ANY waterfall loop
+// that costs ~150 cycles per MMA -- 5x the 32 cycles the tensor core needs for M=128, N=64, K=8
+// (profiles/r1_tc_mma_bench.log).  One elected lane executes the MMA itself.
+__device__ __forceinline__ void mma_tf32_ts_elect(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                                  uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred pe, pacc;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pacc, %4, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, pacc;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_elect(uint32_t bar_smem) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar_smem)
+      : "memory");
+}
+
 // three passes (small terms first: lo*hi, hi*lo, hi*hi) over `ksteps` K = 8 steps of one streamed
-// block (first Linear) or of a whole hidden Linear; descriptors advance by plain adds
-__device__ __forceinline__ void tc_issue_mmas(uint32_t tmc, uint64_t bd_hi, uint64_t bd_lo, uint32_t idesc,
-                                              uint32_t tile16, int koff, int ksteps, bool first) {
-  bool acc = !first;
+// block (first Linear) or of a whole hidden Linear, then the commit onto the team's barrier.
+// K64: the block / layer is exactly 64 wide and starts on a K-tile boundary: 8 unrolled steps.
+template <int TEAM, bool K64>
+__device__ __forceinline__ void tc_issue_mmas(uint32_t wbase, uint32_t bar_base, const TcParams& p, int l, int koff,
+                                              int ksteps, bool first) {
+  constexpr uint32_t tmc = TEAM * TM_CTX;  // TMEM base is 0: the CTA owns the SM's tensor memory (checked at start)
+  const uint32_t idesc = make_idesc_tf32(TC_TM, p.npad[l]);
+  const uint32_t tile16 = (uint32_t)p.npad[l] * 8u;  // bytes of one [npad][32] K tile >> 4
   const uint32_t boff = (uint32_t)(koff >> 5) * tile16 + (uint32_t)((koff & 31) >> 3) * 2u;
+  uint32_t acc = first ? 0u : 1u;
 #pragma unroll 1
   for (int pass = 0; pass < 3; ++pass) {
     uint32_t a = tmc + ((pass == 0) ? TM_A_LO : TM_A_HI);
-    uint64_t bd = ((pass == 1) ? bd_lo : bd_hi) + boff;
-    int sub = (koff & 31) >> 3;
+    uint64_t bd = make_smem_desc_sw128(wbase + p.w_off[l][pass == 1 ? 1 : 0]) + boff;
+    if (K64) {
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        mma_tf32_ts_elect(tmc + TM_D, a + 8 * ks, bd + (uint64_t)((ks >> 2) * tile16 + (ks & 3) * 2), idesc, acc);
+        acc = 1u;
+      }
+    } else {
+      int sub = (koff & 31) >> 3;
 #pragma unroll 1
-    for (int ks = 0; ks < ksteps; ++ks) {
-      mma_tf32_ts(tmc + TM_D, a, bd, idesc, acc);
-      acc = true;
-      a += 8;
-      if (++sub == 4) {
-        sub = 0;
-        bd += tile16 - 6;  // next 32-wide K tile
-      } else {
-        bd += 2;           // +32 bytes inside the swizzled tile
+      for (int ks = 0; ks < ksteps; ++ks) {
+        mma_tf32_ts_elect(tmc + TM_D, a, bd, idesc, acc);
+        acc = 1u;
+        a += 8;
+        if (++sub == 4) {
+          sub = 0;
+          bd += tile16 - 6;  // next 32-wide K tile
+        } else {
+          bd += 2;           // +32 bytes inside the swizzled tile
+        }
       }
     }
   }
+  mma_commit_elect(bar_base + TEAM * 8);
 }
 
 __device__ __forceinline__ void split_store8(uint32_t taddr_hi, uint32_t taddr_lo, const float (&v)[8]) {
@@ -339,69 +438,95 @@ __device__ __forceinline__ void split_store16(uint32_t taddr_hi, uint32_t taddr_
 
 #define TC_PROF(id)                                   \
   do {                                                \
-    if (prof_on) {                                    \
+    if (PROF && prof_on) {                            \
       const long long now_ = clock64();               \
       g_tc_prof[id] += now_ - prof_t;                 \
       prof_t = now_;                                  \
     }                                                 \
   } while (0)
 
+// W64: every streamed block, every hidden Linear and every pre-projected block is exactly 64 wide
+// (the "wide" Interaction-Network configuration): straight-line tile code without width guards.
+// PROF: per-stage clock accumulation by thread 0 of CTA 0 (tests/cuda/tc_diag.py).
+template <bool W64, bool PROF>
 __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  int32_t* segs_all = reinterpret_cast<int32_t*>(smem_raw);                  // [2][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(segs_all + 2 * TC_TM);         // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
-  unsigned char* wsm = smem_raw + TC_HEAD;                     // packed weights + biases (1024-aligned tiles)
-  wsm += (1024u - (smem_u32(wsm) & 1023u)) & 1023u;
-  unsigned char* slots_all = wsm + ((p.w_bytes + 15u) & ~15u);  // rings of staging slots, one per team
+  const uint32_t sm0 = smem_u32(smem_raw);
+  // [2][128] segment ids | [2] MMA barriers | TMEM slot | (pad to 1024) weights | slot rings
+  const uint32_t wbase = (sm0 + TC_HEAD + 1023u) & ~1023u;
+  unsigned char* wsm = smem_raw + (wbase - sm0);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int team = tid >> 8, tt = tid & (TC_TEAM - 1), wteam = tt >> 5;
   const int r = tt & (TC_TM - 1), h = tt >> 7;
-  unsigned char* slots = slots_all + (size_t)team * p.ring * TC_SLOT;
-  int32_t* segs = segs_all + team * TC_TM;
-  uint64_t* mma_bar = bars + team;
-  const bool prof_on = p.prof != 0 && blockIdx.x == 0 && tid == 0;
+  const uint32_t ring = (uint32_t)p.ring;
+  const uint32_t slots = wbase + ((p.w_bytes + 15u) & ~15u) + (uint32_t)team * ring * TC_SLOT;  // this team's ring
+  const uint32_t segs = sm0 + (uint32_t)team * (TC_TM * 4);
+  const uint32_t bar_base = sm0 + 2 * TC_TM * 4;
+  const uint32_t mma_bar = bar_base + team * 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 2 * TC_TM * 4 + 16);
+  const uint32_t rsw = (uint32_t)r * 256u, rx = (uint32_t)(r & 7) << 4;  // own row in a slot: rsw + ((c4 << 4) ^ rx)
+  const bool prof_on = PROF && blockIdx.x == 0 && tid == 0;
   long long prof_t = prof_on ? clock64() : 0;
 
-  // ---- row indices of the first tile: copy-type (per warp slot) and row-type (per row owner)
-  // row-type arrays: 0 = segment ids, 1 / 2 = directly read pre-projected blocks
+  // ---- row indices: copy-type (per warp slot, see tc_copy_slot_row) and row-type (per row owner;
+  // arrays: 0 = segment ids, 1 / 2 = directly read pre-projected blocks), first tile now, then
+  // always one tile ahead
   const int32_t* rarr[3] = {p.seg_id, (p.n_adds > 0 && !p.add[0].staged) ? p.add[0].index : nullptr,
                             (p.n_adds > 1 && !p.add[1].staged) ? p.add[1].index : nullptr};
+  int crow[4], orow_slot = -1;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) crow[q] = q < p.n_iregs ? tc_copy_slot_row(p.ireg_c4n[q], wteam, lane) : -1;
+  if (p.out_mode == 1) orow_slot = tc_copy_slot_row(p.out_c4n, wteam, lane);
   int32_t ccur[4] = {0, 0, 0, 0}, cnext[4] = {0, 0, 0, 0};
   int32_t rcur[3] = {0, 0, 0}, rnext[3] = {0, 0, 0};
   {
-    const int64_t tile0 = team_tile(p, team, 0);
+    const int tile0 = team_tile(p, team, 0);
     if (tile0 < p.n_tiles) {
-      const int64_t row0 = tile0 * TC_TM;
-      const int rows_here = (int)min((int64_t)TC_TM, p.n_rows - row0);
+      const uint32_t row0 = (uint32_t)tile0 * TC_TM;
+      const int rows_here = (int)min((int64_t)TC_TM, p.n_rows - (int64_t)row0);
 #pragma unroll
       for (int q = 0; q < 4; ++q)
-        if (q < p.n_iregs) ccur[q] = tc_load_copy_index(p.ireg_ptr[q], p.ireg_c4n[q], row0, rows_here, wteam, lane);
+        if (crow[q] >= 0 && crow[q] < rows_here) ccur[q] = __ldg(p.ireg_ptr[q] + row0 + crow[q]);
 #pragma unroll
       for (int q = 0; q < 3; ++q)
         if (rarr[q] && r < rows_here) rcur[q] = __ldg(rarr[q] + row0 + r);
     }
   }
-  auto item_index = [&](int g, int t_now) -> int32_t {  // register of item g: current or next tile's
-    const int t = g / p.ipt, ir = p.item_ireg[g - t * p.ipt];
-    if (ir < 0) return 0;
-    const bool nx = t != t_now;
-    const int32_t a0 = nx ? cnext[0] : ccur[0], a1 = nx ? cnext[1] : ccur[1];
-    const int32_t a2 = nx ? cnext[2] : ccur[2], a3 = nx ? cnext[3] : ccur[3];
-    return ir == 0 ? a0 : ir == 1 ? a1 : ir == 2 ? a2 : a3;
+  // ring bookkeeping without divisions: next item to issue (tile sequence, kind position, slot)
+  int iss_t = 0, iss_k = 0, issued = 0, consumed = 0;
+  uint32_t iss_slot = 0, cons_slot = 0;
+  auto issue_next = [&](int t_now) {
+    const int ir = p.item_ireg[iss_k];
+    int32_t idxv = 0;
+    if (ir >= 0) {
+      const bool nx = iss_t != t_now;
+      const int32_t a0 = nx ? cnext[0] : ccur[0], a1 = nx ? cnext[1] : ccur[1];
+      const int32_t a2 = nx ? cnext[2] : ccur[2], a3 = nx ? cnext[3] : ccur[3];
+      idxv = ir == 0 ? a0 : ir == 1 ? a1 : ir == 2 ? a2 : a3;
+    }
+    tc_issue_item<W64>(p, team_tile(p, team, iss_t), iss_k, slots + iss_slot * TC_SLOT, tt, idxv);
+    ++issued;
+    if (++iss_slot == ring) iss_slot = 0;
+    if (++iss_k == p.ipt) {
+      iss_k = 0;
+      ++iss_t;
+    }
+  };
+  auto consume_done = [&]() {  // the item in cons_slot has been read by every thread of the team
+    ++consumed;
+    if (++cons_slot == ring) cons_slot = 0;
   };
 
   // ---- prologue: first items in flight, weights into shared memory, barriers + TMEM set-up
-  int issued = 0;
-  for (; issued < p.ring; ++issued) tc_issue_item(p, issued, team, slots, tt, item_index(issued, 0));
+  for (int i = 0; i < p.ring; ++i) issue_next(0);
   {
     const float4* g4 = reinterpret_cast<const float4*>(p.packed);
     float4* s4 = reinterpret_cast<float4*>(wsm);
     for (int i = tid; i < (int)(p.w_bytes >> 4); i += blockDim.x) s4[i] = __ldg(g4 + i);
   }
   if (tt == 0) {
-    mbar_init(mma_bar, 1);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mma_bar), "r"(1) : "memory");
     fence_barrier_init();
   }
   const uint32_t tmem_cols = p.n_teams == 2 ? 512u : 256u;
@@ -411,44 +536,38 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tm = *tmem_slot;
-  const uint32_t tmc = tm + (uint32_t)team * TM_CTX;                        // this team's TMEM columns
-  const uint32_t tm_lane = tmc + ((uint32_t)((warp & 3) * 32) << 16);      // + this warp's 32 lanes
-  const uint32_t wbase = smem_u32(wsm);
-  uint64_t bd_hi[GTB_MAX_LAYERS], bd_lo[GTB_MAX_LAYERS];
-  uint32_t idesc[GTB_MAX_LAYERS];
-#pragma unroll
-  for (int l = 0; l < GTB_MAX_LAYERS; ++l) {
-    bd_hi[l] = make_smem_desc_sw128(wbase + p.w_off[l][0]);
-    bd_lo[l] = make_smem_desc_sw128(wbase + p.w_off[l][1]);
-    idesc[l] = make_idesc_tf32(TC_TM, p.npad[l] > 0 ? p.npad[l] : 16);
+  if (tm != 0) {  // one CTA per SM and one allocation: the base is column 0 / lane 0; the MMA issue relies on it
+    atomicExch(&g_tc_timeout, 2);
+    __trap();
   }
+  const uint32_t tmc = (uint32_t)team * TM_CTX;                             // this team's TMEM columns
+  const uint32_t tm_lane = tmc + ((uint32_t)((warp & 3) * 32) << 16);      // + this warp's 32 lanes
   uint32_t mma_phase = 0;
   const int last = p.n_layers - 1;
   TC_PROF(0);
 
   for (int t = 0;; ++t) {
-    const int64_t tile = team_tile(p, team, t);
+    const int tile = team_tile(p, team, t);
     if (tile >= p.n_tiles) break;
-    const int64_t row0 = tile * TC_TM;
-    const int rows_here = (int)min((int64_t)TC_TM, p.n_rows - row0);
+    const uint32_t row0 = (uint32_t)tile * TC_TM;
+    const int rows_here = (int)min((int64_t)TC_TM, p.n_rows - (int64_t)row0);
     const bool live = r < rows_here;
-    int g = t * p.ipt;  // sequence number of this tile's next staged item
-    if (tt < TC_TM) segs[tt] = (live && p.seg_id) ? rcur[0] : -1;
+    if (tt < TC_TM) sts_i32(segs + tt * 4, (live && p.seg_id) ? rcur[0] : -1);
     // indices of the NEXT tile (consumed from the end of this tile on) and of this tile's output rows
     int32_t ocur = 0;
     {
-      const int64_t tile_n = team_tile(p, team, t + 1);
+      const int tile_n = team_tile(p, team, t + 1);
       if (tile_n < p.n_tiles) {
-        const int64_t row0n = tile_n * TC_TM;
-        const int rows_n = (int)min((int64_t)TC_TM, p.n_rows - row0n);
+        const uint32_t row0n = (uint32_t)tile_n * TC_TM;
+        const int rows_n = (int)min((int64_t)TC_TM, p.n_rows - (int64_t)row0n);
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          if (q < p.n_iregs) cnext[q] = tc_load_copy_index(p.ireg_ptr[q], p.ireg_c4n[q], row0n, rows_n, wteam, lane);
+          if (crow[q] >= 0 && crow[q] < rows_n) cnext[q] = __ldg(p.ireg_ptr[q] + row0n + crow[q]);
 #pragma unroll
         for (int q = 0; q < 3; ++q)
           if (rarr[q] && r < rows_n) rnext[q] = __ldg(rarr[q] + row0n + r);
       }
-      if (p.out_mode == 1) ocur = tc_load_copy_index(p.out_index, p.out_c4n, row0, rows_here, wteam, lane);
+      if (orow_slot >= 0 && orow_slot < rows_here) ocur = __ldg(p.out_index + row0 + orow_slot);
     }
     const float rscale = (p.row_scale && live) ? __ldg(p.row_scale + row0 + r) : 1.f;
 
@@ -457,7 +576,7 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
       const TcChunk& ch = p.ch[c];
       const int groups = ch.kpad >> 3;
       if (ch.staged) {
-        cp_async_wait_pending(issued - g - 1);
+        cp_async_wait_pending(issued - consumed - 1);
         team_sync(team);
       }
       if (c > 0) {  // the previous block's MMAs still read the A buffer
@@ -467,32 +586,34 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
       }
       TC_PROF(1);
       if (ch.staged) {
-        const unsigned char* sl = slots + (size_t)(g % p.ring) * TC_SLOT;
+        const uint32_t sl = slots + cons_slot * TC_SLOT + rsw;
+        const float clamp = ch.relu ? 0.f : -INFINITY;  // relu on load (layers > 0 of a residual stack)
         float4 a[4], b[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int c4 = 2 * (h + 2 * q);
           a[q] = make_float4(0.f, 0.f, 0.f, 0.f);
           b[q] = a[q];
-          if (c4 * 4 < ch.width) a[q] = *reinterpret_cast<const float4*>(sl + slot_off(r, c4));
-          if ((c4 + 1) * 4 < ch.width) b[q] = *reinterpret_cast<const float4*>(sl + slot_off(r, c4 + 1));
+          if (W64 || c4 * 4 < ch.width) a[q] = lds128(sl + (((uint32_t)c4 << 4) ^ rx));
+          if (W64 || (c4 + 1) * 4 < ch.width) b[q] = lds128(sl + (((uint32_t)(c4 + 1) << 4) ^ rx));
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int g8 = h + 2 * q;
-          if (g8 < groups) {
+          if (W64 || g8 < groups) {
             float v[8] = {a[q].x, a[q].y, a[q].z, a[q].w, b[q].x, b[q].y, b[q].z, b[q].w};
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              if (ch.relu) v[j] = fmaxf(v[j], 0.f);
-              v[j] *= rscale;
+            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], clamp);
+            if (p.row_scale) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] *= rscale;
             }
             split_store8(tm_lane + TM_A_HI + 8 * g8, tm_lane + TM_A_LO + 8 * g8, v);
           }
         }
       } else if (h == 0) {  // narrow block: the row owner reads its own elements
-        const int64_t row = live ? (ch.index ? (int64_t)__ldg(ch.index + row0 + r) : row0 + r) : 0;
-        const float* src = ch.ptr + (size_t)row * ch.ld;
+        const uint32_t row = live ? (ch.index ? (uint32_t)__ldg(ch.index + row0 + r) : row0 + r) : 0u;
+        const float* src = row_ptr(ch.ptr, row, (uint32_t)ch.ld * 4u);
         for (int g8 = 0; g8 < groups; ++g8) {
           float v[8];
 #pragma unroll
@@ -509,16 +630,15 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
       tc_fence_before_sync();
       team_sync(team);
       TC_PROF(2);
-      if (tt == 0) {
+      if (wteam == 0) {  // whole warp, uniform operands (see tc_issue_mmas)
         tc_fence_after_sync();
-        tc_issue_mmas(tmc, bd_hi[0], bd_lo[0], idesc[0], (uint32_t)p.npad[0] * 8u, ch.koff, groups, c == 0);
-        mma_commit(mma_bar);
+        if (team == 0) tc_issue_mmas<0, W64>(wbase, bar_base, p, 0, ch.koff, groups, c == 0);
+        else           tc_issue_mmas<1, W64>(wbase, bar_base, p, 0, ch.koff, groups, c == 0);
       }
       TC_PROF(3);
       if (ch.staged) {  // the slot is free: keep the ring full
-        tc_issue_item(p, issued, team, slots, tt, item_index(issued, t));
-        ++issued;
-        ++g;
+        consume_done();
+        issue_next(t);
       }
       TC_PROF(4);
     }
@@ -526,31 +646,33 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
     // ---------------- hidden layers: accumulator -> bias (+ gathered rows) -> ReLU -> next A operand
     for (int l = 0; l < last; ++l) {
       const float* bias = reinterpret_cast<const float*>(wsm + p.b_off[l]);
-      const int nb = p.npad[l] >> 4, per = (nb + 1) >> 1;
-      const int b0 = h * per, b1 = min(nb, b0 + per);
-      const unsigned char* add_sl[2] = {nullptr, nullptr};
+      const int nb = W64 ? 4 : (p.npad[l] >> 4), per = (nb + 1) >> 1;
+      const int b0 = h * per, b1 = W64 ? b0 + 2 : min(nb, b0 + per);
+      uint32_t add_sl[2] = {0u, 0u};         // staged pre-projected blocks: own row in their slots
       const float* add_row[2] = {nullptr, nullptr};
       float4 pre[8];  // the row owner's columns of the first directly read block, fetched under the MMA
 #pragma unroll
       for (int q = 0; q < 8; ++q) pre[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-      int gg = g;
+      int n_staged = 0;
       if (l == 0) {
         bool have_pre = false;
+        uint32_t s = cons_slot;
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
           if (a >= p.n_adds) break;
           if (p.add[a].staged) {
-            add_sl[a] = slots + (size_t)(gg % p.ring) * TC_SLOT;
-            ++gg;
+            add_sl[a] = slots + s * TC_SLOT + rsw;
+            if (++s == ring) s = 0;
+            ++n_staged;
           } else if (live) {
-            const int64_t row = p.add[a].index ? (int64_t)rcur[1 + a] : row0 + r;
-            const float* rowp = p.add[a].ptr + (size_t)row * p.add[a].ld;
+            const uint32_t row = p.add[a].index ? (uint32_t)rcur[1 + a] : row0 + r;
+            const float* rowp = row_ptr(p.add[a].ptr, row, (uint32_t)p.add[a].ld * 4u);
             if (!have_pre) {
               have_pre = true;
 #pragma unroll
               for (int q = 0; q < 8; ++q) {
                 const int c4 = 4 * b0 + q;
-                if (q < 4 * (b1 - b0) && c4 * 4 < p.ntrue[0]) pre[q] = __ldg(reinterpret_cast<const float4*>(rowp) + c4);
+                if (W64 || (q < 4 * (b1 - b0) && c4 * 4 < p.ntrue[0])) pre[q] = __ldg(reinterpret_cast<const float4*>(rowp) + c4);
               }
             } else {
               add_row[a] = rowp;
@@ -563,15 +685,15 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
       mma_phase ^= 1;
       tc_fence_after_sync();
       TC_PROF(l == 0 ? 6 : 11);
-      if (gg > g) {
-        cp_async_wait_pending(issued - gg);
+      if (n_staged > 0) {
+        cp_async_wait_pending(issued - consumed - n_staged);
         team_sync(team);
       }
       TC_PROF(7);
 #pragma unroll
       for (int bi = 0; bi < 2; ++bi) {  // at most two 16-column blocks per thread
         const int b = b0 + bi;
-        if (b >= b1) break;
+        if (!W64 && b >= b1) break;
         uint32_t acc[16];
         tmem_ld16(tm_lane + TM_D + 16 * b, acc);
         tmem_ld_wait();
@@ -586,13 +708,14 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
           }
 #pragma unroll
           for (int a = 0; a < 2; ++a) {
+            if (add_sl[a] == 0u && add_row[a] == nullptr) continue;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const int c4 = 4 * b + q;
               float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (c4 * 4 < p.ntrue[0]) {
-                if (add_sl[a]) x = *reinterpret_cast<const float4*>(add_sl[a] + slot_off(r, c4));
-                else if (add_row[a]) x = __ldg(reinterpret_cast<const float4*>(add_row[a]) + c4);
+              if (W64 || c4 * 4 < p.ntrue[0]) {
+                if (add_sl[a]) x = lds128(add_sl[a] + (((uint32_t)c4 << 4) ^ rx));
+                else x = __ldg(reinterpret_cast<const float4*>(add_row[a]) + c4);
               }
               v[4 * q + 0] += x.x; v[4 * q + 1] += x.y; v[4 * q + 2] += x.z; v[4 * q + 3] += x.w;
             }
@@ -606,15 +729,15 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
       tc_fence_before_sync();
       team_sync(team);
       TC_PROF(l == 0 ? 8 : 12);
-      if (tt == 0) {
+      if (wteam == 0) {
         tc_fence_after_sync();
-        tc_issue_mmas(tmc, bd_hi[l + 1], bd_lo[l + 1], idesc[l + 1], (uint32_t)p.npad[l + 1] * 8u, 0, p.kpad[l + 1] >> 3, true);
-        mma_commit(mma_bar);
+        if (team == 0) tc_issue_mmas<0, W64>(wbase, bar_base, p, l + 1, 0, p.kpad[l + 1] >> 3, true);
+        else           tc_issue_mmas<1, W64>(wbase, bar_base, p, l + 1, 0, p.kpad[l + 1] >> 3, true);
       }
       TC_PROF(9);
-      for (; g < gg; ++g) {  // the slots of the staged pre-projected blocks are free
-        tc_issue_item(p, issued, team, slots, tt, item_index(issued, t));
-        ++issued;
+      for (int a = 0; a < n_staged; ++a) {  // the slots of the staged pre-projected blocks are free
+        consume_done();
+        issue_next(t);
       }
       TC_PROF(10);
     }
@@ -624,7 +747,7 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
     mma_phase ^= 1;
     tc_fence_after_sync();
     TC_PROF(13);
-    unsigned char* osl = slots + (size_t)(g % p.ring) * TC_SLOT;  // this item's slot was released `ring` items ago
+    const uint32_t osl = slots + cons_slot * TC_SLOT;  // this item's slot was released `ring` items ago
     {
       const float* bias = reinterpret_cast<const float*>(wsm + p.b_off[last]);
       const int nb = p.npad[last] >> 4, per = (nb + 1) >> 1;
@@ -643,7 +766,7 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
             else if (p.final_act == GTB_ACT_SIGMOID_AFFINE) x = p.act_eps + (1.f - 2.f * p.act_eps) * (1.f / (1.f + expf(-x)));
             v[j] = x;
           }
-          *reinterpret_cast<float4*>(osl + slot_off(r, 4 * b + q)) = make_float4(v[0], v[1], v[2], v[3]);
+          sts128(osl + rsw + (((uint32_t)(4 * b + q) << 4) ^ rx), make_float4(v[0], v[1], v[2], v[3]));
         }
       }
     }
@@ -659,7 +782,32 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
     const bool vec = (N & 3) == 0 && (p.out == nullptr || ((p.out_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0)) &&
                      (p.res == nullptr || ((p.res_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.res) & 15) == 0));
     if (p.out != nullptr || touch) {
-      if (vec && p.out_mode != 2) {
+      if (vec && p.out_mode != 2 && N == 64) {  // 16 pieces per row: thread tt stores piece (tt & 15) of rows (tt >> 4) + 16 j
+        const int rb = tt >> 4, c = tt & 15;
+        const uint32_t sp0 = osl + slot_off(rb, c);
+        const uint32_t old4 = (uint32_t)p.out_ld * 4u, rld4 = (uint32_t)p.res_ld * 4u;
+        const float* res0 = p.res ? row_ptr(p.res + (c << 2), row0 + rb, rld4) : nullptr;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int rr = rb + 16 * j;
+          uint32_t orow = row0 + rr;
+          if (p.out_mode == 1) orow = (uint32_t)__shfl_sync(0xffffffffu, ocur, 2 * j + (lane >> 4));
+          if (rr < rows_here) {
+            float4 v = lds128(sp0 + j * 4096);
+            if (touch) {
+              v.x *= p.res_b; v.y *= p.res_b; v.z *= p.res_b; v.w *= p.res_b;
+              if (p.res) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(row_ptr(res0, 16 * j, rld4)));
+                v.x = fmaf(p.res_a, q.x, v.x); v.y = fmaf(p.res_a, q.y, v.y);
+                v.z = fmaf(p.res_a, q.z, v.z); v.w = fmaf(p.res_a, q.w, v.w);
+              }
+              v.x *= oscale; v.y *= oscale; v.z *= oscale; v.w *= oscale;
+              if (want_aggr) sts128(sp0 + j * 4096, v);
+            }
+            if (p.out) *reinterpret_cast<float4*>(const_cast<float*>(row_ptr(p.out + (c << 2), orow, old4))) = v;
+          }
+        }
+      } else if (vec && p.out_mode != 2) {
         const int c4n = N >> 2;  // a power of two here (out_mode 0 / 1)
         const int sh = __ffs(c4n) - 1;
         const int total = rows_here * c4n;
@@ -667,52 +815,52 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
         for (int j = 0; j < 8; ++j) {
           const int i = tt + j * TC_TEAM;
           const int rr = i >> sh, c = i & (c4n - 1);
-          int64_t orow = row0 + rr;
-          if (p.out_mode == 1) orow = __shfl_sync(0xffffffffu, ocur, (j * (32 >> sh) + (lane >> sh)) & 31);
+          uint32_t orow = row0 + rr;
+          if (p.out_mode == 1) orow = (uint32_t)__shfl_sync(0xffffffffu, ocur, (j * (32 >> sh) + (lane >> sh)) & 31);
           if (i < total) {
-            float4* sp = reinterpret_cast<float4*>(osl + slot_off(rr, c));
-            float4 v = *sp;
+            const uint32_t sp = osl + slot_off(rr, c);
+            float4 v = lds128(sp);
             if (touch) {
               v.x *= p.res_b; v.y *= p.res_b; v.z *= p.res_b; v.w *= p.res_b;
               if (p.res) {
-                const float4 q = __ldg(reinterpret_cast<const float4*>(p.res + (size_t)(row0 + rr) * p.res_ld) + c);
+                const float4 q = __ldg(reinterpret_cast<const float4*>(row_ptr(p.res, row0 + rr, (uint32_t)p.res_ld * 4u)) + c);
                 v.x = fmaf(p.res_a, q.x, v.x); v.y = fmaf(p.res_a, q.y, v.y);
                 v.z = fmaf(p.res_a, q.z, v.z); v.w = fmaf(p.res_a, q.w, v.w);
               }
               v.x *= oscale; v.y *= oscale; v.z *= oscale; v.w *= oscale;
-              if (want_aggr) *sp = v;
+              if (want_aggr) sts128(sp, v);
             }
-            if (p.out) *(reinterpret_cast<float4*>(p.out + (size_t)orow * p.out_ld) + c) = v;
+            if (p.out) *(reinterpret_cast<float4*>(const_cast<float*>(row_ptr(p.out, orow, (uint32_t)p.out_ld * 4u))) + c) = v;
           }
         }
       } else if (N == 1 && p.out_mode != 2) {  // one value per row (edge weights): thread = row
-        int64_t orow = row0 + tt;
-        if (p.out_mode == 1) orow = ocur;  // c4n = 1: every lane holds its own row
+        uint32_t orow = row0 + tt;
+        if (p.out_mode == 1) orow = (uint32_t)ocur;  // c4n = 1: every lane holds its own row
         if (tt < rows_here) {
-          float* sp = reinterpret_cast<float*>(osl + slot_off(tt, 0));
-          float v = *sp;
+          const uint32_t sp = osl + slot_off(tt, 0);
+          float v = lds32(sp);
           if (touch) {
             v *= p.res_b;
-            if (p.res) v = fmaf(p.res_a, __ldg(p.res + (size_t)(row0 + tt) * p.res_ld), v);
+            if (p.res) v = fmaf(p.res_a, __ldg(row_ptr(p.res, row0 + tt, (uint32_t)p.res_ld * 4u)), v);
             v *= oscale;
-            if (want_aggr) *sp = v;
+            if (want_aggr) sts32(sp, v);
           }
-          if (p.out) p.out[(size_t)orow * p.out_ld] = v;
+          if (p.out) *const_cast<float*>(row_ptr(p.out, orow, (uint32_t)p.out_ld * 4u)) = v;
         }
       } else {
         for (int i = tt; i < rows_here * N; i += TC_TEAM) {
           const int rr = i / N, n = i - rr * N;
-          float* sp = reinterpret_cast<float*>(osl + slot_off(rr, n >> 2)) + (n & 3);
-          float v = *sp;
+          const uint32_t sp = osl + slot_off(rr, n >> 2) + (n & 3) * 4;
+          float v = lds32(sp);
           if (touch) {
             v *= p.res_b;
-            if (p.res) v = fmaf(p.res_a, __ldg(p.res + (size_t)(row0 + rr) * p.res_ld + n), v);
+            if (p.res) v = fmaf(p.res_a, __ldg(row_ptr(p.res, row0 + rr, (uint32_t)p.res_ld * 4u) + n), v);
             v *= oscale;
-            if (want_aggr) *sp = v;
+            if (want_aggr) sts32(sp, v);
           }
           if (p.out) {
-            const int64_t orow = p.out_index ? (int64_t)__ldg(p.out_index + row0 + rr) : row0 + rr;
-            p.out[(size_t)orow * p.out_ld + n] = v;
+            const uint32_t orow = p.out_index ? (uint32_t)__ldg(p.out_index + row0 + rr) : row0 + rr;
+            const_cast<float*>(row_ptr(p.out, orow, (uint32_t)p.out_ld * 4u))[n] = v;
           }
         }
       }
@@ -726,30 +874,33 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
       if (touch) team_sync(team);
       const int c = tt & 63, r0 = (tt >> 6) * 32, r1 = min(r0 + 32, rows_here);
       if (c < N && r0 < r1) {
-        int cur = segs[r0];
+        const uint32_t al4 = (uint32_t)p.aggr_ld * 4u;
+        const uint32_t cx = (uint32_t)(c >> 2) << 4, cw = (uint32_t)(c & 3) * 4u;
+        int cur = lds_i32(segs + r0 * 4);
         float sum = 0.f;
+#pragma unroll 4
         for (int rr = r0; rr < r1; ++rr) {
-          const int sg = segs[rr];
+          const int sg = lds_i32(segs + rr * 4);
           if (sg != cur) {
-            atomicAdd(p.aggr + (size_t)cur * p.aggr_ld + c, sum);
+            atomicAdd(const_cast<float*>(row_ptr(p.aggr + c, (uint32_t)cur, al4)), sum);
             cur = sg;
             sum = 0.f;
           }
-          sum += *(reinterpret_cast<const float*>(osl + slot_off(rr, c >> 2)) + (c & 3));
+          sum += lds32(osl + (uint32_t)rr * 256u + (cx ^ ((uint32_t)(rr & 7) << 4)) + cw);
         }
-        atomicAdd(p.aggr + (size_t)cur * p.aggr_ld + c, sum);
+        atomicAdd(const_cast<float*>(row_ptr(p.aggr + c, (uint32_t)cur, al4)), sum);
       }
     }
     TC_PROF(16);
     team_sync(team);
-    tc_issue_item(p, issued, team, slots, tt, item_index(issued, t));  // the output slot is free again
-    ++issued;
+    consume_done();
+    issue_next(t);  // the output slot is free again
 #pragma unroll
     for (int q = 0; q < 4; ++q) ccur[q] = cnext[q];
 #pragma unroll
     for (int q = 0; q < 3; ++q) rcur[q] = rnext[q];
     TC_PROF(17);
-    if (prof_on) g_tc_prof[31] += 1;
+    if (PROF && prof_on) g_tc_prof[31] += 1;
   }
 
   cp_async_wait_pending(0);
@@ -887,12 +1038,28 @@ int fused_mlp_tc(const gtb_mlp_desc_t& d, cudaStream_t st) {
   const size_t smem = fixed + (size_t)p.ring * p.n_teams * TC_SLOT;
   static bool configured = false;  // one process drives one GPU (one rank per device)
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(fused_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
+    cudaError_t e = cudaFuncSetAttribute(fused_mlp_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(fused_mlp_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(fused_mlp_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(fused_mlp_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(fused_mlp_tc)");
     configured = true;
   }
+  bool w64 = true;  // the straight-line variant: everything in front of the last Linear is 64 wide
+  for (int c2 = 0; c2 < p.n_chunks; ++c2) w64 = w64 && p.ch[c2].staged && p.ch[c2].width == 64;
+  for (int l = 0; l + 1 < d.n_layers; ++l) w64 = w64 && d.dims[l + 1] == 64;
   const int grid = p.n_tiles < kNumSMs ? p.n_tiles : kNumSMs;
-  fused_mlp_tc_kernel<<<grid, TC_TEAM * p.n_teams, smem, st>>>(p);
+  const int nthr = TC_TEAM * p.n_teams;
+  if (p.prof) {
+    if (w64) fused_mlp_tc_kernel<true, true><<<grid, nthr, smem, st>>>(p);
+    else     fused_mlp_tc_kernel<false, true><<<grid, nthr, smem, st>>>(p);
+  } else {
+    if (w64) fused_mlp_tc_kernel<true, false><<<grid, nthr, smem, st>>>(p);
+    else     fused_mlp_tc_kernel<false, false><<<grid, nthr, smem, st>>>(p);
+  }
   GTB_CHECK_LAUNCH("fused_mlp_tc_kernel");
   return GTB_OK;
 }

@@ -173,15 +173,17 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
                : "memory");
 }
 
-// split an fp32 value into two tf32-exact parts (3xTF32 scheme): hi = rn_tf32(v), lo = rn_tf32(v - hi).
-// Both parts are rounded to nearest HERE because the tensor core truncates its fp32 operands to
-// tf32 (profiles/r1_tc_unit_probe.log): handing it a truncated hi and an unrounded lo leaves a
-// one-sided 2^-21 error per product that adds up coherently over K; with both parts pre-rounded
-// the representation error is <= 2^-23 |v| and unbiased.
+// split an fp32 value for the 3xTF32 scheme: hi = rn_tf32(v), lo = rn_tf32(v - hi), where rn_tf32
+// rounds to the nearest tf32 (ties away from zero: what cvt.rna.tf32.f32 computes, minus its
+// Inf / NaN guard -- two integer instructions instead of four).
+// The tensor core TRUNCATES its fp32 operands to tf32 (profiles/r1_tc_unit_probe.log), so both parts
+// are rounded here: a truncated hi leaves a one-sided 2^-11 |v| remainder whose own truncation
+// error (2^-21 |v| per product, always the same sign) adds up coherently over K; an unrounded lo
+// still costs a one-sided 2^-23 |v|, enough to push a 4-layer stack on unscaled inputs past the
+// 1e-5 parity bar (tests/test_gpu_in_parity.py, ec_skip2).  With both rounded the representation
+// error is <= 2^-24 |v| and unbiased.
 __device__ __forceinline__ float rn_tf32(float v) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-  return __uint_as_float(u);
+  return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
 }
 __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
   hi = rn_tf32(v);
