@@ -346,57 +346,48 @@ __device__ __forceinline__ void tc_issue_item(const TcParams& p, int tile, int k
   cp_async_commit();
 }
 
-// Issued by the WHOLE first warp of a team with warp-uniform operands (kernel parameters, loop
-// counters, the team number as a template constant, TMEM base 0): ptxas then keeps descriptors and
-// addresses in uniform registers and emits one UTCHMMA per step.  Issued from a divergent branch
-// (`if (tid == 0)`) the same code becomes an ELECT / 6 x R2UR / UTCHMMA / BRA.U.ANY waterfall loop
-// that costs ~150 cycles per MMA -- 5x the 32 cycles the tensor core needs for M=128, N=64, K=8
-// (profiles/r1_tc_mma_bench.log).  One elected lane executes the MMA itself.
-__device__ __forceinline__ void mma_tf32_ts_elect(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
-                                                  uint32_t accumulate) {
+// MMA issue.  The whole first warp of a team calls these with warp-uniform arguments; ONE lane,
+// chosen by elect.sync, runs the branch that holds the tcgen05.mma chain.  ptxas recognises the
+// elect-guarded branch as single-lane code and keeps descriptors / TMEM addresses in uniform
+// registers: back-to-back UTCHMMA with UIADD3 in between.  The same chain issued from
+// `if (tid == 0)` compiles to an ELECT / 6 x R2UR / UTCHMMA / BRA.U.ANY waterfall loop per MMA
+// (~150 cycles each, measured: profiles/r1_tc_mma_bench.log), 5x the 32 cycles the tensor core
+// needs for M = 128, N = 64, K = 8.  The TMEM base is 0 (checked at kernel start).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t leader;
   asm volatile(
-      "{\n\t.reg .pred pe, pacc;\n\t"
-      "elect.sync _|pe, 0xffffffff;\n\t"
-      "setp.ne.b32 pacc, %4, 0;\n\t"
-      "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, pacc;\n\t}" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(leader));
+  return leader != 0;
 }
-__device__ __forceinline__ void mma_commit_elect(uint32_t bar_smem) {
-  asm volatile(
-      "{\n\t.reg .pred pe;\n\t"
-      "elect.sync _|pe, 0xffffffff;\n\t"
-      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar_smem)
-      : "memory");
+__device__ __forceinline__ void mma_commit_addr(uint32_t bar_smem) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_smem) : "memory");
 }
 
 // three passes (small terms first: lo*hi, hi*lo, hi*hi) over `ksteps` K = 8 steps of one streamed
-// block (first Linear) or of a whole hidden Linear, then the commit onto the team's barrier.
-// K64: the block / layer is exactly 64 wide and starts on a K-tile boundary: 8 unrolled steps.
-template <int TEAM, bool K64>
+// block (first Linear) or of a whole hidden Linear, then the commit onto the team's barrier
+template <int TEAM>
 __device__ __forceinline__ void tc_issue_mmas(uint32_t wbase, uint32_t bar_base, const TcParams& p, int l, int koff,
                                               int ksteps, bool first) {
-  constexpr uint32_t tmc = TEAM * TM_CTX;  // TMEM base is 0: the CTA owns the SM's tensor memory (checked at start)
+  constexpr uint32_t tmc = TEAM * TM_CTX;
   const uint32_t idesc = make_idesc_tf32(TC_TM, p.npad[l]);
   const uint32_t tile16 = (uint32_t)p.npad[l] * 8u;  // bytes of one [npad][32] K tile >> 4
   const uint32_t boff = (uint32_t)(koff >> 5) * tile16 + (uint32_t)((koff & 31) >> 3) * 2u;
-  uint32_t acc = first ? 0u : 1u;
+  const uint64_t bd_hi = make_smem_desc_sw128(wbase + p.w_off[l][0]) + boff;
+  const uint64_t bd_lo = make_smem_desc_sw128(wbase + p.w_off[l][1]) + boff;
+  if (elect_one()) {
+    bool acc = !first;
 #pragma unroll 1
-  for (int pass = 0; pass < 3; ++pass) {
-    uint32_t a = tmc + ((pass == 0) ? TM_A_LO : TM_A_HI);
-    uint64_t bd = make_smem_desc_sw128(wbase + p.w_off[l][pass == 1 ? 1 : 0]) + boff;
-    if (K64) {
-#pragma unroll
-      for (int ks = 0; ks < 8; ++ks) {
-        mma_tf32_ts_elect(tmc + TM_D, a + 8 * ks, bd + (uint64_t)((ks >> 2) * tile16 + (ks & 3) * 2), idesc, acc);
-        acc = 1u;
-      }
-    } else {
+    for (int pass = 0; pass < 3; ++pass) {
+      uint32_t a = tmc + ((pass == 0) ? TM_A_LO : TM_A_HI);
+      uint64_t bd = (pass == 1) ? bd_lo : bd_hi;
       int sub = (koff & 31) >> 3;
 #pragma unroll 1
       for (int ks = 0; ks < ksteps; ++ks) {
-        mma_tf32_ts_elect(tmc + TM_D, a, bd, idesc, acc);
-        acc = 1u;
+        mma_tf32_ts(tmc + TM_D, a, bd, idesc, acc);
+        acc = true;
         a += 8;
         if (++sub == 4) {
           sub = 0;
@@ -406,8 +397,36 @@ __device__ __forceinline__ void tc_issue_mmas(uint32_t wbase, uint32_t bar_base,
         }
       }
     }
+    mma_commit_addr(bar_base + TEAM * 8);
   }
-  mma_commit_elect(bar_base + TEAM * 8);
+  __syncwarp();
+}
+
+// The common case -- a 64-wide block / layer starting at K = 0 -- with the layer index a template
+// constant and everything unrolled: operands are kernel-parameter loads plus immediates, which
+// ptxas keeps in uniform registers (no R2UR in front of every UTCHMMA).
+template <int TEAM, int L>
+__device__ __forceinline__ void tc_issue_mmas_k64(uint32_t wbase, uint32_t bar_base, const TcParams& p, bool first) {
+  constexpr uint32_t tmc = TEAM * TM_CTX;
+  const uint32_t idesc = make_idesc_tf32(TC_TM, p.npad[L]);
+  const uint32_t tile16 = (uint32_t)p.npad[L] * 8u;
+  const uint64_t bd_hi = make_smem_desc_sw128(wbase + p.w_off[L][0]);
+  const uint64_t bd_lo = make_smem_desc_sw128(wbase + p.w_off[L][1]);
+  if (elect_one()) {  // ptxas knows a single lane runs this branch: operands go to uniform registers once
+    bool acc = !first;
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+      const uint32_t a = tmc + ((pass == 0) ? TM_A_LO : TM_A_HI);
+      const uint64_t bd = (pass == 1) ? bd_lo : bd_hi;
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        mma_tf32_ts(tmc + TM_D, a + 8 * ks, bd + (uint64_t)((ks >> 2) * tile16 + (ks & 3) * 2), idesc, acc);
+        acc = true;
+      }
+    }
+    mma_commit_addr(bar_base + TEAM * 8);
+  }
+  __syncwarp();
 }
 
 __device__ __forceinline__ void split_store8(uint32_t taddr_hi, uint32_t taddr_lo, const float (&v)[8]) {
@@ -632,8 +651,13 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
       TC_PROF(2);
       if (wteam == 0) {  // whole warp, uniform operands (see tc_issue_mmas)
         tc_fence_after_sync();
-        if (team == 0) tc_issue_mmas<0, W64>(wbase, bar_base, p, 0, ch.koff, groups, c == 0);
-        else           tc_issue_mmas<1, W64>(wbase, bar_base, p, 0, ch.koff, groups, c == 0);
+        if (W64 && c == 0) {
+          if (team == 0) tc_issue_mmas_k64<0, 0>(wbase, bar_base, p, true);
+          else           tc_issue_mmas_k64<1, 0>(wbase, bar_base, p, true);
+        } else {
+          if (team == 0) tc_issue_mmas<0>(wbase, bar_base, p, 0, ch.koff, groups, c == 0);
+          else           tc_issue_mmas<1>(wbase, bar_base, p, 0, ch.koff, groups, c == 0);
+        }
       }
       TC_PROF(3);
       if (ch.staged) {  // the slot is free: keep the ring full
@@ -731,8 +755,13 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
       TC_PROF(l == 0 ? 8 : 12);
       if (wteam == 0) {
         tc_fence_after_sync();
-        if (team == 0) tc_issue_mmas<0, W64>(wbase, bar_base, p, l + 1, 0, p.kpad[l + 1] >> 3, true);
-        else           tc_issue_mmas<1, W64>(wbase, bar_base, p, l + 1, 0, p.kpad[l + 1] >> 3, true);
+        if (W64) {
+          if (team == 0) { if (l == 0) tc_issue_mmas_k64<0, 1>(wbase, bar_base, p, true); else tc_issue_mmas_k64<0, 2>(wbase, bar_base, p, true); }
+          else           { if (l == 0) tc_issue_mmas_k64<1, 1>(wbase, bar_base, p, true); else tc_issue_mmas_k64<1, 2>(wbase, bar_base, p, true); }
+        } else {
+          if (team == 0) tc_issue_mmas<0>(wbase, bar_base, p, l + 1, 0, p.kpad[l + 1] >> 3, true);
+          else           tc_issue_mmas<1>(wbase, bar_base, p, l + 1, 0, p.kpad[l + 1] >> 3, true);
+        }
       }
       TC_PROF(9);
       for (int a = 0; a < n_staged; ++a) {  // the slots of the staged pre-projected blocks are free
@@ -872,23 +901,34 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
     // branches.  One fire-and-forget reduction per (run, column) onto the zero-filled aggregate.
     if (want_aggr) {
       if (touch) team_sync(team);
-      const int c = tt & 63, r0 = (tt >> 6) * 32, r1 = min(r0 + 32, rows_here);
-      if (c < N && r0 < r1) {
+      const int c = tt & 63, r0 = (tt >> 6) * 32;
+      // run starts of this warp's 32 rows as a warp-uniform bit mask; all 32 values of the column
+      // are loaded before the (branchy, but uniform) summation so that their latencies overlap
+      const int myrow = r0 + lane;
+      const int myseg = myrow < rows_here ? lds_i32(segs + myrow * 4) : -1;
+      const int prevseg = __shfl_up_sync(0xffffffffu, myseg, 1);
+      const uint32_t starts = __ballot_sync(0xffffffffu, myrow < rows_here && (lane == 0 || myseg != prevseg));
+      if (r0 < rows_here) {  // warp-uniform; `act` is not (N < 64): the shuffles below stay outside of it
+        const bool act = c < N;
         const uint32_t al4 = (uint32_t)p.aggr_ld * 4u;
         const uint32_t cx = (uint32_t)(c >> 2) << 4, cw = (uint32_t)(c & 3) * 4u;
-        int cur = lds_i32(segs + r0 * 4);
+        const uint32_t col0 = osl + (uint32_t)r0 * 256u + cw;
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i)  // (r0 + i) & 7 == i & 7: r0 is a multiple of 32
+          v[i] = (act && r0 + i < rows_here) ? lds32(col0 + (uint32_t)i * 256u + (cx ^ ((uint32_t)(i & 7) << 4))) : 0.f;
+        int cur = __shfl_sync(0xffffffffu, myseg, 0);
         float sum = 0.f;
-#pragma unroll 4
-        for (int rr = r0; rr < r1; ++rr) {
-          const int sg = lds_i32(segs + rr * 4);
-          if (sg != cur) {
-            atomicAdd(const_cast<float*>(row_ptr(p.aggr + c, (uint32_t)cur, al4)), sum);
-            cur = sg;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (i > 0 && ((starts >> i) & 1u)) {  // warp-uniform
+            if (act) atomicAdd(const_cast<float*>(row_ptr(p.aggr + c, (uint32_t)cur, al4)), sum);
+            cur = __shfl_sync(0xffffffffu, myseg, i);
             sum = 0.f;
           }
-          sum += lds32(osl + (uint32_t)rr * 256u + (cx ^ ((uint32_t)(rr & 7) << 4)) + cw);
+          sum += v[i];
         }
-        atomicAdd(const_cast<float*>(row_ptr(p.aggr + c, (uint32_t)cur, al4)), sum);
+        if (act) atomicAdd(const_cast<float*>(row_ptr(p.aggr + c, (uint32_t)cur, al4)), sum);
       }
     }
     TC_PROF(16);
