@@ -199,10 +199,65 @@ def run_reference(args) -> None:
 
 
 # -------------------------------------------------------------------------- ours
+def relabel_by_phi(g: dict) -> dict:
+    """Node ids in ascending phi: contiguous id ranges are then phi wedges, and the graph
+    builder's tight phi cut keeps most edges inside one range."""
+    order = torch.argsort(g["x"][:, 1], stable=True)
+    new_id = torch.empty_like(order)
+    new_id[order] = torch.arange(order.numel())
+    out = dict(g)
+    out["x"] = g["x"][order].contiguous()
+    out["edge_index"] = new_id[g["edge_index"]].contiguous()
+    return out
+
+
+def edge_kernel_time(model, x_dim, plan, n, e, dev, flush, reps):
+    """The dominant kernel alone: one launch of the fused IN edge kernel of a middle layer (ReLU on
+    load; gathered pre-projected node tables, relational MLP, scattered store, segmented sum),
+    timed with CUDA events on the launching stream, L2 flushed before every launch."""
+    from gnn_tracking_b200 import ops
+    from gnn_tracking_b200.ops import Block
+    layer = model.ec_resin.network.layers[1]
+    rel = layer.relational_model
+    dn, de = x_dim
+    gen = torch.Generator(device="cpu").manual_seed(1)
+    xx = torch.randn(n, dn, generator=gen).to(dev)
+    ee = torch.randn(e, de, generator=gen).to(dev)
+    blocks = [Block(xx, plan.dst_sorted, True, sorted_index=True), Block(xx, plan.src_sorted, True),
+              Block(ee, plan.perm, True)]
+    widths = [dn, dn, de]
+    n0 = rel.linears[0].out_features
+    projected = [len(rel.linears) >= 2 and n0 % 4 == 0 and 2 * n <= e] * 2 + [False]
+    packed, proj = rel._cache.get(rel.linears, widths, projected)
+    cur = []
+    for i, b in enumerate(blocks):
+        if projected[i]:
+            table = ops.fused_mlp([Block(b.tensor, None, b.relu)], n, proj[i])
+            cur.append(Block(table, b.index, False, projected=True, sorted_index=b.sorted_index))
+        else:
+            cur.append(b)
+    out = torch.empty((e, de), device=dev)
+    aggr = torch.zeros((n, de), device=dev)
+    ts = []
+    for i in range(3 + reps):
+        flush.zero_()
+        aggr.zero_()
+        s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        ops.fused_mlp(cur, e, packed[0], out=out, out_index=plan.perm, aggr=aggr, seg_id=plan.dst_sorted,
+                      rowptr=plan.rowptr)
+        t.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            ts.append(s.elapsed_time(t))
+    return statistics.mean(ts), ("tcgen05" if packed[0].impl == ops.IMPL_TCGEN05 else "ffma")
+
+
 def run_ours(args) -> None:
     import torch.distributed as dist
     from gnn_tracking_b200 import ops
     from gnn_tracking_b200.models.edge_classifier import ECForGraphTCN
+    from gnn_tracking_b200.partition import HaloExchange, partition_graph
     from gnn_tracking_b200.plan import build_plan, clear_plan_cache
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -213,9 +268,27 @@ def run_ours(args) -> None:
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    # weak scaling: every rank owns one full graph per step (independent events, as the
-    # reference trains with batch_size=1 graph per step); no data-path collective.
-    g = make_graph(N_NODES, N_EDGES, seed=rank)
+    partitioned = world > 1 and args.multi == "partitioned"
+    halo = None
+    if partitioned:
+        # weak scaling on ONE graph: world x (100k nodes / 1M edges), nodes relabelled by phi and
+        # partitioned into contiguous ranges; every rank owns the edges that END in its range and
+        # receives its halo rows by one all-to-all-v per layer (+ one for the W head)
+        gg = relabel_by_phi(make_graph(N_NODES * world, N_EDGES * world, seed=0))
+        shard = partition_graph(gg["edge_index"], gg["n_nodes"], world, rank)
+        g = {"x": gg["x"][shard.node_lo:shard.node_hi].contiguous(), "edge_index": shard.edge_index.contiguous(),
+             "edge_attr": gg["edge_attr"][shard.edge_ids].contiguous(), "n_nodes": shard.n_local,
+             "n_edges": int(shard.edge_ids.numel())}
+        halo = HaloExchange(shard.to(dev))
+        n_total_edges = gg["n_edges"]
+        halo_frac = shard.n_halo / max(1, shard.n_owned)
+        del gg
+    else:
+        # independent graphs: every rank owns one full graph per step (as the reference trains with
+        # batch_size=1 graph per step); no data-path collective
+        g = make_graph(N_NODES, N_EDGES, seed=rank)
+        n_total_edges = g["n_edges"] * world
+        halo_frac = 0.0
     n, e = g["n_nodes"], g["n_edges"]
     torch.manual_seed(0)
     model = ECForGraphTCN(**model_kwargs(args.dims)).to(dev)
@@ -227,13 +300,13 @@ def run_ours(args) -> None:
     def step_resident():
         clear_plan_cache()
         with torch.no_grad():
-            return model.forward_tensors(x, ei, ea)
+            return model.forward_tensors(x, ei, ea, halo=halo)
 
     def step_e2e():
         clear_plan_cache()
         dx, dei, dea = hx.to(dev, non_blocking=True), hei.to(dev, non_blocking=True), hea.to(dev, non_blocking=True)
         with torch.no_grad():
-            out = model.forward_tensors(dx, dei, dea)
+            out = model.forward_tensors(dx, dei, dea, halo=halo)
         hw.copy_(out["W"], non_blocking=True)
         return out
 
@@ -268,29 +341,14 @@ def run_ours(args) -> None:
         ms, launches = timed(step_resident, args.steps, args.warmup)
         ms_e2e, _ = timed(step_e2e, args.steps, max(1, args.warmup))
 
-    # ---- dominant kernel (fused IN edge kernel of a middle layer: ReLU on load), timed alone
+    # ---- dominant kernel alone (rank 0's graph)
     dn, de = (HIDDEN, HIDDEN) if args.dims == "wide" else (5, 4)
     plan = build_plan(ei, n)
-    layer = model.ec_resin.network.layers[1]
-    xx = torch.randn(n, dn, device=dev)
-    ee = torch.randn(e, de, device=dev)
-    kt = []
-    for i in range(3 + args.steps):
-        flush.zero_()
-        s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        aggr = torch.zeros((n, de), device=dev)
-        out = torch.empty((e, de), device=dev)
-        s.record()
-        with torch.no_grad():
-            layer.relational_model.forward_blocks(
-                [ops.Block(xx, plan.dst_sorted, True), ops.Block(xx, plan.src_sorted, True),
-                 ops.Block(ee, plan.perm, True)], e, out=out, out_index=plan.perm, aggr=aggr,
-                seg_id=plan.dst_sorted, rowptr=plan.rowptr)
-        t.record()
-        torch.cuda.synchronize()
-        if i >= 3:
-            kt.append(s.elapsed_time(t))
-    k_ms = statistics.mean(kt)
+    k_ms, k_impl = edge_kernel_time(model, (dn, de), plan, n, e, dev, flush, args.steps)
+    if world > 1:
+        hf = torch.tensor([halo_frac], device=dev, dtype=torch.float64)
+        dist.all_reduce(hf, op=dist.ReduceOp.MAX)
+        halo_frac = float(hf.item())
 
     if rank != 0:
         if world > 1:
@@ -302,26 +360,32 @@ def run_ours(args) -> None:
         peak, peak_src = float(json.loads(peaks_file.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
     else:
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
-    alg = layer_algorithmic_bytes(n, e, dn, de)
+    n_owned = x.size(0)
+    alg = layer_algorithmic_bytes(n_owned, e, dn, de)
     achieved = alg / (k_ms * 1e-3) / 1e9
     traffic = None
     tf = ROOT / "profiles" / "roofline_traffic.json"
     if tf.exists():
-        traffic = json.loads(tf.read_text()).get(args.dims)
+        traffic = json.loads(tf.read_text()).get(f"{args.dims}_{k_impl}")
 
-    value = e * world * args.steps / (ms * 1e-3)
-    e2e_val = e * world * args.steps / (ms_e2e * 1e-3)
+    value = n_total_edges * args.steps / (ms * 1e-3)
+    e2e_val = n_total_edges * args.steps / (ms_e2e * 1e-3)
+    multi = ("one graph of %d x (100k nodes / 1M edges), node-partitioned by phi wedge, edges owned by their destination's rank, "
+             "one NCCL all-to-all-v of halo rows per IN layer + one for the W head; max halo/owned = %.3f" % (world, halo_frac)
+             if partitioned else "one independent graph per rank per step, no data-path collective")
     line = {
         "metric": "edges/sec", "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.dims, n, e), "l2": "flushed between timed iterations (256 MB write)",
-                   "multi_gpu": "one independent graph per rank per step, no data-path collective",
+        "config": {"workload": workload_name(args.dims, N_NODES, N_EDGES) + (f" x {world} ranks" if world > 1 else ""),
+                   "l2": "flushed between timed iterations (256 MB write)", "multi_gpu": multi,
                    "impl": os.environ.get("GTB_IMPL", "auto")},
         "e2e": {"value": e2e_val, "unit": "edges/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": hx.numel() * 4 + hei.numel() * 8 + hea.numel() * 4, "d2h_bytes_per_step": e * 4},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": "fused IN edge kernel (gather + relational MLP + segmented sum), one layer",
+        "roofline": {"bound": "hbm",
+                     "kernel": f"fused IN edge kernel ({k_impl}): gathered pre-projected node rows + relational MLP + scattered store + "
+                               "segmented sum, one layer, one launch",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "algorithmic_bytes_per_launch": alg, "kernel_ms": k_ms, "peak_source": peak_src},
         "clocks": clocks.summary(),
@@ -344,6 +408,8 @@ def main() -> None:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dims", default="wide", choices=["wide", "default"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--multi", default="partitioned", choices=["partitioned", "independent"],
+                    help="N > 1: one node-partitioned graph with halo exchange (default) or one graph per rank")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

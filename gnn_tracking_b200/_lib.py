@@ -63,6 +63,7 @@ SIGNATURES = {
     "gtb_mlp_packed_bytes": (_sz, [C.c_int, C.POINTER(_i32), C.c_int, C.POINTER(_i32), C.c_int]),
     "gtb_mlp_pack": (C.c_int, [C.c_int, C.POINTER(_i32), C.c_int, C.POINTER(_i32), C.POINTER(_vp), C.POINTER(_vp),
                                C.c_int, _vp, _vp]),
+    "gtb_mlp_tc_slots": (C.c_int, [C.c_int, C.POINTER(_i32), C.c_int, C.POINTER(_i32)]),
     "gtb_fused_mlp_f32": (C.c_int, [C.POINTER(MlpDesc), _vp]),
     "gtb_debug_tc_timeout": (C.c_int, [C.POINTER(C.c_int)]),
     "gtb_debug_tc_profile": (C.c_int, [C.c_int, C.POINTER(C.c_longlong)]),

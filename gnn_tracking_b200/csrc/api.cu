@@ -29,6 +29,7 @@ size_t tc_packed_bytes(int, const int32_t*, int, const int32_t*);
 int pack_tc(int, const int32_t*, int, const int32_t*, const float* const*, const float* const*, void*, cudaStream_t);
 int fused_mlp_tc(const gtb_mlp_desc_t&, cudaStream_t);
 int tc_timeout_flag(int*);
+int tc_slots(int, const int32_t*, int, const int32_t*);
 int tc_profile(int, long long*);
 int ec_loss(const float*, const void*, int, int64_t, const int64_t*, const float*, float, int, float, float, float,
             double*, cudaStream_t);
@@ -118,6 +119,11 @@ size_t gtb_mlp_packed_bytes(int n_layers, const int32_t* dims, int n_blocks, con
   FfmaLayout L;
   if (!ffma_layout(n_layers, dims, &L)) return 0;
   return L.total_floats * sizeof(float);
+}
+
+int gtb_mlp_tc_slots(int n_layers, const int32_t* dims, int n_blocks, const int32_t* block_widths) {
+  if (n_layers < 1 || n_layers > GTB_MAX_LAYERS || dims == nullptr) return 0;
+  return tc_slots(n_layers, dims, n_blocks, block_widths);
 }
 
 int gtb_mlp_pack(int n_layers, const int32_t* dims, int n_blocks, const int32_t* block_widths,

@@ -138,6 +138,14 @@ bool tc_layout(int n_layers, const int32_t* dims, int n_chunks, const int32_t* c
   return (size_t)off + TC_SLOT + TC_MISC <= (size_t)TC_SMEM_MAX;
 }
 
+// staging slots (32 KB each) left beside the packed weights: >= 4 lets two teams share an SM,
+// 1 leaves every gather latency exposed; 0: the widths are not supported
+int tc_slots(int n_layers, const int32_t* dims, int n_chunks, const int32_t* chunk_w) {
+  TcLayout L;
+  if (!tc_layout(n_layers, dims, n_chunks, chunk_w, &L)) return 0;
+  return (int)((TC_SMEM_MAX - (((size_t)L.total_bytes + 15) / 16 * 16 + TC_MISC)) / TC_SLOT);
+}
+
 size_t tc_packed_bytes(int n_layers, const int32_t* dims, int n_chunks, const int32_t* chunk_w) {
   TcLayout L;
   if (!tc_layout(n_layers, dims, n_chunks, chunk_w, &L)) return 0;

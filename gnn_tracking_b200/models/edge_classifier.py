@@ -44,22 +44,26 @@ class ECForGraphTCN(nn.Module, HyperparametersMixin):
         return self.forward_tensors(x, edge_index, edge_attr)
 
     def forward_tensors(self, x: Tensor, edge_index: Tensor, edge_attr: Tensor,
-                        plan: GraphPlan | None = None) -> dict[str, Tensor]:
+                        plan: GraphPlan | None = None, halo=None) -> dict[str, Tensor]:
+        """``halo`` (``partition.HaloExchange``): ``x`` / ``edge_attr`` are the owned nodes / edges of
+        a node-partitioned graph and ``edge_index`` its local numbering (``GraphShard.edge_index``);
+        the outputs cover the owned edges and nodes."""
         assert_feat_dim(x, self.hparams.node_indim)
         assert_feat_dim(edge_attr, self.hparams.edge_indim)
         ops.require_cuda(x, edge_index, edge_attr)
         if plan is None:
-            plan = get_plan(edge_index, x.size(0))
+            plan = get_plan(edge_index, x.size(0) if halo is None else halo.shard.n_local)
         n, e = x.size(0), edge_attr.size(0)
         # encoders + the ReLU behind them (edge_classifier.py:102-103)
         h = self.ec_node_encoder.forward_blocks([Block(x)], n, final_act=ACT_RELU)
         ea = self.ec_edge_encoder.forward_blocks([Block(edge_attr)], e, final_act=ACT_RELU)
-        h, ea, eas = self.ec_resin.forward_planned(h, plan, ea)
+        h, ea, eas = self.ec_resin.forward_planned(h, plan, ea, halo=halo)
         # W head over cat[h[src], h[dst], e_0 .. e_L] (edge_classifier.py:108-117), walked in
         # dst-sorted order (h[dst] rows repeat) and written back in the caller's edge order
         blocks = []
         if self.hparams.use_node_embedding:
-            blocks += [Block(h, plan.src_sorted), Block(h, plan.dst_sorted, sorted_index=True)]
+            blocks += [Block(h, plan.src_sorted, extend=None if halo is None else halo.extend),
+                       Block(h, plan.dst_sorted, sorted_index=True)]
         blocks += [Block(t, plan.perm) for t in (eas if self.hparams.use_intermediate_edge_embeddings else [ea])]
         w = self.W.forward_blocks(blocks, e, final_act=ACT_SIGMOID_AFFINE, act_eps=0.001, out_index=plan.perm)
         return {"W": w.squeeze(), "node_embedding": h, "edge_embedding": ea}

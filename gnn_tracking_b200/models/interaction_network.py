@@ -35,18 +35,21 @@ class InteractionNetwork(nn.Module, HyperparametersMixin):
 
     def forward_planned(self, x: Tensor, plan: GraphPlan, edge_attr: Tensor, *, relu_x: bool = False,
                         relu_e: bool = False, res: Tensor | None = None, res_a: float = 0.0,
-                        res_b: float = 1.0) -> tuple[Tensor, Tensor]:
+                        res_b: float = 1.0, halo=None) -> tuple[Tensor, Tensor]:
         """One layer on a planned graph.  ``relu_*`` apply the activation on load (layers
         > 0 of a residual stack see relu(x), reference models/resin.py:104-105); ``res``
-        fuses ``sqconvex_combination`` (resin.py:17-42) into the node kernel."""
+        fuses ``sqconvex_combination`` (resin.py:17-42) into the node kernel.  ``halo`` (a
+        ``partition.HaloExchange``): ``x`` holds the owned nodes of a node-partitioned graph and
+        ``plan`` its local edges; the source rows other ranks own are exchanged once per layer."""
         dev = ops.require_cuda(x, edge_attr)
         n, e = x.size(0), edge_attr.size(0)
         e_out = self.hparams.edge_outdim
         # zeroed: isolated nodes keep 0 (SumAggregation), partial runs are added atomically
+        ext = None if halo is None else halo.extend
         aggr = torch.zeros((n, e_out), dtype=torch.float32, device=dev)
         # message(): cat[x_i (target), x_j (source), edge_attr]  (interaction_network.py:75-89)
         e_tilde = self.relational_model.forward_blocks(
-            [Block(x, plan.dst_sorted, relu_x, sorted_index=True), Block(x, plan.src_sorted, relu_x),
+            [Block(x, plan.dst_sorted, relu_x, sorted_index=True), Block(x, plan.src_sorted, relu_x, extend=ext),
              Block(edge_attr, plan.perm, relu_e)],
             e, out_index=plan.perm, aggr=aggr, seg_id=plan.dst_sorted, rowptr=plan.rowptr)
         # update(): cat[x, aggr]  (interaction_network.py:92-103)

@@ -12,6 +12,11 @@ from .. import ops
 from ..ops import ACT_NONE, ACT_RELU, Block, PackedMLP
 
 
+def _stream_dims(linears, widths, projected):
+    k0 = sum(w for w, pr in zip(widths, projected) if not pr)
+    return [k0] + [lin.out_features for lin in linears], [w for w, pr in zip(widths, projected) if not pr]
+
+
 class PackedCache:
     """Packed copies of a chain of ``nn.Linear`` layers for one calling pattern (widths of
     the concatenated source blocks, which of them are pre-projected), re-packed when a weight
@@ -21,6 +26,19 @@ class PackedCache:
         self._key = None
         self._packed: list[PackedMLP] = []
         self._proj: dict[int, PackedMLP] = {}
+
+    @staticmethod
+    def _groups(linears, widths, projected, impl):
+        """<= 3 Linear layers per launch.  With the tcgen05 tiles a 3-layer chain whose weights
+        would leave less than two staging slots in shared memory (the W head: 4 x 64 edge-embedding
+        columns in front of the first Linear) runs as 2 + 1 layers instead: one more pass over
+        E x H activations, but the gathers of a tile overlap the previous tile's MMAs again."""
+        linears = list(linears)
+        if len(linears) == 3 and impl != ops.IMPL_FFMA:
+            dims3, bw = _stream_dims(linears, widths, projected)
+            if 0 < ops.tc_slots(dims3, bw) < 2 and ops.tc_slots(dims3[:3], bw) >= 2:
+                return [linears[:2], linears[2:]]
+        return [linears[i:i + 3] for i in range(0, len(linears), 3)]
 
     def get(self, linears: Sequence[nn.Linear], widths: Sequence[int] | None = None,
             projected: Sequence[bool] | None = None, impl: int | None = None):
@@ -32,7 +50,7 @@ class PackedCache:
         projected = tuple(projected) if projected is not None else (False,) * len(widths)
         key = (impl, widths, projected) + tuple((p.data_ptr(), p._version) for lin in linears for p in lin.parameters())
         if key != self._key:
-            groups = [list(linears[i:i + 3]) for i in range(0, len(linears), 3)]
+            groups = self._groups(linears, widths, projected, impl)
             self._packed, self._proj = [], {}
             for gi, g in enumerate(groups):
                 ws, bs = [l.weight for l in g], [l.bias for l in g]
@@ -82,7 +100,11 @@ def run_linears(cache: PackedCache, linears: Sequence[nn.Linear], blocks: Sequen
     for i, b in enumerate(blocks):
         if projected[i]:
             table = ops.fused_mlp([Block(b.tensor, None, b.relu)], b.tensor.size(0), proj[i])
+            if b.extend is not None:  # halo rows of the projected table from their owners
+                table = b.extend(table)
             cur.append(Block(table, b.index, False, projected=True, sorted_index=b.sorted_index))
+        elif b.extend is not None:
+            cur.append(Block(b.extend(b.tensor), b.index, b.relu, sorted_index=b.sorted_index))
         else:
             cur.append(b)
     for i, p in enumerate(packed):

@@ -33,15 +33,21 @@ class ResidualNetwork(ABC, nn.Module):
     def forward(self, x: Tensor, edge_index: Tensor, edge_attr: Tensor) -> tuple[Tensor, Tensor, list[Tensor] | None]:
         return self._forward(x, get_plan(edge_index, x.size(0)), edge_attr)
 
-    def forward_planned(self, x: Tensor, plan: GraphPlan, edge_attr: Tensor):
-        return self._forward(x, plan, edge_attr)
+    def forward_planned(self, x: Tensor, plan: GraphPlan, edge_attr: Tensor, halo=None):
+        self._halo = halo
+        try:
+            return self._forward(x, plan, edge_attr)
+        finally:
+            self._halo = None
+
+    _halo = None
 
     def _layer(self, i: int, x: Tensor, plan: GraphPlan, e: Tensor, *, first: bool, residue: Tensor | None):
         """IN layer i on (act(x), act(e)) with the residual onto the un-activated
         ``residue`` fused in; act = identity for the very first layer, else ReLU."""
         co = _res_coeffs(self._alpha) if residue is not None else None
         kw = {} if co is None else dict(res=residue, res_a=co[0], res_b=co[1])
-        return self.layers[i].forward_planned(x, plan, e, relu_x=not first, relu_e=not first, **kw)
+        return self.layers[i].forward_planned(x, plan, e, relu_x=not first, relu_e=not first, halo=self._halo, **kw)
 
     @abstractmethod
     def _forward(self, x: Tensor, plan: GraphPlan, edge_attr: Tensor):
@@ -142,5 +148,5 @@ class ResIN(nn.Module, HyperparametersMixin):
     def forward(self, x: Tensor, edge_index: Tensor, edge_attr: Tensor):
         return self.network.forward(x, edge_index, edge_attr)
 
-    def forward_planned(self, x: Tensor, plan: GraphPlan, edge_attr: Tensor):
-        return self.network.forward_planned(x, plan, edge_attr)
+    def forward_planned(self, x: Tensor, plan: GraphPlan, edge_attr: Tensor, halo=None):
+        return self.network.forward_planned(x, plan, edge_attr, halo=halo)

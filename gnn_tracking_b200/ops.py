@@ -15,7 +15,8 @@ from ._lib import (ACT_NONE, ACT_RELU, ACT_SIGMOID_AFFINE, IMPL_AUTO, IMPL_FFMA,
                    SRC_SORTED, GtbError, MlpDesc, Src, check, lib)
 
 __all__ = ["ACT_NONE", "ACT_RELU", "ACT_SIGMOID_AFFINE", "IMPL_AUTO", "IMPL_FFMA", "IMPL_TCGEN05", "Block",
-           "PackedMLP", "fused_mlp", "pack_linears", "require_cuda", "default_impl", "launch_count"]
+           "PackedMLP", "fused_mlp", "pack_linears", "require_cuda", "default_impl", "launch_count", "rows_gather",
+           "tc_slots"]
 
 _LAUNCHES = 0  # kernels launched through the C ABI by this process (bench.py reports it)
 
@@ -82,6 +83,10 @@ class Block:
     relu: bool = False
     projected: bool = False
     sorted_index: bool = False
+    # node-partitioned graphs: maps the per-node table of the OWNED rows (the block itself, or its
+    # pre-projected table) to owned + halo rows (partition.HaloExchange.extend); ``index`` then
+    # addresses the extended table
+    extend: object = None
 
     @property
     def flags(self) -> int:
@@ -111,6 +116,12 @@ def resolve_impl(dims: Sequence[int], impl: int, block_widths: Sequence[int] | N
     bw = list(block_widths) if block_widths else [dims[0]]
     ok = lib().gtb_mlp_packed_bytes(len(dims) - 1, _i32arr(dims), len(bw), _i32arr(bw), IMPL_TCGEN05) > 0
     return IMPL_TCGEN05 if ok else IMPL_FFMA
+
+
+def tc_slots(dims: Sequence[int], block_widths: Sequence[int] | None = None) -> int:
+    """Staging slots the tcgen05 tiles would have beside these weights (0 = unsupported)."""
+    bw = list(block_widths) if block_widths else [dims[0]]
+    return lib().gtb_mlp_tc_slots(len(dims) - 1, _i32arr(dims), len(bw), _i32arr(bw))
 
 
 def pack_linears(weights: Sequence[Tensor], biases: Sequence[Tensor | None], impl: int = IMPL_AUTO,
@@ -201,6 +212,20 @@ def fused_mlp(blocks: Sequence[Block], n_rows: int, packed: PackedMLP, *, final_
         _count(1)
     del keep
     return out if want_out else None
+
+
+def rows_gather(table: Tensor, index: Tensor, out: Tensor | None = None) -> Tensor:
+    """``out[i] = table[index[i]]`` (int32 index): packs the halo rows a peer rank needs."""
+    table = _f32c(table)
+    dev = require_cuda(table, index)
+    n, w = index.numel(), table.size(1)
+    if out is None:
+        out = torch.empty((n, w), dtype=torch.float32, device=dev)
+    if n:
+        check(lib().gtb_rows_gather_f32(table.data_ptr(), table.stride(0), _idx(index), n, w, out.data_ptr(),
+                                        out.stride(0), stream_ptr(dev)))
+        _count(1)
+    return out
 
 
 def rows_inv_l2norm(blocks: Sequence[Block], n_rows: int, eps: float = 1e-12) -> Tensor:

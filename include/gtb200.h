@@ -98,6 +98,12 @@ int gtb_mlp_pack(int n_layers, const int32_t* dims, int n_blocks, const int32_t*
                  const float* const* weights, const float* const* biases /* entries may be NULL */,
                  int impl, void* packed, void* stream);
 
+/* Number of 32 KB shared-memory staging slots the tcgen05 tiles keep beside the packed weights of
+ * this MLP (0: widths unsupported).  The host side uses it to split a long Linear chain where the
+ * weights would leave fewer than two slots (no gather in flight while a tile is computed): the W
+ * head of the edge classifier, edge_classifier.py:79-84 with 2*Dn + De*(L+1) input columns. */
+int gtb_mlp_tc_slots(int n_layers, const int32_t* dims, int n_blocks, const int32_t* block_widths);
+
 /* flags of a source block.
  * GTB_SRC_PROJECTED: the block was already multiplied by its column block of the first Linear
  *   (a per-node table [*, N0], N0 = dims[1]); the gathered rows are ADDED to the output of

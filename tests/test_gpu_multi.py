@@ -1,0 +1,83 @@
+"""Node-partitioned edge classifier on 2 GPUs (NCCL halo exchange per layer) against the
+single-GPU forward of the same graph: 1e-5 on the owned edges / nodes of every rank.
+Needs >= 2 CUDA devices (``gpurun --gpus 2``); skipped otherwise."""
+import os
+import socket
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    from gnn_tracking_b200.models.edge_classifier import ECForGraphTCN
+    from gnn_tracking_b200.partition import HaloExchange, partition_graph
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        gen = torch.Generator().manual_seed(11)
+        n, e = 6000, 50000
+        src = torch.randint(0, n, (e,), generator=gen)
+        dst = (src + torch.randint(-40, 41, (e,), generator=gen)).clamp(0, n - 1)
+        far = torch.rand(e, generator=gen) < 0.03
+        dst = torch.where(far, torch.randint(0, n, (e,), generator=gen), dst)
+        ei = torch.stack([src, dst])
+        x = torch.randn(n, 14, generator=gen)
+        ea = torch.randn(e, 4, generator=gen)
+        errs = {}
+        for name, kw in (("wide", dict(interaction_node_dim=64, interaction_edge_dim=64, hidden_dim=64)),
+                         ("default", dict(hidden_dim=64))):
+            torch.manual_seed(0)
+            m = ECForGraphTCN(node_indim=14, edge_indim=4, L_ec=3, **kw).to(dev)
+            sh = partition_graph(ei, n, world, rank)
+            halo = HaloExchange(sh.to(dev))
+            with torch.no_grad():
+                full = m.forward_tensors(x.to(dev), ei.to(dev), ea.to(dev))
+                part = m.forward_tensors(x[sh.node_lo:sh.node_hi].to(dev), sh.edge_index.to(dev).contiguous(),
+                                         ea[sh.edge_ids].to(dev), halo=halo)
+            torch.cuda.synchronize()
+            ids = sh.edge_ids.to(dev)
+            errs[name] = (float((part["W"] - full["W"][ids]).abs().max()),
+                          float((part["edge_embedding"] - full["edge_embedding"][ids]).abs().max()
+                                / full["edge_embedding"].abs().max().clamp_min(1.0)),
+                          float((part["node_embedding"] - full["node_embedding"][sh.node_lo:sh.node_hi]).abs().max()
+                                / full["node_embedding"].abs().max().clamp_min(1.0)),
+                          sh.n_halo, halo.bytes_sent)
+        q.put((rank, errs))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_partitioned_ec_matches_single_gpu():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, errs in res:
+        for name, (ew, ee, en, n_halo, sent) in errs.items():
+            assert n_halo > 0 and sent > 0, (rank, name)
+            assert ew <= TOL and ee <= TOL and en <= TOL, (rank, name, ew, ee, en)
