@@ -107,3 +107,33 @@ def test_width_mismatch_is_an_assertion_error():
     m = InteractionNetwork(node_indim=3, edge_indim=2)
     with pytest.raises(AssertionError):
         m(torch.zeros(4, 5), torch.zeros(2, 2, dtype=torch.long), torch.zeros(2, 2))
+
+
+def test_install_patches_the_reference_package():
+    """`gnn_tracking_b200.install()` rebinds the hot-path classes inside the reference package
+    (authoring container only: needs /root/reference through the oracle's shims)."""
+    from oracle import reference_loader as rl
+    if not rl.available():
+        pytest.skip("reference sources not present")
+    rl.load()
+    import gnn_tracking_b200
+    import importlib
+    saved = {}
+    for ref_mod, attrs in gnn_tracking_b200._PATCHES.items():
+        mod = importlib.import_module(ref_mod)
+        saved[ref_mod] = {k: getattr(mod, k) for k in attrs}
+    try:
+        done = gnn_tracking_b200.install(strict=True)
+        assert "gnn_tracking.models.resin.InteractionNetwork" in done
+        import gnn_tracking.models.resin as ref_resin
+        import gnn_tracking.models.track_condensation_networks as ref_tcn
+        from gnn_tracking_b200.models.interaction_network import InteractionNetwork
+        assert ref_resin.InteractionNetwork is InteractionNetwork and ref_tcn.IN is InteractionNetwork
+        # a reference-side ResIN now builds B200 layers with the reference's ctor arguments
+        m = ref_resin.ResIN(node_dim=4, edge_dim=3, object_hidden_dim=8, relational_hidden_dim=8, n_layers=2)
+        assert all(isinstance(l, InteractionNetwork) for l in m.network.layers)
+    finally:
+        for ref_mod, attrs in saved.items():
+            mod = importlib.import_module(ref_mod)
+            for k, v in attrs.items():
+                setattr(mod, k, v)
