@@ -17,6 +17,8 @@
 //     scattered by out_index, with the residual fused in) and the in-tile segmented sum by
 //     destination.
 // Reference semantics: see include/gtb200.h (gtb_fused_mlp_f32).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -47,6 +49,10 @@ struct TcLayout {
   int chunk_w[GTB_MAX_SRCS], chunk_koff[GTB_MAX_SRCS], chunk_kpad[GTB_MAX_SRCS];
   int kpad[GTB_MAX_LAYERS], npad[GTB_MAX_LAYERS], ntrue[GTB_MAX_LAYERS], ktiles[GTB_MAX_LAYERS];
   uint32_t w_off[GTB_MAX_LAYERS][2], b_off[GTB_MAX_LAYERS], total_bytes;
+  // a last Linear with <= 4 outputs behind a hidden layer (edge weights, beta) is evaluated on the
+  // CUDA cores from the fp32 activations the row owners already hold: plain fp32 rows [4][kpad],
+  // no MMA, no tf32 split of the last hidden activation
+  int narrow_last;
 };
 
 struct TcChunk {
@@ -71,6 +77,7 @@ struct TcParams {
   const int32_t* ireg_ptr[4];
   int32_t out_mode, out_c4n;      // same for the output rows (out_index)
   int32_t prof;                   // debug: per-stage clock accumulation by one thread
+  int32_t narrow_last;            // see TcLayout
   TcChunk ch[TC_MAXCH];
   TcAdd add[2];
   int32_t kpad[GTB_MAX_LAYERS], npad[GTB_MAX_LAYERS], ntrue[GTB_MAX_LAYERS];
@@ -116,6 +123,7 @@ bool tc_layout(int n_layers, const int32_t* dims, int n_chunks, const int32_t* c
   }
   if (sum != dims[0]) return false;
   L->n_layers = n_layers;
+  L->narrow_last = n_layers >= 2 && dims[n_layers] <= 4;
   uint32_t off = 0;
   for (int l = 0; l < n_layers; ++l) {
     const int n = dims[l + 1];
@@ -124,6 +132,11 @@ bool tc_layout(int n_layers, const int32_t* dims, int n_chunks, const int32_t* c
     L->npad[l] = round_up(n, 16);
     L->kpad[l] = (l == 0) ? k0 : L->npad[l - 1];
     L->ktiles[l] = (L->kpad[l] + 31) / 32;
+    if (l == n_layers - 1 && L->narrow_last) {
+      L->w_off[l][0] = L->w_off[l][1] = off;
+      off += (uint32_t)n * (uint32_t)L->kpad[l] * 4u;  // n rows of kpad floats: a multiple of 64 bytes
+      continue;
+    }
     const uint32_t bytes = (uint32_t)L->ktiles[l] * L->npad[l] * 128u;  // multiple of 2048
     L->w_off[l][0] = off;
     off += bytes;
@@ -132,7 +145,7 @@ bool tc_layout(int n_layers, const int32_t* dims, int n_chunks, const int32_t* c
   }
   for (int l = 0; l < n_layers; ++l) {
     L->b_off[l] = off;
-    off += 64 * 4;
+    off += (l == n_layers - 1 && L->narrow_last) ? 4 * 4 : 64 * 4;
   }
   L->total_bytes = off;
   return (size_t)off + TC_SLOT + TC_MISC <= (size_t)TC_SMEM_MAX;
@@ -163,6 +176,20 @@ struct PackArgs {
 __global__ void pack_tc_kernel(const __grid_constant__ PackArgs a, unsigned char* __restrict__ packed) {
   const TcLayout& L = a.L;
   for (int l = 0; l < L.n_layers; ++l) {
+    if (l == L.n_layers - 1 && L.narrow_last) {  // plain fp32 rows [4][kpad] + bias
+      const int kp = L.kpad[l];
+      const int nr = L.ntrue[l];
+      for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nr * kp + 4; i += gridDim.x * blockDim.x) {
+        if (i < nr * kp) {
+          const int n = i / kp, k = i - n * kp;
+          reinterpret_cast<float*>(packed + L.w_off[l][0])[i] = k < a.ktrue[l] ? a.w[l][(size_t)n * a.ktrue[l] + k] : 0.f;
+        } else {
+          const int n = i - nr * kp;
+          reinterpret_cast<float*>(packed + L.b_off[l])[n] = (a.b[l] != nullptr && n < L.ntrue[l]) ? a.b[l][n] : 0.f;
+        }
+      }
+      continue;
+    }
     const int kext = L.ktiles[l] * 32, npad = L.npad[l];
     const int total = kext * npad;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total + npad; i += gridDim.x * blockDim.x) {
@@ -472,8 +499,9 @@ __device__ __forceinline__ void split_store16(uint32_t taddr_hi, uint32_t taddr_
     }                                                 \
   } while (0)
 
-// W64: every streamed block, every hidden Linear and every pre-projected block is exactly 64 wide
-// (the "wide" Interaction-Network configuration): straight-line tile code without width guards.
+// W64: every staged streamed block, every hidden Linear and every pre-projected block is exactly 64
+// wide (the "wide" Interaction-Network configuration; narrow blocks read directly by the row owner,
+// as in the encoders, are fine): straight-line tile code without width guards.
 // PROF: per-stage clock accumulation by thread 0 of CTA 0 (tests/cuda/tc_diag.py).
 template <bool W64, bool PROF>
 __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __grid_constant__ TcParams p) {
@@ -659,7 +687,7 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
       TC_PROF(2);
       if (wteam == 0) {  // whole warp, uniform operands (see tc_issue_mmas)
         tc_fence_after_sync();
-        if (W64 && c == 0) {
+        if (W64 && ch.staged && c == 0) {
           if (team == 0) tc_issue_mmas_k64<0, 0>(wbase, bar_base, p, true);
           else           tc_issue_mmas_k64<1, 0>(wbase, bar_base, p, true);
         } else {
@@ -685,6 +713,8 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
       float4 pre[8];  // the row owner's columns of the first directly read block, fetched under the MMA
 #pragma unroll
       for (int q = 0; q < 8; ++q) pre[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const bool dot_last = p.narrow_last && l == last - 1;  // the last Linear on the CUDA cores
+      float part[4] = {0.f, 0.f, 0.f, 0.f};
       int n_staged = 0;
       if (l == 0) {
         bool have_pre = false;
@@ -755,13 +785,34 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
         }
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-        split_store16(tm_lane + TM_A_HI + 16 * b, tm_lane + TM_A_LO + 16 * b, v);
+        if (dot_last) {
+          const float* wl = reinterpret_cast<const float*>(wsm + p.w_off[last][0]) + 16 * b;
+          const int kp = p.kpad[last];
+#pragma unroll
+          for (int nn = 0; nn < 4; ++nn) {
+            if (nn < p.ntrue[last]) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 w4 = *reinterpret_cast<const float4*>(wl + nn * kp + 4 * q);
+                part[nn] = fmaf(v[4 * q + 0], w4.x, part[nn]); part[nn] = fmaf(v[4 * q + 1], w4.y, part[nn]);
+                part[nn] = fmaf(v[4 * q + 2], w4.z, part[nn]); part[nn] = fmaf(v[4 * q + 3], w4.w, part[nn]);
+              }
+            }
+          }
+        } else {
+          split_store16(tm_lane + TM_A_HI + 16 * b, tm_lane + TM_A_LO + 16 * b, v);
+        }
+      }
+      if (dot_last) {  // the two column halves of a row meet in the (free) output slot: 16-byte chunks 8 + h
+        uint32_t so = cons_slot + (uint32_t)n_staged;
+        if (so >= ring) so -= ring;
+        sts128(slots + so * TC_SLOT + rsw + (((uint32_t)(8 + h) << 4) ^ rx), make_float4(part[0], part[1], part[2], part[3]));
       }
       tmem_st_wait();
       tc_fence_before_sync();
       team_sync(team);
       TC_PROF(l == 0 ? 8 : 12);
-      if (wteam == 0) {
+      if (wteam == 0 && !dot_last) {
         tc_fence_after_sync();
         if (W64) {
           if (team == 0) { if (l == 0) tc_issue_mmas_k64<0, 1>(wbase, bar_base, p, true); else tc_issue_mmas_k64<0, 2>(wbase, bar_base, p, true); }
@@ -780,12 +831,26 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
     }
 
     // ---------------- output: accumulator -> bias -> activation -> staged tile
-    wait_or_trap(mma_bar, mma_phase);
-    mma_phase ^= 1;
-    tc_fence_after_sync();
-    TC_PROF(13);
     const uint32_t osl = slots + cons_slot * TC_SLOT;  // this item's slot was released `ring` items ago
-    {
+    if (p.narrow_last) {
+      if (h == 0) {
+        const float* bias = reinterpret_cast<const float*>(wsm + p.b_off[last]);
+        const float4 a = lds128(osl + rsw + ((8u << 4) ^ rx)), b = lds128(osl + rsw + ((9u << 4) ^ rx));
+        float v[4] = {a.x + b.x + bias[0], a.y + b.y + bias[1], a.z + b.z + bias[2], a.w + b.w + bias[3]};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (p.final_act == GTB_ACT_RELU) v[j] = fmaxf(v[j], 0.f);
+          else if (p.final_act == GTB_ACT_SIGMOID_AFFINE) v[j] = p.act_eps + (1.f - 2.f * p.act_eps) * (1.f / (1.f + expf(-v[j])));
+        }
+        sts128(osl + rsw + rx, make_float4(v[0], v[1], v[2], v[3]));  // chunk 0 of the own row
+      }
+    } else {
+      wait_or_trap(mma_bar, mma_phase);
+      mma_phase ^= 1;
+      tc_fence_after_sync();
+    }
+    TC_PROF(13);
+    if (!p.narrow_last) {
       const float* bias = reinterpret_cast<const float*>(wsm + p.b_off[last]);
       const int nb = p.npad[last] >> 4, per = (nb + 1) >> 1;
       const int b0 = h * per, b1 = min(nb, b0 + per);
@@ -1057,6 +1122,7 @@ int fused_mlp_tc(const gtb_mlp_desc_t& d, cudaStream_t st) {
     p.b_off[l] = L.b_off[l];
   }
   p.w_bytes = L.total_bytes;
+  p.narrow_last = L.narrow_last;
   p.packed = static_cast<const unsigned char*>(d.packed);
   GTB_REQUIRE((reinterpret_cast<uintptr_t>(d.packed) & 15) == 0, GTB_ERR_BAD_ARG, "gtb_fused_mlp_f32: packed weights must be 16-byte aligned");
   p.final_act = d.final_act;
@@ -1077,11 +1143,25 @@ int fused_mlp_tc(const gtb_mlp_desc_t& d, cudaStream_t st) {
   const size_t fixed = ((size_t)L.total_bytes + 15) / 16 * 16 + TC_MISC;
   const int n_slots = (int)((TC_SMEM_MAX - fixed) / TC_SLOT);
   GTB_REQUIRE(n_slots >= 1, GTB_ERR_UNSUPPORTED_DIM, "gtb_fused_mlp_f32 (tcgen05): weights do not fit in shared memory");
-  // two teams when every team still gets two slots (one item in flight while one is consumed)
-  p.n_teams = (n_slots >= 4 && p.n_tiles > kNumSMs) ? 2 : 1;
+  // two teams whenever there are two slots: with one slot each, a team's gather latency is exposed
+  // but overlaps the other team's conversion / epilogue work (measured better than one team with a
+  // two-slot ring on the W head); GTB_TC_TEAMS=1 forces one team (experiments)
+  static const int force_teams = getenv("GTB_TC_TEAMS") ? atoi(getenv("GTB_TC_TEAMS")) : 0;
+  p.n_teams = (n_slots >= 2 && p.n_tiles > kNumSMs) ? 2 : 1;
+  if (force_teams == 1) p.n_teams = 1;
   p.ring = n_slots / p.n_teams;
   if (p.ring > 4) p.ring = 4;
   if (p.ring > p.ipt) p.ring = p.ipt;  // at most one tile of look-ahead: the index registers hold one tile
+  bool staged_add = false;
+  for (int a2 = 0; a2 < p.n_adds; ++a2) staged_add = staged_add || p.add[a2].staged;
+  if (p.narrow_last && d.n_layers == 2 && staged_add && p.ring < 2) {
+    // the last hidden epilogue then writes its partial dot products into the output slot while it
+    // still reads a staged block: they must be different slots
+    GTB_REQUIRE(n_slots >= 2, GTB_ERR_UNSUPPORTED_DIM, "gtb_fused_mlp_f32 (tcgen05): not enough shared memory for this shape");
+    p.n_teams = 1;
+    p.ring = n_slots < p.ipt ? n_slots : p.ipt;
+    if (p.ring > 4) p.ring = 4;
+  }
   if (d.n_rows == 0) return GTB_OK;
   const size_t smem = fixed + (size_t)p.ring * p.n_teams * TC_SLOT;
   static bool configured = false;  // one process drives one GPU (one rank per device)
@@ -1097,7 +1177,7 @@ int fused_mlp_tc(const gtb_mlp_desc_t& d, cudaStream_t st) {
     configured = true;
   }
   bool w64 = true;  // the straight-line variant: everything in front of the last Linear is 64 wide
-  for (int c2 = 0; c2 < p.n_chunks; ++c2) w64 = w64 && p.ch[c2].staged && p.ch[c2].width == 64;
+  for (int c2 = 0; c2 < p.n_chunks; ++c2) w64 = w64 && (!p.ch[c2].staged || p.ch[c2].width == 64);
   for (int l = 0; l + 1 < d.n_layers; ++l) w64 = w64 && d.dims[l + 1] == 64;
   const int grid = p.n_tiles < kNumSMs ? p.n_tiles : kNumSMs;
   const int nthr = TC_TEAM * p.n_teams;

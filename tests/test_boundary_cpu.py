@@ -50,6 +50,9 @@ def test_packed_bytes_host_logic():
     assert nbytes((64, 64, 64, 64), _lib.IMPL_TCGEN05) == 3 * 2 * (2 * 64 * 128) + 3 * 256
     # blocks are padded to 8 columns each (5 -> 8, 4 -> 8: K0 = 16 -> one K tile); N = 5 -> 16 rows
     assert nbytes((9, 64, 64, 5), _lib.IMPL_TCGEN05, (5, 4)) == 2 * (64 * 128) + 2 * (2 * 64 * 128) + 2 * (2 * 16 * 128) + 3 * 256
+    # a last Linear with <= 4 outputs behind a hidden layer is kept as plain fp32 rows (CUDA-core dot products)
+    assert nbytes((64, 64, 64, 1), _lib.IMPL_TCGEN05) == 2 * 2 * (2 * 64 * 128) + 64 * 4 + 2 * 256 + 16
+    assert L.gtb_mlp_tc_slots(3, (C.c_int32 * 4)(256, 64, 64, 1), 4, (C.c_int32 * 4)(64, 64, 64, 64)) == 2  # the W head: two teams
     assert nbytes((9, 64, 64, 5), _lib.IMPL_TCGEN05, (5, 5)) == 0      # blocks do not sum to K0
     assert nbytes((64, 128, 128, 64), _lib.IMPL_TCGEN05) == 0          # Linear wider than 64: FFMA path
     assert nbytes((18, 64, 64, 1), _lib.IMPL_TCGEN05, (18,)) == 0      # neither 16-byte rows nor narrow
