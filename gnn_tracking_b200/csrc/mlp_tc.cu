@@ -280,6 +280,10 @@ __device__ __forceinline__ const float* row_ptr(const float* base, uint32_t row,
   return reinterpret_cast<const float*>(reinterpret_cast<const char*>(base) + (uint64_t)row * ld4);
 }
 
+__device__ __forceinline__ void red_add_v4(const float* gaddr, const float4& v) {  // 16-byte aligned
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(gaddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 __device__ __forceinline__ uint32_t slot_off(int r, int c4) {  // 16-byte chunk c4 of row r
   return (uint32_t)(r * 256 + ((c4 ^ (r & 7)) << 4));
 }
@@ -469,7 +473,7 @@ __device__ __forceinline__ void split_store8(uint32_t taddr_hi, uint32_t taddr_l
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     float h, l;
-    split_tf32(v[j], h, l);
+    split_tf32_act(v[j], h, l);
     hi[j] = __float_as_uint(h);
     lo[j] = __float_as_uint(l);
   }
@@ -482,7 +486,7 @@ __device__ __forceinline__ void split_store16(uint32_t taddr_hi, uint32_t taddr_
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     float h, l;
-    split_tf32(v[j], h, l);
+    split_tf32_act(v[j], h, l);
     hi[j] = __float_as_uint(h);
     lo[j] = __float_as_uint(l);
   }
@@ -972,7 +976,41 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
     // ---------------- in-tile segmented sum by destination (rows are destination-sorted): thread =
     // (column, 32-row quarter); a warp shares its quarter, so the run boundaries are warp-uniform
     // branches.  One fire-and-forget reduction per (run, column) onto the zero-filled aggregate.
-    if (want_aggr) {
+    const bool aggr_vec = want_aggr && (N & 3) == 0 && (p.aggr_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.aggr) & 15) == 0;
+    if (aggr_vec) {
+      // thread = (4 adjacent columns, group of 8 rows): 8 x 16-byte shared loads, one vector
+      // reduction (red.global.add.v4.f32) per run of equal destinations inside the group
+      if (touch) team_sync(team);
+      const int c4 = tt & 15, rg0 = (tt >> 4) * 8;
+      if (c4 * 4 < N && rg0 < rows_here) {
+        const uint32_t al4 = (uint32_t)p.aggr_ld * 4u;
+        int sg[8];
+        {
+          const uint32_t sa = segs + (uint32_t)rg0 * 4u;
+          int4 s0, s1;
+          asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(s0.x), "=r"(s0.y), "=r"(s0.z), "=r"(s0.w) : "r"(sa) : "memory");
+          asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(s1.x), "=r"(s1.y), "=r"(s1.z), "=r"(s1.w) : "r"(sa + 16) : "memory");
+          sg[0] = s0.x; sg[1] = s0.y; sg[2] = s0.z; sg[3] = s0.w; sg[4] = s1.x; sg[5] = s1.y; sg[6] = s1.z; sg[7] = s1.w;
+        }
+        float4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)  // (rg0 + i) & 7 == i: rg0 is a multiple of 8
+          v[i] = lds128(osl + (uint32_t)(rg0 + i) * 256u + (((uint32_t)c4 << 4) ^ ((uint32_t)i << 4)));
+        int cur = sg[0];
+        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (sg[i] < 0) break;  // rows past the end of the last tile
+          if (sg[i] != cur) {
+            red_add_v4(row_ptr(p.aggr + 4 * c4, (uint32_t)cur, al4), sum);
+            cur = sg[i];
+            sum = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          sum.x += v[i].x; sum.y += v[i].y; sum.z += v[i].z; sum.w += v[i].w;
+        }
+        red_add_v4(row_ptr(p.aggr + 4 * c4, (uint32_t)cur, al4), sum);
+      }
+    } else if (want_aggr) {
       if (touch) team_sync(team);
       const int c = tt & 63, r0 = (tt >> 6) * 32;
       // run starts of this warp's 32 rows as a warp-uniform bit mask; all 32 values of the column

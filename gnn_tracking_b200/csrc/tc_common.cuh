@@ -189,6 +189,14 @@ __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
   hi = rn_tf32(v);
   lo = rn_tf32(v - hi);
 }
+// Activation-side variant used inside the tiles, one instruction cheaper: instead of rounding lo
+// to nearest, scale it by (1 + 2^-11.5) so that the tensor core's truncation (which drops on
+// average 2^-11.5 |lo|: half a tf32 ulp, the ulp being 2^-11..2^-10 of |lo|) is unbiased on
+// average.  The residual per-operand error is <= 2^-22 |v| with zero mean instead of <= 2^-24.
+__device__ __forceinline__ void split_tf32_act(float v, float& hi, float& lo) {
+  hi = rn_tf32(v);
+  lo = (v - hi) * 1.000345266f;
+}
 
 }  // namespace tc
 }  // namespace gtb
