@@ -46,6 +46,7 @@ class MlpDesc(C.Structure):
         ("row_scale", C.c_void_p), ("out_scale", C.c_void_p),
         ("out", C.c_void_p), ("out_index", C.c_void_p), ("out_ld", C.c_int32),
         ("aggr_ld", C.c_int32), ("aggr", C.c_void_p), ("seg_id", C.c_void_p), ("rowptr", C.c_void_p),
+        ("gate", C.c_void_p), ("gate_ld", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -72,11 +73,14 @@ SIGNATURES = {
     "gtb_in_node_forward_f32": (C.c_int, [_vp, _i32, _i32, _vp, _i64, _i32, _i32, _i32, _i32, _vp, C.c_int,
                                           _f32, _f32, _vp, _i32, _vp, _i32, _vp]),
     "gtb_ec_loss_f32": (C.c_int, [_vp, _vp, C.c_int, _i64, _vp, _vp, _f32, C.c_int, _f32, _f32, _f32, _vp, _vp]),
+    "gtb_ec_loss_grad_f32": (C.c_int, [_vp, _vp, C.c_int, _i64, _vp, _vp, _f32, C.c_int, _f32, _f32, _f32, _vp, _vp, _vp]),
     "gtb_oc_workspace_bytes": (_sz, [_i64]),
     "gtb_oc_prepare": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gtb_oc_alphas": (C.c_int, [_vp, _vp, _i64, _f32, _i32, _vp, _vp, _vp]),
     "gtb_oc_potentials": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _i64, _vp, _i32, _f32, _i64, _vp, _vp]),
     "gtb_rows_inv_l2norm_f32": (C.c_int, [C.POINTER(Src), _i32, _i64, _f32, _vp, _vp]),
+    "gtb_rows_atb_f32": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _vp, _i32, _i32, _i64, _vp, _i32, _vp, _vp]),
+    "gtb_rows_scatter_add_f32": (C.c_int, [_vp, _i32, _vp, _i64, _i32, _vp, _i32, _vp]),
     "gtb_rows_gather_f32": (C.c_int, [_vp, _i32, _vp, _i64, _i32, _vp, _i32, _vp]),
     "gtb_rows_scatter_f32": (C.c_int, [_vp, _i32, _vp, _i64, _i32, _vp, _i32, _vp]),
 }

@@ -29,6 +29,10 @@ size_t tc_packed_bytes(int, const int32_t*, int, const int32_t*);
 int pack_tc(int, const int32_t*, int, const int32_t*, const float* const*, const float* const*, void*, cudaStream_t);
 int fused_mlp_tc(const gtb_mlp_desc_t&, cudaStream_t);
 int tc_timeout_flag(int*);
+int ec_loss_grad(const float*, const void*, int, int64_t, const int64_t*, const float*, float, int, float, float, float,
+                 const float*, float*, cudaStream_t);
+int rows_atb(const float*, int, const int32_t*, int, int, const float*, int, int, int64_t, float*, int, float*, cudaStream_t);
+int rows_scatter_add(const float*, int, const int32_t*, int64_t, int, float*, int, cudaStream_t);
 int tc_slots(int, const int32_t*, int, const int32_t*);
 int tc_profile(int, long long*);
 int ec_loss(const float*, const void*, int, int64_t, const int64_t*, const float*, float, int, float, float, float,
@@ -67,6 +71,8 @@ static int validate_desc(const gtb_mlp_desc_t* d) {
   GTB_REQUIRE(d->out != nullptr || d->aggr != nullptr, GTB_ERR_BAD_ARG, "gtb_fused_mlp_f32: no output requested");
   GTB_REQUIRE(d->aggr == nullptr || (d->seg_id != nullptr && d->rowptr != nullptr), GTB_ERR_BAD_ARG,
               "gtb_fused_mlp_f32: aggregate requested without seg_id / rowptr");
+  GTB_REQUIRE(d->gate == nullptr || (d->gate_ld >= d->dims[d->n_layers] && d->aggr == nullptr), GTB_ERR_BAD_ARG,
+              "gtb_fused_mlp_f32: bad gate (row stride below the output width, or combined with an aggregate)");
   return GTB_OK;
 }
 
@@ -219,6 +225,13 @@ int gtb_ec_loss_f32(const float* w, const void* y, int label_kind, int64_t n_edg
                  static_cast<cudaStream_t>(stream));
 }
 
+int gtb_ec_loss_grad_f32(const float* w, const void* y, int label_kind, int64_t n_edges, const int64_t* src,
+                         const float* pt, float pt_thld, int mode, float alpha, float gamma, float pos_weight,
+                         const float* scale, float* dw, void* stream) {
+  return ec_loss_grad(w, y, label_kind, n_edges, src, pt, pt_thld, mode, alpha, gamma, pos_weight, scale, dw,
+                      static_cast<cudaStream_t>(stream));
+}
+
 size_t gtb_oc_workspace_bytes(int64_t n_nodes) { return oc_workspace_bytes(n_nodes); }
 
 int gtb_oc_prepare(const int64_t* object_id, const uint8_t* object_mask, int64_t n_nodes, int64_t* uniq,
@@ -252,6 +265,16 @@ int gtb_rows_gather_f32(const float* src, int32_t src_ld, const int32_t* index, 
 int gtb_rows_scatter_f32(const float* src, int32_t src_ld, const int32_t* index, int64_t n_rows, int32_t width,
                          float* dst, int32_t dst_ld, void* stream) {
   return rows_move(src, src_ld, index, n_rows, width, dst, dst_ld, true, static_cast<cudaStream_t>(stream));
+}
+
+int gtb_rows_atb_f32(const float* a, int32_t a_ld, const int32_t* a_index, int32_t a_relu, int32_t ka, const float* b,
+                     int32_t b_ld, int32_t nb, int64_t n_rows, float* out, int32_t out_ld, float* colsum, void* stream) {
+  return rows_atb(a, a_ld, a_index, a_relu, ka, b, b_ld, nb, n_rows, out, out_ld, colsum, static_cast<cudaStream_t>(stream));
+}
+
+int gtb_rows_scatter_add_f32(const float* src, int32_t src_ld, const int32_t* index, int64_t n_rows, int32_t width,
+                             float* dst, int32_t dst_ld, void* stream) {
+  return rows_scatter_add(src, src_ld, index, n_rows, width, dst, dst_ld, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

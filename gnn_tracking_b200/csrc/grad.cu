@@ -1,0 +1,109 @@
+// Building blocks of the backward pass of the fused row MLP (recompute-based, see
+// gnn_tracking_b200/autograd.py).  The activation-gradient products dX = dY W reuse the forward
+// tiles (gtb_fused_mlp_f32 with transposed weights and the `gate` epilogue); this file holds what
+// has no forward counterpart:
+//   * gtb_rows_atb_f32        : weight / bias gradients, out[Ka, Nb] += sum_r act(A[ia(r)])^T B[r]
+//   * gtb_rows_scatter_add_f32: gradient of a row gather, dst[index[r]] += src[r]
+// Reference semantics: torch autograd through models/mlp.py:59-62 and the index_select /
+// torch.cat / scatter_add_ chain of models/interaction_network.py:67-103.
+#include "common.cuh"
+
+namespace gtb {
+
+constexpr int ATB_ROWS = 64;     // rows per staged tile
+constexpr int ATB_THREADS = 256;
+
+// A tile [64][KA] and B tile [64][NB] in shared memory (KA, NB <= 64, zero padded to 64);
+// thread (ki = tid >> 4, nj = tid & 15) owns the 4 x 4 block out[4 ki .. , 4 nj ..].
+__global__ void __launch_bounds__(ATB_THREADS) rows_atb_kernel(const float* __restrict__ A, int a_ld,
+                                                               const int32_t* __restrict__ a_index, int a_relu, int ka,
+                                                               const float* __restrict__ B, int b_ld, int nb,
+                                                               int64_t n_rows, float* __restrict__ out, int out_ld,
+                                                               float* __restrict__ colsum) {
+  __shared__ __align__(16) float As[ATB_ROWS][68];
+  __shared__ __align__(16) float Bs[ATB_ROWS][68];
+  const int tid = threadIdx.x, ki = tid >> 4, nj = tid & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float csum = 0.f;  // column tid of B (tid < nb)
+  const int64_t n_tiles = (n_rows + ATB_ROWS - 1) / ATB_ROWS;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t row0 = tile * ATB_ROWS;
+    const int rows_here = (int)min((int64_t)ATB_ROWS, n_rows - row0);
+    for (int i = tid; i < ATB_ROWS * 64; i += ATB_THREADS) {
+      const int r = i >> 6, c = i & 63;
+      float a = 0.f, b = 0.f;
+      if (r < rows_here) {
+        if (c < ka) {
+          const int64_t ar = a_index ? (int64_t)__ldg(a_index + row0 + r) : row0 + r;
+          a = __ldg(A + (size_t)ar * a_ld + c);
+          if (a_relu) a = fmaxf(a, 0.f);
+        }
+        if (c < nb) b = __ldg(B + (size_t)(row0 + r) * b_ld + c);
+      }
+      As[r][c] = a;
+      Bs[r][c] = b;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int r = 0; r < ATB_ROWS; ++r) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[r][4 * ki]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[r][4 * nj]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (colsum != nullptr && tid < nb)
+      for (int r = 0; r < rows_here; ++r) csum += Bs[r][tid];
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = 4 * ki + i, n = 4 * nj + j;
+      if (k < ka && n < nb) atomicAdd(out + (size_t)k * out_ld + n, acc[i][j]);
+    }
+  if (colsum != nullptr && tid < nb) atomicAdd(colsum + tid, csum);
+}
+
+int rows_atb(const float* A, int a_ld, const int32_t* a_index, int a_relu, int ka, const float* B, int b_ld, int nb,
+             int64_t n_rows, float* out, int out_ld, float* colsum, cudaStream_t st) {
+  GTB_REQUIRE(A && B && out && ka >= 1 && ka <= 64 && nb >= 1 && nb <= 64 && a_ld >= ka && b_ld >= nb && out_ld >= nb,
+              GTB_ERR_BAD_ARG, "gtb_rows_atb_f32: widths must be in [1, 64] (got %d x %d)", ka, nb);
+  if (n_rows == 0) return GTB_OK;
+  const int64_t n_tiles = (n_rows + ATB_ROWS - 1) / ATB_ROWS;
+  const int grid = (int)imin64(n_tiles, (int64_t)kNumSMs * 4);
+  rows_atb_kernel<<<grid, ATB_THREADS, 0, st>>>(A, a_ld, a_index, a_relu, ka, B, b_ld, nb, n_rows, out, out_ld, colsum);
+  GTB_CHECK_LAUNCH("rows_atb_kernel");
+  return GTB_OK;
+}
+
+__global__ void rows_scatter_add_kernel(const float* __restrict__ src, int src_ld, const int32_t* __restrict__ index,
+                                        int64_t n_rows, int width, float* __restrict__ dst, int dst_ld) {
+  const int64_t total = n_rows * width;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t r = i / width;
+    const int c = (int)(i - r * width);
+    atomicAdd(dst + (size_t)__ldg(index + r) * dst_ld + c, __ldg(src + (size_t)r * src_ld + c));
+  }
+}
+
+int rows_scatter_add(const float* src, int src_ld, const int32_t* index, int64_t n_rows, int width, float* dst,
+                     int dst_ld, cudaStream_t st) {
+  GTB_REQUIRE(src && index && dst && width >= 1, GTB_ERR_BAD_ARG, "gtb_rows_scatter_add_f32: bad arguments");
+  if (n_rows == 0) return GTB_OK;
+  const int64_t total = n_rows * width;
+  const int blocks = (int)imin64((total + 255) / 256, (int64_t)kNumSMs * 32);
+  rows_scatter_add_kernel<<<blocks, 256, 0, st>>>(src, src_ld, index, n_rows, width, dst, dst_ld);
+  GTB_CHECK_LAUNCH("rows_scatter_add_kernel");
+  return GTB_OK;
+}
+
+}  // namespace gtb

@@ -55,6 +55,49 @@ __global__ void ec_loss_kernel(const float* __restrict__ w, const void* __restri
   }
 }
 
+// d(mean loss)/dw per edge, times `scale` (= upstream gradient / n_edges): the analytic derivative
+// of the terms above (torch's BCE backward: (w - y) / max(w (1 - w), 1e-12)).
+__global__ void ec_loss_grad_kernel(const float* __restrict__ w, const void* __restrict__ y, int label_kind,
+                                    int64_t n_edges, const int64_t* __restrict__ src, const float* __restrict__ pt,
+                                    float pt_thld, int mode, float alpha, float gamma, float pos_weight,
+                                    const float* __restrict__ scale, float* __restrict__ dw) {
+  const float sc = __ldg(scale);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += stride) {
+    const float we = w[e];
+    float yraw = label_kind == 0 ? static_cast<const float*>(y)[e]
+                                 : (static_cast<const uint8_t*>(y)[e] ? 1.f : 0.f);
+    float yf = yraw;
+    if (pt != nullptr) yf = (yraw != 0.f && pt[src[e]] > pt_thld) ? 1.f : 0.f;
+    float g;
+    if (mode == 0) {
+      g = (we - yf) / fmaxf(we * (1.f - we), 1e-12f);
+    } else {
+      const float target = (mode == 2) ? (yraw != 0.f ? 1.f : 0.f) : yf;
+      const float pw = (mode == 2) ? yf : pos_weight;
+      const float pn = 1.f - we;
+      const float dpos = -alpha * pw * target * (-gamma * powf(pn, gamma - 1.f) * logf(we) + powf(pn, gamma) / we);
+      const float dneg = -(1.f - alpha) * (1.f - target) * (gamma * powf(we, gamma - 1.f) * logf(pn) - powf(we, gamma) / pn);
+      g = dpos + dneg;
+    }
+    dw[e] = g * sc;
+  }
+}
+
+int ec_loss_grad(const float* w, const void* y, int label_kind, int64_t n_edges, const int64_t* src, const float* pt,
+                 float pt_thld, int mode, float alpha, float gamma, float pos_weight, const float* scale, float* dw,
+                 cudaStream_t st) {
+  GTB_REQUIRE(mode >= 0 && mode <= 2 && (label_kind == 0 || label_kind == 1) && scale && dw, GTB_ERR_BAD_ARG,
+              "gtb_ec_loss_grad_f32: bad arguments");
+  if (n_edges == 0) return GTB_OK;
+  const int threads = 256;
+  const int blocks = (int)imax64(1, imin64((n_edges + threads - 1) / threads, (int64_t)kNumSMs * 8));
+  ec_loss_grad_kernel<<<blocks, threads, 0, st>>>(w, y, label_kind, n_edges, src, pt, pt_thld, mode, alpha, gamma,
+                                                  pos_weight, scale, dw);
+  GTB_CHECK_LAUNCH("ec_loss_grad_kernel");
+  return GTB_OK;
+}
+
 int ec_loss(const float* w, const void* y, int label_kind, int64_t n_edges, const int64_t* src, const float* pt,
             float pt_thld, int mode, float alpha, float gamma, float pos_weight, double* out, cudaStream_t st) {
   GTB_REQUIRE(mode >= 0 && mode <= 2 && (label_kind == 0 || label_kind == 1), GTB_ERR_BAD_ARG,

@@ -236,6 +236,7 @@ fused_mlp_ffma_kernel(const __grid_constant__ gtb_mlp_desc_t d, const __grid_con
     v *= d.res_b;
     if (d.res) v = fmaf(d.res_a, __ldg(d.res + (size_t)(row0 + r) * d.res_ld + n), v);
     if (d.out_scale) v *= __ldg(d.out_scale);
+    if (d.gate && !(__ldg(d.gate + (size_t)(row0 + r) * d.gate_ld + n) > 0.f)) v = 0.f;
     if (d.out) d.out[(size_t)orow[r] * d.out_ld + n] = v;
     if (want_aggr) Hs[r * HS + n] = v;
   }

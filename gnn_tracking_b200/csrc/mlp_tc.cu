@@ -89,6 +89,8 @@ struct TcParams {
   int32_t res_ld;
   const float* row_scale;
   const float* out_scale;
+  const float* gate;
+  int32_t gate_ld;
   float* out;
   const int32_t* out_index;
   int32_t out_ld;
@@ -885,9 +887,11 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
     const bool want_aggr = p.aggr != nullptr;
     const float oscale = p.out_scale ? __ldg(p.out_scale) : 1.f;
     const bool touch = p.res != nullptr || p.res_b != 1.f || p.out_scale != nullptr;
-    const bool vec = (N & 3) == 0 && (p.out == nullptr || ((p.out_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0)) &&
+    // a gate (backward launches only) takes the plain scalar path below
+    const bool vec = p.gate == nullptr && (N & 3) == 0 &&
+                     (p.out == nullptr || ((p.out_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0)) &&
                      (p.res == nullptr || ((p.res_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.res) & 15) == 0));
-    if (p.out != nullptr || touch) {
+    if (p.out != nullptr || touch || p.gate != nullptr) {
       if (vec && p.out_mode != 2 && N == 64) {  // 16 pieces per row: thread tt stores piece (tt & 15) of rows (tt >> 4) + 16 j
         const int rb = tt >> 4, c = tt & 15;
         const uint32_t sp0 = osl + slot_off(rb, c);
@@ -939,7 +943,7 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
             if (p.out) *(reinterpret_cast<float4*>(const_cast<float*>(row_ptr(p.out, orow, (uint32_t)p.out_ld * 4u))) + c) = v;
           }
         }
-      } else if (N == 1 && p.out_mode != 2) {  // one value per row (edge weights): thread = row
+      } else if (N == 1 && p.out_mode != 2 && p.gate == nullptr) {  // one value per row (edge weights): thread = row
         uint32_t orow = row0 + tt;
         if (p.out_mode == 1) orow = (uint32_t)ocur;  // c4n = 1: every lane holds its own row
         if (tt < rows_here) {
@@ -964,6 +968,7 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
             v *= oscale;
             if (want_aggr) sts32(sp, v);
           }
+          if (p.gate && !(__ldg(row_ptr(p.gate, row0 + rr, (uint32_t)p.gate_ld * 4u) + n) > 0.f)) v = 0.f;
           if (p.out) {
             const uint32_t orow = p.out_index ? (uint32_t)__ldg(p.out_index + row0 + rr) : row0 + rr;
             const_cast<float*>(row_ptr(p.out, orow, (uint32_t)p.out_ld * 4u))[n] = v;
@@ -1171,6 +1176,8 @@ int fused_mlp_tc(const gtb_mlp_desc_t& d, cudaStream_t st) {
   p.res_ld = d.res_ld;
   p.row_scale = d.row_scale;
   p.out_scale = d.out_scale;
+  p.gate = d.gate;
+  p.gate_ld = d.gate_ld;
   p.out = d.out;
   p.out_index = d.out_index;
   p.out_ld = d.out_ld;

@@ -16,12 +16,41 @@ from ..._lib import check, lib
 _BCE, _FOCAL, _HAUGHTY = 0, 1, 2
 
 
+class _ECLossFn(torch.autograd.Function):
+    """Mean EC loss with its analytic gradient w.r.t. the edge weights (``gtb_ec_loss_grad_f32``)."""
+
+    @staticmethod
+    def forward(ctx, w, yk, kind, src, ptf, pt_thld, mode, alpha, gamma, pos_weight):
+        dev = w.device
+        out = torch.zeros(2, dtype=torch.float64, device=dev)
+        check(lib().gtb_ec_loss_f32(w.data_ptr(), yk.data_ptr(), kind, w.numel(), None if src is None else src.data_ptr(),
+                                    None if ptf is None else ptf.data_ptr(), float(pt_thld), mode, float(alpha), float(gamma),
+                                    float(pos_weight), out.data_ptr(), ops.stream_ptr(dev)))
+        ops._count(1)
+        ctx.save_for_backward(w, yk, *([src, ptf] if src is not None else []))
+        ctx.cfg = (kind, float(pt_thld), mode, float(alpha), float(gamma), float(pos_weight), src is not None)
+        return (out[0] / out[1]).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, grad):
+        kind, pt_thld, mode, alpha, gamma, pos_weight, has_pt = ctx.cfg
+        saved = ctx.saved_tensors
+        w, yk = saved[0], saved[1]
+        src, ptf = (saved[2], saved[3]) if has_pt else (None, None)
+        scale = (grad.detach().to(torch.float32) / max(w.numel(), 1)).reshape(1).contiguous()
+        dw = torch.empty_like(w)
+        check(lib().gtb_ec_loss_grad_f32(w.data_ptr(), yk.data_ptr(), kind, w.numel(), None if src is None else src.data_ptr(),
+                                         None if ptf is None else ptf.data_ptr(), pt_thld, mode, alpha, gamma, pos_weight,
+                                         scale.data_ptr(), dw.data_ptr(), ops.stream_ptr(w.device)))
+        ops._count(1)
+        return (dw,) + (None,) * 9
+
+
 def _ec_loss(w: Tensor, y: Tensor, *, mode: int, edge_index: Tensor | None, pt: Tensor | None, pt_thld: float,
              alpha: float = 0.25, gamma: float = 2.0, pos_weight: float = 1.0) -> Tensor:
-    dev = ops.require_cuda(w, y)
+    ops.require_cuda(w, y)
+    shape_w = w.shape
     w = w.reshape(-1)
-    assert not torch.is_grad_enabled() or not w.requires_grad, \
-        "gnn_tracking_b200 EC losses are forward-only in this build"
     if w.dtype != torch.float32:
         raise TypeError("w must be float32")
     w = w.contiguous()
@@ -30,20 +59,13 @@ def _ec_loss(w: Tensor, y: Tensor, *, mode: int, edge_index: Tensor | None, pt: 
         yk, kind = y.contiguous().view(torch.uint8), 1
     else:
         yk, kind = y.to(torch.float32).contiguous(), 0
-    src_p = pt_p = None
-    keep = []
+    src = ptf = None
     if not math.isclose(pt_thld, 0.0):  # falsify_low_pt_edges ec.py:71-92
         assert edge_index is not None and pt is not None
         src = edge_index[0].contiguous()
         ptf = pt.to(torch.float32).contiguous()
-        keep += [src, ptf]
-        src_p, pt_p = src.data_ptr(), ptf.data_ptr()
-    out = torch.zeros(2, dtype=torch.float64, device=dev)
-    check(lib().gtb_ec_loss_f32(w.data_ptr(), yk.data_ptr(), kind, w.numel(), src_p, pt_p, float(pt_thld), mode,
-                                float(alpha), float(gamma), float(pos_weight), out.data_ptr(),
-                                ops.stream_ptr(dev)))
-    ops._count(1)
-    return (out[0] / out[1]).to(torch.float32)
+    del shape_w
+    return _ECLossFn.apply(w, yk, kind, src, ptf, pt_thld, mode, alpha, gamma, pos_weight)
 
 
 class FalsifyLowPtEdgeWeightLoss(torch.nn.Module, HyperparametersMixin):

@@ -64,6 +64,6 @@ class ECForGraphTCN(nn.Module, HyperparametersMixin):
         if self.hparams.use_node_embedding:
             blocks += [Block(h, plan.src_sorted, extend=None if halo is None else halo.extend),
                        Block(h, plan.dst_sorted, sorted_index=True)]
-        blocks += [Block(t, plan.perm) for t in (eas if self.hparams.use_intermediate_edge_embeddings else [ea])]
+        blocks += [Block(t, plan.perm, unique_index=True) for t in (eas if self.hparams.use_intermediate_edge_embeddings else [ea])]
         w = self.W.forward_blocks(blocks, e, final_act=ACT_SIGMOID_AFFINE, act_eps=0.001, out_index=plan.perm)
         return {"W": w.squeeze(), "node_embedding": h, "edge_embedding": ea}

@@ -46,12 +46,12 @@ class InteractionNetwork(nn.Module, HyperparametersMixin):
         e_out = self.hparams.edge_outdim
         # zeroed: isolated nodes keep 0 (SumAggregation), partial runs are added atomically
         ext = None if halo is None else halo.extend
-        aggr = torch.zeros((n, e_out), dtype=torch.float32, device=dev)
-        # message(): cat[x_i (target), x_j (source), edge_attr]  (interaction_network.py:75-89)
-        e_tilde = self.relational_model.forward_blocks(
+        # message(): cat[x_i (target), x_j (source), edge_attr]  (interaction_network.py:75-89); the
+        # aggregate starts from zero: isolated nodes keep 0 (SumAggregation)
+        e_tilde, aggr = self.relational_model.forward_blocks(
             [Block(x, plan.dst_sorted, relu_x, sorted_index=True), Block(x, plan.src_sorted, relu_x, extend=ext),
-             Block(edge_attr, plan.perm, relu_e)],
-            e, out_index=plan.perm, aggr=aggr, seg_id=plan.dst_sorted, rowptr=plan.rowptr)
+             Block(edge_attr, plan.perm, relu_e, unique_index=True)],
+            e, out_index=plan.perm, aggr_rows=n, seg_id=plan.dst_sorted, rowptr=plan.rowptr)
         # update(): cat[x, aggr]  (interaction_network.py:92-103)
         x_tilde = self.object_model.forward_blocks([Block(x, None, relu_x), Block(aggr)], n,
                                                    res=res, res_a=res_a, res_b=res_b)

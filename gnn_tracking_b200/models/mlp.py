@@ -74,7 +74,7 @@ class PackedCache:
         return self._packed, self._proj
 
 
-def run_linears(cache: PackedCache, linears: Sequence[nn.Linear], blocks: Sequence[Block], n_rows: int,
+def _run_nograd(cache: PackedCache, linears: Sequence[nn.Linear], blocks: Sequence[Block], n_rows: int,
                 *, final_act: int = ACT_NONE, **epilogue) -> Tensor | None:
     """Linear/ReLU chain over concatenated column blocks; <= 3 Linear layers per
     fused launch, longer chains are split with the intermediate kept in HBM.
@@ -82,11 +82,6 @@ def run_linears(cache: PackedCache, linears: Sequence[nn.Linear], blocks: Sequen
     Gathered blocks of a smaller table (``x[dst]``, ``x[src]`` with E >> N) are multiplied by
     their columns of the first Linear once per table row and the gathered products added
     behind the first Linear -- same sum, 2*Dn*H fewer multiply-adds per edge."""
-    if torch.is_grad_enabled() and (any(b.tensor.requires_grad for b in blocks)
-                                    or any(p.requires_grad for lin in linears for p in lin.parameters())):
-        raise NotImplementedError(
-            "gnn_tracking_b200 kernels are forward-only in this build: call the model under torch.no_grad() "
-            "(there is no silent autograd fallback)")
     blocks = list(blocks)
     widths = [b.tensor.size(1) if b.tensor.dim() > 1 else 1 for b in blocks]
     n0 = linears[0].out_features
@@ -114,6 +109,49 @@ def run_linears(cache: PackedCache, linears: Sequence[nn.Linear], blocks: Sequen
         else:
             return ops.fused_mlp(cur, n_rows, p, final_act=final_act, **epilogue)
     raise AssertionError("unreachable")
+
+
+def run_linears(cache: PackedCache, linears: Sequence[nn.Linear], blocks: Sequence[Block], n_rows: int,
+                *, final_act: int = ACT_NONE, aggr_rows: int | None = None, **epilogue):
+    """``_run_nograd`` plus autograd (``autograd.FusedMLPFunction``, recompute-based backward through
+    the same kernels) when a block, a weight or the residual requires a gradient.  With
+    ``aggr_rows`` the per-destination sum is returned as well: ``(out, aggr)``."""
+    res = epilogue.get("res")
+    needs_grad = torch.is_grad_enabled() and (
+        any(b.tensor.requires_grad for b in blocks) or any(p.requires_grad for lin in linears for p in lin.parameters())
+        or (res is not None and res.requires_grad))
+    if not needs_grad:
+        if aggr_rows is None:
+            return _run_nograd(cache, linears, blocks, n_rows, final_act=final_act, **epilogue)
+        dev = blocks[0].tensor.device
+        aggr = torch.zeros((aggr_rows, linears[-1].out_features), dtype=torch.float32, device=dev)
+        out = _run_nograd(cache, linears, blocks, n_rows, final_act=final_act, aggr=aggr, **epilogue)
+        return out, aggr
+    from ..autograd import _BwdPacks, fused_mlp_autograd
+    bad = [k for k in ("row_scale", "out_scale", "out", "gate", "aggr") if epilogue.get(k) is not None]
+    if bad or epilogue.get("want_out") is False:
+        raise NotImplementedError(f"backward with the epilogue options {bad or ['want_out=False']} is not implemented")
+    if not hasattr(cache, "bwd"):
+        cache.bwd = _BwdPacks()
+
+    def runner(cfg, block_tensors, res_t):
+        bl = [Block(t, m[0], m[1], sorted_index=s, unique_index=m[2]) for t, m, s in zip(block_tensors, cfg["blocks"], cfg["sorted"])]
+        dev = block_tensors[0].device
+        aggr = None
+        kw = {}
+        if cfg["aggr_rows"] is not None:
+            aggr = torch.zeros((cfg["aggr_rows"], linears[-1].out_features), dtype=torch.float32, device=dev)
+            kw.update(aggr=aggr, seg_id=cfg["seg_id"], rowptr=cfg["rowptr"])
+        if res_t is not None:
+            kw.update(res=res_t, res_a=cfg["res_a"])
+        out = _run_nograd(cache, linears, bl, cfg["n_rows"], final_act=cfg["final_act"], act_eps=cfg["act_eps"],
+                          res_b=cfg["res_b"], out_index=cfg["out_index"], **kw)
+        return out, aggr
+
+    return fused_mlp_autograd(runner, cache.bwd, linears, blocks, n_rows, final_act=final_act,
+                              act_eps=epilogue.get("act_eps", 0.0), res=res, res_a=epilogue.get("res_a", 0.0),
+                              res_b=epilogue.get("res_b", 1.0), out_index=epilogue.get("out_index"), aggr_rows=aggr_rows,
+                              seg_id=epilogue.get("seg_id"), rowptr=epilogue.get("rowptr"))
 
 
 class MLP(nn.Module):
@@ -192,6 +230,10 @@ class ResFCNN(nn.Module):
             nn.init.normal_(p.data, mean=0.0, std=math.sqrt(var))
 
     def forward_blocks(self, blocks: Sequence[Block], n_rows: int, *, final_act: int = ACT_NONE) -> Tensor:
+        if torch.is_grad_enabled() and (any(b.tensor.requires_grad for b in blocks)
+                                        or any(p.requires_grad for p in self.parameters())):
+            raise NotImplementedError("ResFCNN (the GraphTCN node encoder) is forward-only in this build: "
+                                      "call it under torch.no_grad()")
         inv = ops.rows_inv_l2norm(blocks, n_rows, 1e-12)
         if len(self._layers) == 0:
             p = self._cache.get([self._encoder, self._decoder], [b.tensor.size(1) for b in blocks])[0][0]

@@ -83,6 +83,7 @@ class Block:
     relu: bool = False
     projected: bool = False
     sorted_index: bool = False
+    unique_index: bool = False   # hint: ``index`` is a permutation of the table's rows (the plan's ``perm``)
     # node-partitioned graphs: maps the per-node table of the OWNED rows (the block itself, or its
     # pre-projected table) to owned + halo rows (partition.HaloExchange.extend); ``index`` then
     # addresses the extended table
@@ -167,7 +168,7 @@ def fused_mlp(blocks: Sequence[Block], n_rows: int, packed: PackedMLP, *, final_
               act_eps: float = 0.0, res: Tensor | None = None, res_a: float = 0.0, res_b: float = 1.0,
               row_scale: Tensor | None = None, out_scale: Tensor | None = None, out: Tensor | None = None, out_index: Tensor | None = None,
               want_out: bool = True, aggr: Tensor | None = None, seg_id: Tensor | None = None,
-              rowptr: Tensor | None = None, out_rows: int | None = None) -> Tensor | None:
+              rowptr: Tensor | None = None, out_rows: int | None = None, gate: Tensor | None = None) -> Tensor | None:
     """``out[orow(r)] = epilogue(MLP(cat_s act_s(block_s[irow_s(r)])))`` -- see
     ``gtb_fused_mlp_f32`` in include/gtb200.h."""
     tensors = [_f32c(b.tensor) for b in blocks]
@@ -204,6 +205,9 @@ def fused_mlp(blocks: Sequence[Block], n_rows: int, packed: PackedMLP, *, final_
             out = torch.empty((n_rows if out_rows is None else out_rows, n_out), dtype=torch.float32, device=dev)
         d.out, d.out_ld = out.data_ptr(), out.stride(0)
         d.out_index = _idx(out_index)
+    if gate is not None:
+        gate = _f32c(gate)
+        d.gate, d.gate_ld = gate.data_ptr(), gate.stride(0)
     if aggr is not None:
         d.aggr, d.aggr_ld = aggr.data_ptr(), aggr.stride(0)
         d.seg_id, d.rowptr = _idx(seg_id), _idx(rowptr)
@@ -212,6 +216,36 @@ def fused_mlp(blocks: Sequence[Block], n_rows: int, packed: PackedMLP, *, final_
         _count(1)
     del keep
     return out if want_out else None
+
+
+def rows_atb(a: Tensor, b: Tensor, out: Tensor, *, a_index: Tensor | None = None, a_relu: bool = False,
+             colsum: Tensor | None = None) -> None:
+    """``out[Ka, Nb] += act(a[a_index])^T @ b`` (and ``colsum += b.sum(0)``): weight / bias gradient
+    of one Linear.  Blocks wider than 64 columns are split here."""
+    a, b = _f32c(a), _f32c(b)
+    dev = require_cuda(a, b, out)
+    n = b.size(0)
+    for k0 in range(0, a.size(1), 64):
+        ka = min(64, a.size(1) - k0)
+        for n0 in range(0, b.size(1), 64):
+            nb = min(64, b.size(1) - n0)
+            cs = None
+            if colsum is not None and k0 == 0:
+                cs = colsum.data_ptr() + 4 * n0
+            check(lib().gtb_rows_atb_f32(a.data_ptr() + 4 * k0, a.stride(0), _idx(a_index), int(a_relu), ka,
+                                         b.data_ptr() + 4 * n0, b.stride(0), nb, n,
+                                         out.data_ptr() + 4 * (k0 * out.stride(0) + n0), out.stride(0), cs, stream_ptr(dev)))
+            _count(1)
+
+
+def rows_scatter_add(src: Tensor, index: Tensor, dst: Tensor) -> None:
+    """``dst[index[r]] += src[r]`` (int32 index): gradient of a row gather."""
+    src = _f32c(src)
+    dev = require_cuda(src, index, dst)
+    if src.size(0):
+        check(lib().gtb_rows_scatter_add_f32(src.data_ptr(), src.stride(0), _idx(index), src.size(0), src.size(1),
+                                             dst.data_ptr(), dst.stride(0), stream_ptr(dev)))
+        _count(1)
 
 
 def rows_gather(table: Tensor, index: Tensor, out: Tensor | None = None) -> Tensor:

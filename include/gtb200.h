@@ -165,6 +165,12 @@ typedef struct {
   float*    aggr;
   const int32_t* seg_id;
   const int32_t* rowptr;
+  /* optional gate [n_rows, gate_ld] in launch-row order: out = gate > 0 ? value : 0 after the
+   * epilogue above.  The backward pass multiplies dY W by the ReLU mask of the recomputed
+   * activation with it (d relu, models/mlp.py:44-51). */
+  const float* gate;
+  int32_t   gate_ld;
+  int32_t   reserved;
 } gtb_mlp_desc_t;
 
 int gtb_fused_mlp_f32(const gtb_mlp_desc_t* desc, void* stream);
@@ -217,6 +223,13 @@ int gtb_ec_loss_f32(const float* w, const void* y, int label_kind, int64_t n_edg
                     int mode, float alpha, float gamma, float pos_weight,
                     double* out /* [2] */, void* stream);
 
+/* dw[e] = (*scale) * d term_e / d w_e for the same modes (scale = upstream gradient / n_edges, a
+ * device scalar): backward of the losses above; BCE as torch does, (w - y) / max(w (1 - w), 1e-12). */
+int gtb_ec_loss_grad_f32(const float* w, const void* y, int label_kind, int64_t n_edges,
+                         const int64_t* src, const float* pt, float pt_thld,
+                         int mode, float alpha, float gamma, float pos_weight,
+                         const float* scale, float* dw, void* stream);
+
 /* ------------------------------------------------------- condensation loss (tiger)
  * metrics/losses/oc.py:251-347 without the N x K planes.
  *   beta [N], x [N, d] (ld = d), object_id int64 [N], object_mask uint8 [N]
@@ -252,6 +265,19 @@ int gtb_rows_gather_f32(const float* src, int32_t src_ld, const int32_t* index, 
                         int32_t width, float* dst, int32_t dst_ld, void* stream);
 int gtb_rows_scatter_f32(const float* src, int32_t src_ld, const int32_t* index, int64_t n_rows,
                          int32_t width, float* dst, int32_t dst_ld, void* stream);
+
+/* ------------------------------------------------------------- backward blocks
+ * out[Ka, Nb] += sum_r act(A[ia(r), 0:Ka])^T B[r, 0:Nb] and (colsum != NULL) colsum[Nb] += sum_r B[r]:
+ * the weight and bias gradients of one Linear (torch autograd of models/mlp.py:59-62), with the
+ * gather / ReLU-on-load of the forward source block (a_index NULL = identity rows).  Ka, Nb <= 64;
+ * out / colsum are accumulated atomically (zero them first). */
+int gtb_rows_atb_f32(const float* a, int32_t a_ld, const int32_t* a_index, int32_t a_relu, int32_t ka,
+                     const float* b, int32_t b_ld, int32_t nb, int64_t n_rows,
+                     float* out, int32_t out_ld, float* colsum, void* stream);
+/* dst[index[r], 0:width] += src[r, 0:width]: the gradient of a row gather x[index]
+ * (index_select inside MessagePassing.propagate, models/interaction_network.py:67). */
+int gtb_rows_scatter_add_f32(const float* src, int32_t src_ld, const int32_t* index, int64_t n_rows,
+                             int32_t width, float* dst, int32_t dst_ld, void* stream);
 
 #ifdef __cplusplus
 }
