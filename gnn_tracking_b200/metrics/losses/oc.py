@@ -19,6 +19,9 @@ def condensation_loss_tiger(*, beta: Tensor, x: Tensor, object_id: Tensor, objec
     if max_n_rep:
         raise NotImplementedError("max_n_rep sub-sampling uses the reference's fp16 torch RNG stream and is "
                                   "not reproduced; the tiled kernel needs no sub-sampling to fit in memory")
+    if torch.is_grad_enabled() and (beta.requires_grad or x.requires_grad):
+        raise NotImplementedError("the condensation loss is forward-only in this build: call it under torch.no_grad() "
+                                  "(there is no silent autograd fallback)")
     dev = ops.require_cuda(beta, x, object_id, object_mask)
     n, d = x.shape
     st = ops.stream_ptr(dev)
