@@ -31,7 +31,7 @@ constexpr int TC_SLOT = TC_TM * 256;       // one staging slot: [128 rows][64 fp
 constexpr int TC_MAXCH = 8;                // streamed sub-blocks (<= 64 columns each) of the first Linear
 constexpr int TC_MAXITEMS = TC_MAXCH + 3;
 constexpr int TC_SMEM_MAX = 232448;        // 227 KB opt-in shared memory per CTA
-constexpr int TC_HEAD = 1056;              // per team: 128 segment ids + MMA barrier; TMEM slot
+constexpr int TC_HEAD = 1072;              // per team: 128 segment ids + two MMA barriers; TMEM slot
 constexpr int TC_MISC = TC_HEAD + 1023;    // + slack to align the weight tiles to 1024 bytes
 constexpr uint32_t TM_A_HI = 0, TM_A_LO = 64, TM_D = 128, TM_CTX = 192;  // TMEM column map of one team
 
@@ -438,7 +438,7 @@ __device__ __forceinline__ void tc_issue_mmas(uint32_t wbase, uint32_t bar_base,
         }
       }
     }
-    mma_commit_addr(bar_base + TEAM * 8);
+    mma_commit_addr(bar_base + TEAM * 16);
   }
   __syncwarp();
 }
@@ -446,26 +446,35 @@ __device__ __forceinline__ void tc_issue_mmas(uint32_t wbase, uint32_t bar_base,
 // The common case -- a 64-wide block / layer starting at K = 0 -- with the layer index a template
 // constant and everything unrolled: operands are kernel-parameter loads plus immediates, which
 // ptxas keeps in uniform registers (no R2UR in front of every UTCHMMA).
+// `halves`: a 64-wide output is issued as two N = 32 chains with one commit each, output columns
+// 0..31 first: the epilogue of the first half then runs under the MMAs of the second.
 template <int TEAM, int L>
-__device__ __forceinline__ void tc_issue_mmas_k64(uint32_t wbase, uint32_t bar_base, const TcParams& p, bool first) {
+__device__ __forceinline__ void tc_issue_mmas_k64(uint32_t wbase, uint32_t bar_base, const TcParams& p, bool first,
+                                                  bool halves) {
   constexpr uint32_t tmc = TEAM * TM_CTX;
-  const uint32_t idesc = make_idesc_tf32(TC_TM, p.npad[L]);
+  const uint32_t n = halves ? 32u : (uint32_t)p.npad[L];
+  const uint32_t idesc = make_idesc_tf32(TC_TM, (int)n);
   const uint32_t tile16 = (uint32_t)p.npad[L] * 8u;
   const uint64_t bd_hi = make_smem_desc_sw128(wbase + p.w_off[L][0]);
   const uint64_t bd_lo = make_smem_desc_sw128(wbase + p.w_off[L][1]);
   if (elect_one()) {  // ptxas knows a single lane runs this branch: operands go to uniform registers once
-    bool acc = !first;
+#pragma unroll 1
+    for (uint32_t hf = 0; hf < (halves ? 2u : 1u); ++hf) {
+      bool acc = !first;
+      const uint32_t d = tmc + TM_D + 32u * hf;
+      const uint64_t rows = (uint64_t)(hf * 256u);  // 32 rows x 128 bytes of every K tile, >> 4
 #pragma unroll
-    for (int pass = 0; pass < 3; ++pass) {
-      const uint32_t a = tmc + ((pass == 0) ? TM_A_LO : TM_A_HI);
-      const uint64_t bd = (pass == 1) ? bd_lo : bd_hi;
+      for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t a = tmc + ((pass == 0) ? TM_A_LO : TM_A_HI);
+        const uint64_t bd = ((pass == 1) ? bd_lo : bd_hi) + rows;
 #pragma unroll
-      for (int ks = 0; ks < 8; ++ks) {
-        mma_tf32_ts(tmc + TM_D, a + 8 * ks, bd + (uint64_t)((ks >> 2) * tile16 + (ks & 3) * 2), idesc, acc);
-        acc = true;
+        for (int ks = 0; ks < 8; ++ks) {
+          mma_tf32_ts(d, a + 8 * ks, bd + (uint64_t)((ks >> 2) * tile16 + (ks & 3) * 2), idesc, acc);
+          acc = true;
+        }
       }
+      mma_commit_addr(bar_base + TEAM * 16 + hf * 8);  // one barrier per half: a waiter never lags two phases
     }
-    mma_commit_addr(bar_base + TEAM * 8);
   }
   __syncwarp();
 }
@@ -524,8 +533,8 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
   const uint32_t slots = wbase + ((p.w_bytes + 15u) & ~15u) + (uint32_t)team * ring * TC_SLOT;  // this team's ring
   const uint32_t segs = sm0 + (uint32_t)team * (TC_TM * 4);
   const uint32_t bar_base = sm0 + 2 * TC_TM * 4;
-  const uint32_t mma_bar = bar_base + team * 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 2 * TC_TM * 4 + 16);
+  const uint32_t mma_bar = bar_base + team * 16, mma_bar1 = mma_bar + 8;  // second barrier: second output half
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 2 * TC_TM * 4 + 32);
   const uint32_t rsw = (uint32_t)r * 256u, rx = (uint32_t)(r & 7) << 4;  // own row in a slot: rsw + ((c4 << 4) ^ rx)
   const bool prof_on = PROF && blockIdx.x == 0 && tid == 0;
   long long prof_t = prof_on ? clock64() : 0;
@@ -588,6 +597,7 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
   }
   if (tt == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mma_bar), "r"(1) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mma_bar1), "r"(1) : "memory");
     fence_barrier_init();
   }
   const uint32_t tmem_cols = p.n_teams == 2 ? 512u : 256u;
@@ -603,8 +613,12 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
   }
   const uint32_t tmc = (uint32_t)team * TM_CTX;                             // this team's TMEM columns
   const uint32_t tm_lane = tmc + ((uint32_t)((warp & 3) * 32) << 16);      // + this warp's 32 lanes
-  uint32_t mma_phase = 0;
+  uint32_t mma_phase = 0, mma_phase1 = 0;
   const int last = p.n_layers - 1;
+  // A 64-wide LAST Linear of the straight-line variant is produced in two halves (tc_issue_mmas_k64):
+  // its epilogue only writes shared memory.  Hidden layers are not: their epilogue overwrites the TMEM
+  // A operand the second half's MMAs would still be reading.
+  const bool halves0 = W64 && last == 0 && p.n_chunks == 1 && p.ch[0].staged && p.npad[0] == 64;
   TC_PROF(0);
 
   for (int t = 0;; ++t) {
@@ -694,8 +708,8 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
       if (wteam == 0) {  // whole warp, uniform operands (see tc_issue_mmas)
         tc_fence_after_sync();
         if (W64 && ch.staged && c == 0) {
-          if (team == 0) tc_issue_mmas_k64<0, 0>(wbase, bar_base, p, true);
-          else           tc_issue_mmas_k64<1, 0>(wbase, bar_base, p, true);
+          if (team == 0) tc_issue_mmas_k64<0, 0>(wbase, bar_base, p, true, halves0);
+          else           tc_issue_mmas_k64<1, 0>(wbase, bar_base, p, true, halves0);
         } else {
           if (team == 0) tc_issue_mmas<0>(wbase, bar_base, p, 0, ch.koff, groups, c == 0);
           else           tc_issue_mmas<1>(wbase, bar_base, p, 0, ch.koff, groups, c == 0);
@@ -738,7 +752,7 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
             if (!have_pre) {
               have_pre = true;
 #pragma unroll
-              for (int q = 0; q < 8; ++q) {
+              for (int q = 0; q < 8; ++q) {  // pre[4 bi + q]: 16-byte piece q of this thread's block bi
                 const int c4 = 4 * b0 + q;
                 if (W64 || (q < 4 * (b1 - b0) && c4 * 4 < p.ntrue[0])) pre[q] = __ldg(reinterpret_cast<const float4*>(rowp) + c4);
               }
@@ -749,15 +763,14 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
         }
       }
       TC_PROF(5);
-      wait_or_trap(mma_bar, mma_phase);
-      mma_phase ^= 1;
-      tc_fence_after_sync();
-      TC_PROF(l == 0 ? 6 : 11);
       if (n_staged > 0) {
         cp_async_wait_pending(issued - consumed - n_staged);
         team_sync(team);
       }
       TC_PROF(7);
+      wait_or_trap(mma_bar, mma_phase);  // every thread, also one without a column block
+      mma_phase ^= 1;
+      tc_fence_after_sync();
 #pragma unroll
       for (int bi = 0; bi < 2; ++bi) {  // at most two 16-column blocks per thread
         const int b = b0 + bi;
@@ -821,8 +834,9 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
       if (wteam == 0 && !dot_last) {
         tc_fence_after_sync();
         if (W64) {
-          if (team == 0) { if (l == 0) tc_issue_mmas_k64<0, 1>(wbase, bar_base, p, true); else tc_issue_mmas_k64<0, 2>(wbase, bar_base, p, true); }
-          else           { if (l == 0) tc_issue_mmas_k64<1, 1>(wbase, bar_base, p, true); else tc_issue_mmas_k64<1, 2>(wbase, bar_base, p, true); }
+          const bool hv_next = l + 1 == last && p.npad[last] == 64;  // only the last Linear, see halves0
+          if (team == 0) { if (l == 0) tc_issue_mmas_k64<0, 1>(wbase, bar_base, p, true, hv_next); else tc_issue_mmas_k64<0, 2>(wbase, bar_base, p, true, hv_next); }
+          else           { if (l == 0) tc_issue_mmas_k64<1, 1>(wbase, bar_base, p, true, hv_next); else tc_issue_mmas_k64<1, 2>(wbase, bar_base, p, true, hv_next); }
         } else {
           if (team == 0) tc_issue_mmas<0>(wbase, bar_base, p, l + 1, 0, p.kpad[l + 1] >> 3, true);
           else           tc_issue_mmas<1>(wbase, bar_base, p, l + 1, 0, p.kpad[l + 1] >> 3, true);
@@ -850,17 +864,25 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
         }
         sts128(osl + rsw + rx, make_float4(v[0], v[1], v[2], v[3]));  // chunk 0 of the own row
       }
-    } else {
-      wait_or_trap(mma_bar, mma_phase);
-      mma_phase ^= 1;
-      tc_fence_after_sync();
     }
     TC_PROF(13);
     if (!p.narrow_last) {
       const float* bias = reinterpret_cast<const float*>(wsm + p.b_off[last]);
       const int nb = p.npad[last] >> 4, per = (nb + 1) >> 1;
       const int b0 = h * per, b1 = min(nb, b0 + per);
-      for (int b = b0; b < b1; ++b) {
+      // the last accumulator arrives in two halves when it was issued that way (see halves0 / hv_next)
+      const bool hv = W64 && p.npad[last] == 64 && (last > 0 || halves0);
+      wait_or_trap(mma_bar, mma_phase);
+      mma_phase ^= 1;
+      tc_fence_after_sync();
+      for (int bi = 0; bi < 2; ++bi) {
+        const int b = hv ? (bi == 0 ? h : 2 + h) : b0 + bi;
+        if (!hv && b >= b1) break;
+        if (hv && bi == 1) {
+          wait_or_trap(mma_bar1, mma_phase1);
+          mma_phase1 ^= 1;
+          tc_fence_after_sync();
+        }
         uint32_t acc[16];
         tmem_ld16(tm_lane + TM_D + 16 * b, acc);
         tmem_ld_wait();
