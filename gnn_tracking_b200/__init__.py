@@ -23,7 +23,10 @@ _PATCHES = {
     "gnn_tracking.metrics.losses.ec": {"EdgeWeightBCELoss": ("metrics.losses.ec", "EdgeWeightBCELoss"),
                                        "EdgeWeightFocalLoss": ("metrics.losses.ec", "EdgeWeightFocalLoss"),
                                        "HaughtyFocalLoss": ("metrics.losses.ec", "HaughtyFocalLoss")},
-    "gnn_tracking.metrics.losses.oc": {"CondensationLossTiger": ("metrics.losses.oc", "CondensationLossTiger")},
+    "gnn_tracking.metrics.losses.oc": {"CondensationLossTiger": ("metrics.losses.oc", "CondensationLossTiger"),
+                                       "CondensationLossRG": ("metrics.losses.oc", "CondensationLossRG")},
+    "gnn_tracking.metrics.losses.metric_learning": {
+        "GraphConstructionHingeEmbeddingLoss": ("metrics.losses.metric_learning", "GraphConstructionHingeEmbeddingLoss")},
 }
 
 

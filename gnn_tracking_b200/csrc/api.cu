@@ -29,6 +29,9 @@ size_t tc_packed_bytes(int, const int32_t*, int, const int32_t*);
 int pack_tc(int, const int32_t*, int, const int32_t*, const float* const*, const float* const*, void*, cudaStream_t);
 int fused_mlp_tc(const gtb_mlp_desc_t&, cudaStream_t);
 int tc_timeout_flag(int*);
+int radius_pair_sum(const float*, int, int64_t, const int64_t*, const int64_t*, const unsigned char*, const float*, float, float,
+                    float, float, int, int, double*, cudaStream_t);
+int edge_dist_pow_sum(const float*, int, const int64_t*, int64_t, const unsigned char*, float, double*, cudaStream_t);
 int ec_loss_grad(const float*, const void*, int, int64_t, const int64_t*, const float*, float, int, float, float, float,
                  const float*, float*, cudaStream_t);
 int rows_atb(const float*, int, const int32_t*, int, int, const float*, int, int, int64_t, float*, int, float*, cudaStream_t);
@@ -250,6 +253,18 @@ int gtb_oc_potentials(const float* beta, const float* x, int32_t d, const int64_
                       int32_t k, float q_min, int64_t noise_threshold, double* out, void* stream) {
   return oc_potentials(beta, x, d, object_id, object_mask, obj_slot, n_nodes, alphas, k, q_min, noise_threshold,
                        out, static_cast<cudaStream_t>(stream));
+}
+
+int gtb_radius_pair_sum_f32(const float* x, int32_t d, int64_t n, const int64_t* batch, const int64_t* pid,
+                            const uint8_t* src_flag, const float* beta, float q_min, float r, float p, float eps,
+                            int32_t max_num_neighbors, int32_t mode, double* out, void* stream) {
+  return radius_pair_sum(x, d, n, batch, pid, src_flag, beta, q_min, r, p, eps, max_num_neighbors, mode, out,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int gtb_edge_dist_pow_sum_f32(const float* x, int32_t d, const int64_t* edges, int64_t n_edges, const uint8_t* src_flag,
+                              float p, double* out, void* stream) {
+  return edge_dist_pow_sum(x, d, edges, n_edges, src_flag, p, out, static_cast<cudaStream_t>(stream));
 }
 
 int gtb_rows_inv_l2norm_f32(const gtb_src_t* srcs, int32_t n_srcs, int64_t n_rows, float eps, float* inv_norm,

@@ -1,5 +1,6 @@
-"""Object-condensation loss "tiger" behind the reference interface (reference
-metrics/losses/oc.py:251-436) without the N x K planes (``gtb_oc_*``)."""
+"""Object-condensation losses behind the reference interface: "tiger" (reference
+metrics/losses/oc.py:251-436) without the N x K planes (``gtb_oc_*``) and the radius-graph variant
+(oc.py:87-248) without the radius graph (``gtb_radius_pair_sum_f32``)."""
 from __future__ import annotations
 
 import torch
@@ -58,6 +59,31 @@ def condensation_loss_tiger(*, beta: Tensor, x: Tensor, object_id: Tensor, objec
     return losses, {"n_rep": n_rep.to(torch.int64), "alphas": alphas, "unique_ids": uniq[:k]}
 
 
+def condensation_loss_rg(*, beta: Tensor, x: Tensor, particle_id: Tensor, mask: Tensor, q_min: float,
+                         radius_threshold: float = 1.0, max_num_neighbors: int = 256):
+    """``_radius_graph_condensation_loss`` (oc.py:87-161).  Condensation points, attraction and the
+    coward term are those of the tiger kernels (the most-charged hit of every particle of interest;
+    the reference's argsort-by-beta + first occurrence picks the same hit); the repulsion runs over
+    the radius-graph edges that start at a condensation point (``gtb_radius_pair_sum_f32`` mode 1:
+    ``sqrt(1e-9 + d^2)``, neighbour cap), the noise term over ``particle_id == 0`` exactly."""
+    from .metric_learning import radius_pair_sum
+    tiger, extra = condensation_loss_tiger(beta=beta, x=x, object_id=particle_id, object_mask=mask, q_min=q_min)
+    n = x.size(0)
+    k = extra["alphas"].numel()
+    is_cp = torch.zeros(n, dtype=torch.bool, device=x.device)
+    is_cp[extra["alphas"].long()] = True
+    rep = radius_pair_sum(x=x, particle_id=particle_id, src_flag=is_cp, r=radius_threshold, mode=1, beta=beta, q_min=q_min,
+                          eps=1e-9, max_num_neighbors=max_num_neighbors)
+    eps = 1e-9
+    losses = {
+        "attractive": tiger["attractive"],
+        "repulsive": (rep[0] / (eps + (k - 1) * n)).float(),
+        "coward": tiger["coward"],
+        "noise": (rep[2] / rep[3]).float(),  # NaN without noise hits, as torch.mean of an empty selection
+    }
+    return losses, {}
+
+
 class CondensationLossTiger(MultiLossFct, HyperparametersMixin):
     def __init__(self, *, lw_repulsive: float = 1.0, lw_noise: float = 0.0, lw_coward: float = 0.0,
                  q_min: float = 0.01, pt_thld: float = 0.9, max_eta: float = 4.0, max_n_rep: int = 0,
@@ -78,3 +104,28 @@ class CondensationLossTiger(MultiLossFct, HyperparametersMixin):
                                                 q_min=hp.q_min, noise_threshold=0, max_n_rep=hp.max_n_rep)
         weights = {"attractive": 1.0, "repulsive": hp.lw_repulsive, "noise": hp.lw_noise, "coward": hp.lw_coward}
         return MultiLossFctReturn(loss_dct=losses, weight_dct=weights, extra_metrics={"n_rep": extra["n_rep"]})
+
+
+class CondensationLossRG(MultiLossFct, HyperparametersMixin):
+    def __init__(self, *, lw_repulsive: float = 1.0, lw_noise: float = 0.0, lw_coward: float = 0.0,
+                 q_min: float = 0.01, pt_thld: float = 0.9, max_eta: float = 4.0, max_num_neighbors: int = 256,
+                 sample_pids: float = 1.0):
+        """Radius-graph condensation loss with the reference's arguments (oc.py:164-194)."""
+        super().__init__()
+        self.save_hyperparameters()
+
+    def forward(self, *, beta: Tensor, x: Tensor, particle_id: Tensor, reconstructable: Tensor, pt: Tensor,
+                ec_hit_mask: Tensor | None = None, eta: Tensor, **kwargs) -> MultiLossFctReturn:
+        hp = self.hparams
+        if ec_hit_mask is not None:
+            # the reference masks particle_id / reconstructable / pt but forgets eta (oc.py:207-213), which
+            # makes its mask computation fail on pruned graphs; eta is masked here as the tiger loss does
+            particle_id, reconstructable, pt, eta = (t[ec_hit_mask] for t in (particle_id, reconstructable, pt, eta))
+        mask = get_good_node_mask_tensors(pt=pt, particle_id=particle_id, reconstructable=reconstructable,
+                                          eta=eta, pt_thld=hp.pt_thld, max_eta=hp.max_eta)
+        if hp.sample_pids < 1:
+            raise NotImplementedError("sample_pids < 1 draws from the reference's fp16 torch RNG stream")
+        losses, extra = condensation_loss_rg(beta=beta, x=x, particle_id=particle_id, mask=mask, q_min=hp.q_min,
+                                             radius_threshold=1.0, max_num_neighbors=hp.max_num_neighbors)
+        weights = {"attractive": 1.0, "repulsive": hp.lw_repulsive, "noise": hp.lw_noise, "coward": hp.lw_coward}
+        return MultiLossFctReturn(loss_dct=losses, weight_dct=weights, extra_metrics=extra)

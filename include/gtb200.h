@@ -253,6 +253,26 @@ int gtb_oc_potentials(const float* beta, const float* x, int32_t d, const int64_
                       const int32_t* alphas, int32_t k, float q_min, int64_t noise_threshold,
                       double* out /* [8], zeroed by caller */, void* stream);
 
+/* ------------------------------------------------ radius-graph potentials (hinge, RG)
+ * Replaces torch_cluster.radius_graph(x, r, batch, loop=False, max_num_neighbors) + the sums over
+ * its edges (metrics/losses/metric_learning.py:93-112,47-52; metrics/losses/oc.py:46-69,115-117)
+ * without materialising the edge list.  An edge (neighbour j -> centre i) exists when
+ * ||x_i - x_j||^2 < r^2, i != j, batch[i] == batch[j] (batch may be NULL); a centre keeps its
+ * max_num_neighbors lowest-index neighbours.  Kept edges additionally need src_flag[j] != 0 and
+ * pid[j] != pid[i].
+ *   mode 0: term = relu(r - dist^p)                         (hinge repulsion; src_flag = hits of interest)
+ *   mode 1: term = (r - sqrt(eps + dist^2)) * q_j * q_i     (condensation repulsion; src_flag = is
+ *           condensation point; q = atanh(beta)^2 + q_min; beta required)
+ * out double[4] += {sum of terms, kept edges, sum of beta over pid == 0, hits with pid == 0}
+ * (the last two only when beta != NULL).  x: [n, d] fp32, d <= 16. */
+int gtb_radius_pair_sum_f32(const float* x, int32_t d, int64_t n, const int64_t* batch, const int64_t* pid,
+                            const uint8_t* src_flag, const float* beta, float q_min, float r, float p,
+                            float eps, int32_t max_num_neighbors, int32_t mode, double* out, void* stream);
+/* out double[2] += {sum over edges e with src_flag[edges[0][e]] of ||x_a - x_b||^p, their number}:
+ * attractive hinge term (metric_learning.py:28-30,111).  edges: int64 [2, n_edges]. */
+int gtb_edge_dist_pow_sum_f32(const float* x, int32_t d, const int64_t* edges, int64_t n_edges,
+                              const uint8_t* src_flag, float p, double* out, void* stream);
+
 /* inv_norm[r] = 1 / max(||cat_s src_s[r]||_2, eps): torch.nn.functional.normalize(x, p=2, dim=1,
  * eps) as used by ResFCNN.forward (mlp.py:115-116); feed the result as row_scale. */
 int gtb_rows_inv_l2norm_f32(const gtb_src_t* srcs, int32_t n_srcs, int64_t n_rows, float eps,
