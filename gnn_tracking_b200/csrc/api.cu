@@ -29,6 +29,7 @@ size_t tc_packed_bytes(int, const int32_t*, int, const int32_t*);
 int pack_tc(int, const int32_t*, int, const int32_t*, const float* const*, const float* const*, void*, cudaStream_t);
 int fused_mlp_tc(const gtb_mlp_desc_t&, cudaStream_t);
 int tc_timeout_flag(int*);
+int dbscan(const float*, int, int64_t, float, int, unsigned char*, int*, int*, cudaStream_t);
 int radius_pair_sum(const float*, int, int64_t, const int64_t*, const int64_t*, const unsigned char*, const float*, float, float,
                     float, float, int, int, double*, cudaStream_t);
 int edge_dist_pow_sum(const float*, int, const int64_t*, int64_t, const unsigned char*, float, double*, cudaStream_t);
@@ -265,6 +266,11 @@ int gtb_radius_pair_sum_f32(const float* x, int32_t d, int64_t n, const int64_t*
 int gtb_edge_dist_pow_sum_f32(const float* x, int32_t d, const int64_t* edges, int64_t n_edges, const uint8_t* src_flag,
                               float p, double* out, void* stream) {
   return edge_dist_pow_sum(x, d, edges, n_edges, src_flag, p, out, static_cast<cudaStream_t>(stream));
+}
+
+int gtb_dbscan_f32(const float* x, int32_t d, int64_t n, float eps, int32_t min_pts, uint8_t* core, int32_t* parent,
+                   int32_t* root, void* stream) {
+  return dbscan(x, d, n, eps, min_pts, core, parent, root, static_cast<cudaStream_t>(stream));
 }
 
 int gtb_rows_inv_l2norm_f32(const gtb_src_t* srcs, int32_t n_srcs, int64_t n_rows, float eps, float* inv_norm,

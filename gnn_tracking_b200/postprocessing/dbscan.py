@@ -1,0 +1,53 @@
+"""DBSCAN for the cluster hyper-parameter scan, on the GPU (reference
+postprocessing/fastrescanner.py:6-66; caller postprocessing/dbscanscanner.py:146-187).
+
+The reference copies the latent coordinates ``H`` to the host, lets sklearn build one radius-neighbour
+graph at ``max_eps`` and re-filters it per trial before calling sklearn's Cython ``dbscan_inner``.
+Here every trial is one ``gtb_dbscan_f32`` call on the device-resident ``H`` (three brute-force
+passes over shared-memory tiles: core flags, union-find of the core samples, labels); the labels
+are identical to sklearn's, including their numbering."""
+from __future__ import annotations
+
+import torch
+from torch import Tensor
+
+from .. import ops
+from .._lib import check, lib
+
+
+def dbscan(x: Tensor, eps: float = 1.0, min_samples: int = 1) -> Tensor:
+    """``sklearn.cluster.DBSCAN(eps, min_samples).fit_predict(x)`` as an int64 tensor on ``x``'s
+    device (-1 = noise)."""
+    dev = ops.require_cuda(x)
+    x = x.detach().to(torch.float32).contiguous()
+    n, d = x.shape
+    if n == 0:
+        return torch.empty(0, dtype=torch.int64, device=dev)
+    core = torch.empty(n, dtype=torch.uint8, device=dev)
+    parent = torch.empty(n, dtype=torch.int32, device=dev)
+    root = torch.empty(n, dtype=torch.int32, device=dev)
+    check(lib().gtb_dbscan_f32(x.data_ptr(), d, n, float(eps), int(min_samples), core.data_ptr(), parent.data_ptr(),
+                               root.data_ptr(), ops.stream_ptr(dev)))
+    ops._count(3)
+    # number the clusters in increasing order of their lowest core index (dbscan_inner's order)
+    is_root = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    clustered = root >= 0
+    is_root[root[clustered].long()] = 1
+    rank = torch.cumsum(is_root, 0) - 1
+    labels = torch.full((n,), -1, dtype=torch.int64, device=dev)
+    labels[clustered] = rank[root[clustered].long()]
+    return labels
+
+
+class DBSCANFastRescan:
+    """Interface of the reference class (fastrescanner.py:6-66): ``cluster(eps, min_pts)`` for many
+    trials over the same points.  ``x`` stays on the device; ``max_eps`` is accepted for
+    compatibility (no neighbour graph is cached: a trial is a few milliseconds)."""
+
+    def __init__(self, x: Tensor, max_eps: float = 1.0, *, n_jobs: int | None = None):
+        ops.require_cuda(x)
+        self.x = x.detach().to(torch.float32).contiguous()
+        self._max_eps = max_eps
+
+    def cluster(self, eps: float = 1.0, min_pts: int = 1) -> Tensor:
+        return dbscan(self.x, eps, min_pts)

@@ -273,6 +273,18 @@ int gtb_radius_pair_sum_f32(const float* x, int32_t d, int64_t n, const int64_t*
 int gtb_edge_dist_pow_sum_f32(const float* x, int32_t d, const int64_t* edges, int64_t n_edges,
                               const uint8_t* src_flag, float p, double* out, void* stream);
 
+/* ----------------------------------------------------------------------- DBSCAN
+ * One DBSCAN clustering of x [n, d] fp32 (d <= 16), replacing sklearn's radius_neighbors +
+ * dbscan_inner as driven by DBSCANFastRescan.cluster (postprocessing/fastrescanner.py:40-66) inside the
+ * hyper-parameter scan (postprocessing/dbscanscanner.py:146-187).  Neighbourhood dist <= eps
+ * (float64, self included), core = at least min_pts neighbours.
+ *   core   uint8 [n]: core-sample flags
+ *   parent int32 [n]: scratch (union-find forest of the core samples, rooted at the lowest index)
+ *   root   int32 [n]: lowest core index of the point's cluster; border points: the smallest adjacent
+ *                     root; noise: -1.  sklearn's label = rank of `root` among the distinct roots. */
+int gtb_dbscan_f32(const float* x, int32_t d, int64_t n, float eps, int32_t min_pts,
+                   uint8_t* core, int32_t* parent, int32_t* root, void* stream);
+
 /* inv_norm[r] = 1 / max(||cat_s src_s[r]||_2, eps): torch.nn.functional.normalize(x, p=2, dim=1,
  * eps) as used by ResFCNN.forward (mlp.py:115-116); feed the result as row_scale. */
 int gtb_rows_inv_l2norm_f32(const gtb_src_t* srcs, int32_t n_srcs, int64_t n_rows, float eps,

@@ -1,0 +1,70 @@
+"""GPU DBSCAN (gtb_dbscan_f32) against the reference's DBSCANFastRescan labels (committed goldens,
+tests/golden/make_golden_dbscan.py) and against sklearn run live: labels must be IDENTICAL, numbering
+included (integer work: bit-exact)."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = Path(__file__).parent / "golden" / "dbscan.pt"
+
+
+def test_dbscan_matches_reference_goldens():
+    from gnn_tracking_b200.postprocessing.dbscan import DBSCANFastRescan
+
+    g = torch.load(GOLDEN)
+    scanners = [DBSCANFastRescan(x.cuda(), max_eps=1.0) for x in g["datasets"]]
+    for case in g["cases"]:
+        got = scanners[case["dataset"]].cluster(eps=case["eps"], min_pts=case["min_pts"]).cpu()
+        assert torch.equal(got, case["labels"].long()), (case["dataset"], case["eps"], case["min_pts"])
+
+
+@pytest.mark.parametrize("n,d,eps,min_samples", [(1, 2, 0.5, 1), (1, 2, 0.5, 2), (257, 3, 0.3, 2), (6000, 2, 0.04, 3),
+                                                 (20000, 8, 0.9, 4), (3000, 16, 2.0, 2)])
+def test_dbscan_matches_sklearn(n, d, eps, min_samples):
+    from sklearn.cluster import DBSCAN
+
+    from gnn_tracking_b200.postprocessing.dbscan import dbscan
+
+    rng = np.random.default_rng(n + d)
+    centres = rng.uniform(-2, 2, size=(max(n // 12, 1), d))
+    x = (centres[rng.integers(0, len(centres), n)] + 0.1 * rng.standard_normal((n, d))).astype(np.float32)
+    want = DBSCAN(eps=eps, min_samples=min_samples).fit_predict(x)
+    got = dbscan(torch.from_numpy(x).cuda(), eps, min_samples).cpu().numpy()
+    assert np.array_equal(got, want)
+
+
+def test_dbscan_duplicates_and_empty():
+    from sklearn.cluster import DBSCAN
+
+    from gnn_tracking_b200.postprocessing.dbscan import dbscan
+
+    assert dbscan(torch.zeros((0, 3), device="cuda"), 0.1, 1).numel() == 0
+    x = torch.tensor([[0.0, 0.0]] * 5 + [[1.0, 1.0]] * 2 + [[5.0, 5.0]], device="cuda")
+    want = DBSCAN(eps=0.1, min_samples=2).fit_predict(x.cpu().numpy())
+    assert np.array_equal(dbscan(x, 0.1, 2).cpu().numpy(), want)
+    with pytest.raises(RuntimeError):
+        dbscan(torch.zeros((4, 17), device="cuda"), 0.1, 1)
+
+
+def test_dbscan_full_size_properties():
+    """100k points (BASELINE config 5 scale): properties that do not need the CPU run."""
+    from gnn_tracking_b200.postprocessing.dbscan import dbscan
+
+    g = torch.Generator(device="cuda").manual_seed(0)
+    n = 100_000
+    centres = torch.rand((n // 10, 8), device="cuda", generator=g) * 20
+    x = centres[torch.randint(0, n // 10, (n,), device="cuda", generator=g)] + 0.02 * torch.randn((n, 8), device="cuda", generator=g)
+    a = dbscan(x, 0.2, 1)
+    assert int(a.min()) == 0  # min_samples=1: no noise
+    # cluster ids are dense and ordered by first appearance
+    first = torch.full((int(a.max()) + 1,), n, dtype=torch.int64, device="cuda").scatter_reduce(0, a, torch.arange(n, device="cuda"), "amin")
+    assert bool((first[1:] > first[:-1]).all())
+    # permutation invariance of the partition (labels up to renumbering)
+    perm = torch.randperm(n, device="cuda", generator=g)
+    b = dbscan(x[perm], 0.2, 1)
+    pairs = torch.unique(torch.stack([a[perm], b]), dim=1)
+    assert pairs.size(1) == int(a.max()) + 1 == int(b.max()) + 1
