@@ -19,7 +19,8 @@ _PATCHES = {
     "gnn_tracking.models.track_condensation_networks": {
         "IN": ("models.interaction_network", "InteractionNetwork"),
         "ModularGraphTCN": ("models.track_condensation_networks", "ModularGraphTCN"),
-        "GraphTCN": ("models.track_condensation_networks", "GraphTCN")},
+        "GraphTCN": ("models.track_condensation_networks", "GraphTCN"),
+        "PreTrainedECGraphTCN": ("models.track_condensation_networks", "PreTrainedECGraphTCN")},
     "gnn_tracking.metrics.losses.ec": {"EdgeWeightBCELoss": ("metrics.losses.ec", "EdgeWeightBCELoss"),
                                        "EdgeWeightFocalLoss": ("metrics.losses.ec", "EdgeWeightFocalLoss"),
                                        "HaughtyFocalLoss": ("metrics.losses.ec", "HaughtyFocalLoss")},

@@ -193,3 +193,38 @@ def fused_mlp_autograd(runner, cache_bwd: _BwdPacks, linears: Sequence[torch.nn.
     if res is not None:
         tensors.append(res)
     return FusedMLPFunction.apply(cfg, *tensors)
+
+
+class GatherRows(torch.autograd.Function):
+    """``table[index]`` (``gtb_rows_gather_f32``); the gradient is the scatter-add of the row
+    gradients (``gtb_rows_scatter_add_f32``)."""
+
+    @staticmethod
+    def forward(ctx, table: Tensor, index: Tensor):
+        ctx.save_for_backward(index)
+        ctx.n = table.size(0)
+        return ops.rows_gather(table.contiguous(), index)
+
+    @staticmethod
+    def backward(ctx, g):
+        (index,) = ctx.saved_tensors
+        out = torch.zeros((ctx.n, g.size(1)), dtype=torch.float32, device=g.device)
+        ops.rows_scatter_add(g.contiguous(), index, out)
+        return out, None
+
+
+class L2NormalizeRows(torch.autograd.Function):
+    """``F.normalize(x, dim=1)`` of ``ResFCNN.forward`` (models/mlp.py:115-116) with the row norms
+    from ``gtb_rows_inv_l2norm_f32``; ``dx = (g - y <y, g>) / max(|x|, eps)``."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, eps: float):
+        inv = ops.rows_inv_l2norm([Block(x)], x.size(0), eps)
+        y = x * inv.unsqueeze(1)
+        ctx.save_for_backward(y, inv)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        y, inv = ctx.saved_tensors
+        return (g - y * (y * g).sum(1, keepdim=True)) * inv.unsqueeze(1), None

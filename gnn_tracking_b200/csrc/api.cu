@@ -29,6 +29,8 @@ size_t tc_packed_bytes(int, const int32_t*, int, const int32_t*);
 int pack_tc(int, const int32_t*, int, const int32_t*, const float* const*, const float* const*, void*, cudaStream_t);
 int fused_mlp_tc(const gtb_mlp_desc_t&, cudaStream_t);
 int tc_timeout_flag(int*);
+int oc_potentials_grad(const float*, const float*, int32_t, const int64_t*, const int32_t*, int64_t, const int32_t*, int32_t,
+                       float, int64_t, const float*, float*, float*, float*, cudaStream_t);
 int dbscan(const float*, int, int64_t, float, int, unsigned char*, int*, int*, cudaStream_t);
 int radius_pair_sum(const float*, int, int64_t, const int64_t*, const int64_t*, const unsigned char*, const float*, float, float,
                     float, float, int, int, double*, cudaStream_t);
@@ -266,6 +268,13 @@ int gtb_radius_pair_sum_f32(const float* x, int32_t d, int64_t n, const int64_t*
 int gtb_edge_dist_pow_sum_f32(const float* x, int32_t d, const int64_t* edges, int64_t n_edges, const uint8_t* src_flag,
                               float p, double* out, void* stream) {
   return edge_dist_pow_sum(x, d, edges, n_edges, src_flag, p, out, static_cast<cudaStream_t>(stream));
+}
+
+int gtb_oc_potentials_grad(const float* beta, const float* x, int32_t d, const int64_t* object_id, const int32_t* obj_slot,
+                           int64_t n_nodes, const int32_t* alphas, int32_t k, float q_min, int64_t noise_threshold,
+                           const float* coef, float* gq, float* gbeta, float* gx, void* stream) {
+  return oc_potentials_grad(beta, x, d, object_id, obj_slot, n_nodes, alphas, k, q_min, noise_threshold, coef, gq, gbeta, gx,
+                            static_cast<cudaStream_t>(stream));
 }
 
 int gtb_dbscan_f32(const float* x, int32_t d, int64_t n, float eps, int32_t min_pts, uint8_t* core, int32_t* parent,

@@ -192,4 +192,166 @@ int oc_potentials(const float* beta, const float* x, int32_t d, const int64_t* o
   return GTB_OK;
 }
 
+// ------------------------------------------------------------------ gradients of the four sums
+// What torch autograd derives for oc.py:282-336 (cdist, indexing by alphas_k, the masked sums):
+//   attractive pair (k == slot_j):      q_j q_k D^2      -> d/dx_j = 2 q_j q_k (x_j - x_k), d/dq_j = q_k D^2
+//   repulsive pair (k != slot_j, D<1):  q_j q_k (1 - D)  -> d/dx_j = -q_j q_k (x_j - x_k)/D (0 at D = 0, as
+//                                                           cdist's backward), d/dq_j = q_k (1 - D)
+// and the mirror terms for the condensation point.  Hit-side sums: one thread per hit over tiles of
+// condensation points; CP-side sums: one thread per condensation point over tiles of hits (the pair
+// is evaluated twice rather than reduced across threads with ~N*K atomics).
+// coef = {g_att / norm_att, g_rep / norm_rep, g_coward / K, g_noise / n_noise}.
+__global__ void __launch_bounds__(OC_TJ)
+oc_grad_hits_kernel(const float* __restrict__ beta, const float* __restrict__ x, int d,
+                    const int32_t* __restrict__ slot, int64_t n, const int32_t* __restrict__ alphas, int k, float q_min,
+                    const float* __restrict__ coef, float* __restrict__ gq, float* __restrict__ gx) {
+  __shared__ float xs[OC_TK * OC_MAXD];
+  __shared__ float qs[OC_TK];
+  const int64_t j = (int64_t)blockIdx.x * OC_TJ + threadIdx.x;
+  const bool valid = j < n;
+  const float c_att = coef[0], c_rep = coef[1];
+  float xj[OC_MAXD], gxj[OC_MAXD];
+#pragma unroll
+  for (int t = 0; t < OC_MAXD; ++t) {
+    xj[t] = (valid && t < d) ? x[j * d + t] : 0.f;
+    gxj[t] = 0.f;
+  }
+  const float qj = valid ? oc_charge(beta[j], q_min) : 0.f;
+  const int sj = valid ? slot[j] : -1;
+  float gqj = 0.f;
+  for (int kt = 0; kt < k; kt += OC_TK) {
+    const int kn = min(OC_TK, k - kt);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kn; i += OC_TJ) {
+      const int a = alphas[kt + i];
+      qs[i] = oc_charge(beta[a], q_min);
+      for (int t = 0; t < d; ++t) xs[i * d + t] = x[(int64_t)a * d + t];
+    }
+    __syncthreads();
+    if (!valid) continue;
+    for (int i = 0; i < kn; ++i) {
+      float df[OC_MAXD];
+      float d2 = 0.f;
+#pragma unroll
+      for (int t = 0; t < OC_MAXD; ++t) {
+        df[t] = t < d ? xj[t] - xs[i * d + t] : 0.f;
+        d2 = fmaf(df[t], df[t], d2);
+      }
+      const float dist = sqrtf(d2);
+      float wq, wx;  // d/dq_j = wq, d/dx_j = wx * (x_j - x_k)
+      if (kt + i == sj) {
+        wq = c_att * qs[i] * (dist * dist);
+        wx = 2.f * c_att * qj * qs[i];
+      } else if (dist < 1.f) {
+        wq = c_rep * qs[i] * (1.f - dist);
+        wx = dist > 0.f ? -c_rep * qj * qs[i] / dist : 0.f;
+      } else {
+        continue;
+      }
+      gqj += wq;
+#pragma unroll
+      for (int t = 0; t < OC_MAXD; ++t) gxj[t] = fmaf(wx, df[t], gxj[t]);
+    }
+  }
+  if (!valid) return;
+  gq[j] = gqj;
+  for (int t = 0; t < d; ++t) gx[j * d + t] = gxj[t];
+}
+
+constexpr int OC_JSPLIT = 8192;  // hits per blockIdx.y of the CP-side kernel
+
+__global__ void __launch_bounds__(OC_TK)
+oc_grad_cps_kernel(const float* __restrict__ beta, const float* __restrict__ x, int d,
+                   const int32_t* __restrict__ slot, int64_t n, const int32_t* __restrict__ alphas, int k, float q_min,
+                   const float* __restrict__ coef, float* __restrict__ gq, float* __restrict__ gx) {
+  __shared__ float xs[OC_TJ * OC_MAXD];
+  __shared__ float qs[OC_TJ];
+  __shared__ int ss[OC_TJ];
+  const int i = blockIdx.x * OC_TK + threadIdx.x;
+  const bool valid = i < k;
+  const float c_att = coef[0], c_rep = coef[1];
+  const int a = valid ? alphas[i] : 0;
+  float xk[OC_MAXD], gxk[OC_MAXD];
+#pragma unroll
+  for (int t = 0; t < OC_MAXD; ++t) {
+    xk[t] = (valid && t < d) ? x[(int64_t)a * d + t] : 0.f;
+    gxk[t] = 0.f;
+  }
+  const float qk = valid ? oc_charge(beta[a], q_min) : 0.f;
+  float gqk = 0.f;
+  const int64_t j_beg = (int64_t)blockIdx.y * OC_JSPLIT, j_end = min(n, j_beg + OC_JSPLIT);
+  for (int64_t jt = j_beg; jt < j_end; jt += OC_TJ) {
+    const int jn = (int)min((int64_t)OC_TJ, j_end - jt);
+    __syncthreads();
+    for (int u = threadIdx.x; u < jn; u += OC_TK) {
+      const int64_t j = jt + u;
+      qs[u] = oc_charge(beta[j], q_min);
+      ss[u] = slot[j];
+      for (int t = 0; t < d; ++t) xs[u * d + t] = x[j * d + t];
+    }
+    __syncthreads();
+    if (!valid) continue;
+    for (int u = 0; u < jn; ++u) {
+      float df[OC_MAXD];
+      float d2 = 0.f;
+#pragma unroll
+      for (int t = 0; t < OC_MAXD; ++t) {
+        df[t] = t < d ? xs[u * d + t] - xk[t] : 0.f;  // x_j - x_k
+        d2 = fmaf(df[t], df[t], d2);
+      }
+      const float dist = sqrtf(d2);
+      float wq, wx;  // d/dq_k = wq, d/dx_k = -wx * (x_j - x_k)
+      if (ss[u] == i) {
+        wq = c_att * qs[u] * (dist * dist);
+        wx = 2.f * c_att * qs[u] * qk;
+      } else if (dist < 1.f) {
+        wq = c_rep * qs[u] * (1.f - dist);
+        wx = dist > 0.f ? -c_rep * qs[u] * qk / dist : 0.f;
+      } else {
+        continue;
+      }
+      gqk += wq;
+#pragma unroll
+      for (int t = 0; t < OC_MAXD; ++t) gxk[t] = fmaf(-wx, df[t], gxk[t]);
+    }
+  }
+  if (!valid) return;
+  atomicAdd(gq + a, gqk);
+  for (int t = 0; t < d; ++t) atomicAdd(gx + (int64_t)a * d + t, gxk[t]);
+}
+
+// gbeta_j = gq_j dq/dbeta + [noise hit] c_noise - [condensation point] c_coward, q = atanh(beta)^2 + q_min
+__global__ void oc_grad_beta_kernel(const float* __restrict__ beta, const int64_t* __restrict__ object_id,
+                                    const int32_t* __restrict__ slot, int64_t n, const int32_t* __restrict__ alphas,
+                                    int64_t noise_thr, const float* __restrict__ coef, const float* __restrict__ gq,
+                                    float* __restrict__ gbeta) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+    const float b = beta[j];
+    float g = gq[j] * 2.f * atanhf(b) / (1.f - b * b);
+    if (!(object_id[j] > noise_thr)) g += coef[3];
+    const int s = slot[j];
+    if (s >= 0 && alphas[s] == (int32_t)j) g -= coef[2];
+    gbeta[j] = g;
+  }
+}
+
+int oc_potentials_grad(const float* beta, const float* x, int32_t d, const int64_t* object_id, const int32_t* slot,
+                       int64_t n, const int32_t* alphas, int32_t k, float q_min, int64_t noise_thr, const float* coef,
+                       float* gq, float* gbeta, float* gx, cudaStream_t st) {
+  GTB_REQUIRE(d >= 1 && d <= OC_MAXD, GTB_ERR_UNSUPPORTED_DIM, "gtb_oc_potentials_grad: latent dim %d outside [1,%d]", d,
+              OC_MAXD);
+  GTB_REQUIRE(k >= 1 && n >= 1 && coef && gq && gbeta && gx, GTB_ERR_BAD_ARG, "gtb_oc_potentials_grad: bad arguments");
+  oc_grad_hits_kernel<<<(unsigned)((n + OC_TJ - 1) / OC_TJ), OC_TJ, 0, st>>>(beta, x, d, slot, n, alphas, k, q_min, coef, gq,
+                                                                             gx);
+  GTB_CHECK_LAUNCH("oc_grad_hits_kernel");
+  dim3 grid((unsigned)((k + OC_TK - 1) / OC_TK), (unsigned)((n + OC_JSPLIT - 1) / OC_JSPLIT));
+  oc_grad_cps_kernel<<<grid, OC_TK, 0, st>>>(beta, x, d, slot, n, alphas, k, q_min, coef, gq, gx);
+  GTB_CHECK_LAUNCH("oc_grad_cps_kernel");
+  const int blocks = (int)imin64((n + 255) / 256, (int64_t)kNumSMs * 16);
+  oc_grad_beta_kernel<<<blocks, 256, 0, st>>>(beta, object_id, slot, n, alphas, noise_thr, coef, gq, gbeta);
+  GTB_CHECK_LAUNCH("oc_grad_beta_kernel");
+  return GTB_OK;
+}
+
 }  // namespace gtb

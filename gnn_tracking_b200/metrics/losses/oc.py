@@ -13,50 +13,78 @@ from ...utils.graph_masks import get_good_node_mask_tensors
 from . import MultiLossFct, MultiLossFctReturn
 
 
+class _TigerFn(torch.autograd.Function):
+    """The four tiger loss terms with their analytic gradients w.r.t. ``beta`` and ``x``
+    (``gtb_oc_potentials_grad``)."""
+
+    @staticmethod
+    def forward(ctx, beta, x, oid, mask, q_min, noise_threshold):
+        dev = beta.device
+        n, d = x.shape
+        st = ops.stream_ptr(dev)
+        uniq = torch.empty(n, dtype=torch.int64, device=dev)
+        slot = torch.empty(n, dtype=torch.int32, device=dev)
+        n_uniq = torch.zeros(1, dtype=torch.int32, device=dev)
+        ws_bytes = lib().gtb_oc_workspace_bytes(n)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        check(lib().gtb_oc_prepare(oid.data_ptr(), mask.data_ptr(), n, uniq.data_ptr(), slot.data_ptr(),
+                                   n_uniq.data_ptr(), ws.data_ptr(), ws_bytes, st))
+        k = int(n_uniq.item())  # the reference's torch.unique syncs at the same place
+        assert k > 0, "No hits left after masking"
+        scratch = torch.empty(k, dtype=torch.int64, device=dev)
+        alphas = torch.empty(k, dtype=torch.int32, device=dev)
+        check(lib().gtb_oc_alphas(beta.data_ptr(), slot.data_ptr(), n, float(q_min), k, scratch.data_ptr(),
+                                  alphas.data_ptr(), st))
+        out = torch.zeros(8, dtype=torch.float64, device=dev)
+        check(lib().gtb_oc_potentials(beta.data_ptr(), x.data_ptr(), d, oid.data_ptr(), mask.data_ptr(),
+                                      slot.data_ptr(), n, alphas.data_ptr(), k, float(q_min), int(noise_threshold),
+                                      out.data_ptr(), st))
+        ops._count(9)
+        eps = 1e-9
+        v_att, v_rep, coward, noise, n_noise, n_oi, n_rep, _ = out.unbind(0)
+        norms = torch.stack([eps + n_oi - k, (eps + (k - 1) * n) * torch.ones_like(n_oi), k * torch.ones_like(n_oi), n_noise])
+        ctx.save_for_backward(beta, x, oid, slot, alphas, norms)
+        ctx.cfg = (float(q_min), int(noise_threshold), k)
+        # noise: NaN without noise hits, as in the reference (oc.py:335-336)
+        return ((v_att / norms[0]).float(), (v_rep / norms[1]).float(), (coward / k).float(), (noise / n_noise).float(),
+                n_rep.to(torch.int64), alphas, uniq[:k])
+
+    @staticmethod
+    def backward(ctx, g_att, g_rep, g_cow, g_noise, *unused):
+        beta, x, oid, slot, alphas, norms = ctx.saved_tensors
+        q_min, noise_threshold, k = ctx.cfg
+        n, d = x.shape
+        dev = x.device
+        g = torch.stack([t.to(torch.float64).reshape(()) for t in (g_att, g_rep, g_cow, g_noise)])
+        coef = (g / norms).to(torch.float32).contiguous()
+        gq = torch.empty(n, dtype=torch.float32, device=dev)
+        gbeta = torch.empty(n, dtype=torch.float32, device=dev)
+        gx = torch.empty((n, d), dtype=torch.float32, device=dev)
+        check(lib().gtb_oc_potentials_grad(beta.data_ptr(), x.data_ptr(), d, oid.data_ptr(), slot.data_ptr(), n,
+                                           alphas.data_ptr(), k, q_min, noise_threshold, coef.data_ptr(), gq.data_ptr(),
+                                           gbeta.data_ptr(), gx.data_ptr(), ops.stream_ptr(dev)))
+        ops._count(3)
+        return gbeta, gx, None, None, None, None
+
+
 def condensation_loss_tiger(*, beta: Tensor, x: Tensor, object_id: Tensor, object_mask: Tensor, q_min: float,
                             noise_threshold: int = 0, max_n_rep: int = 0):
     """Same contract as the reference function (oc.py:251-347): returns
-    ``({"attractive", "repulsive", "coward", "noise"}, {"n_rep"})``."""
+    ``({"attractive", "repulsive", "coward", "noise"}, {"n_rep"})``.  Differentiable w.r.t. ``beta``
+    and ``x``."""
     if max_n_rep:
         raise NotImplementedError("max_n_rep sub-sampling uses the reference's fp16 torch RNG stream and is "
                                   "not reproduced; the tiled kernel needs no sub-sampling to fit in memory")
-    if torch.is_grad_enabled() and (beta.requires_grad or x.requires_grad):
-        raise NotImplementedError("the condensation loss is forward-only in this build: call it under torch.no_grad() "
-                                  "(there is no silent autograd fallback)")
-    dev = ops.require_cuda(beta, x, object_id, object_mask)
-    n, d = x.shape
-    st = ops.stream_ptr(dev)
+    ops.require_cuda(beta, x, object_id, object_mask)
+    shape = beta.shape
     beta = beta.reshape(-1).to(torch.float32).contiguous()
     x = x.to(torch.float32).contiguous()
     oid = object_id.to(torch.int64).contiguous()
     mask = object_mask.to(torch.bool).contiguous().view(torch.uint8)
-    uniq = torch.empty(n, dtype=torch.int64, device=dev)
-    slot = torch.empty(n, dtype=torch.int32, device=dev)
-    n_uniq = torch.zeros(1, dtype=torch.int32, device=dev)
-    ws_bytes = lib().gtb_oc_workspace_bytes(n)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    check(lib().gtb_oc_prepare(oid.data_ptr(), mask.data_ptr(), n, uniq.data_ptr(), slot.data_ptr(),
-                               n_uniq.data_ptr(), ws.data_ptr(), ws_bytes, st))
-    k = int(n_uniq.item())  # the reference's torch.unique syncs at the same place
-    assert k > 0, "No hits left after masking"
-    scratch = torch.empty(k, dtype=torch.int64, device=dev)
-    alphas = torch.empty(k, dtype=torch.int32, device=dev)
-    check(lib().gtb_oc_alphas(beta.data_ptr(), slot.data_ptr(), n, float(q_min), k, scratch.data_ptr(),
-                              alphas.data_ptr(), st))
-    out = torch.zeros(8, dtype=torch.float64, device=dev)
-    check(lib().gtb_oc_potentials(beta.data_ptr(), x.data_ptr(), d, oid.data_ptr(), mask.data_ptr(),
-                                  slot.data_ptr(), n, alphas.data_ptr(), k, float(q_min), int(noise_threshold),
-                                  out.data_ptr(), st))
-    ops._count(9)
-    eps = 1e-9
-    v_att, v_rep, coward, noise, n_noise, n_oi, n_rep, _ = out.unbind(0)
-    losses = {
-        "attractive": (v_att / (eps + n_oi - k)).float(),
-        "repulsive": (v_rep / (eps + (k - 1) * n)).float(),
-        "coward": (coward / k).float(),
-        "noise": (noise / n_noise).float(),  # NaN without noise hits, as in the reference (oc.py:335-336)
-    }
-    return losses, {"n_rep": n_rep.to(torch.int64), "alphas": alphas, "unique_ids": uniq[:k]}
+    del shape
+    att, rep, cow, noise, n_rep, alphas, uniq = _TigerFn.apply(beta, x, oid, mask, q_min, noise_threshold)
+    losses = {"attractive": att, "repulsive": rep, "coward": cow, "noise": noise}
+    return losses, {"n_rep": n_rep, "alphas": alphas, "unique_ids": uniq}
 
 
 def condensation_loss_rg(*, beta: Tensor, x: Tensor, particle_id: Tensor, mask: Tensor, q_min: float,
@@ -67,6 +95,9 @@ def condensation_loss_rg(*, beta: Tensor, x: Tensor, particle_id: Tensor, mask: 
     the radius-graph edges that start at a condensation point (``gtb_radius_pair_sum_f32`` mode 1:
     ``sqrt(1e-9 + d^2)``, neighbour cap), the noise term over ``particle_id == 0`` exactly."""
     from .metric_learning import radius_pair_sum
+    if torch.is_grad_enabled() and (beta.requires_grad or x.requires_grad):
+        raise NotImplementedError("the radius-graph condensation loss is forward-only in this build: call it under "
+                                  "torch.no_grad() (there is no silent autograd fallback)")
     tiger, extra = condensation_loss_tiger(beta=beta, x=x, object_id=particle_id, object_mask=mask, q_min=q_min)
     n = x.size(0)
     k = extra["alphas"].numel()

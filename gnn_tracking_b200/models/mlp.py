@@ -232,8 +232,7 @@ class ResFCNN(nn.Module):
     def forward_blocks(self, blocks: Sequence[Block], n_rows: int, *, final_act: int = ACT_NONE) -> Tensor:
         if torch.is_grad_enabled() and (any(b.tensor.requires_grad for b in blocks)
                                         or any(p.requires_grad for p in self.parameters())):
-            raise NotImplementedError("ResFCNN (the GraphTCN node encoder) is forward-only in this build: "
-                                      "call it under torch.no_grad()")
+            return self._forward_grad(blocks, n_rows, final_act)
         inv = ops.rows_inv_l2norm(blocks, n_rows, 1e-12)
         if len(self._layers) == 0:
             p = self._cache.get([self._encoder, self._decoder], [b.tensor.size(1) for b in blocks])[0][0]
@@ -244,6 +243,26 @@ class ResFCNN(nn.Module):
             x = ops.fused_mlp([Block(x, relu=True)], n_rows, cache.get([lay])[0][0], res=x, res_a=a, res_b=b)
         return ops.fused_mlp([Block(x, relu=True)], n_rows, self._cache.get([self._decoder])[0][0],
                              final_act=final_act)
+
+    def _forward_grad(self, blocks: Sequence[Block], n_rows: int, final_act: int) -> Tensor:
+        """Differentiable variant: the normalised input is materialised once (its gradient needs it),
+        every Linear then runs through ``run_linears`` and its recompute-based backward."""
+        from ..autograd import GatherRows, L2NormalizeRows
+        cols = []
+        for b in blocks:
+            t = b.tensor if b.tensor.dim() > 1 else b.tensor.unsqueeze(1)
+            if b.extend is not None or b.projected:
+                raise NotImplementedError("ResFCNN backward over halo / pre-projected blocks is not implemented")
+            t = t if b.index is None else GatherRows.apply(t, b.index)
+            cols.append(torch.relu(t) if b.relu else t)
+        x = L2NormalizeRows.apply(cols[0] if len(cols) == 1 else torch.cat(cols, 1), 1e-12)
+        if len(self._layers) == 0:
+            return run_linears(self._cache, [self._encoder, self._decoder], [Block(x)], n_rows, final_act=final_act)
+        x = run_linears(self._layer_caches[0], [self._encoder], [Block(x)], n_rows)
+        a, b = math.sqrt(self._alpha), math.sqrt(1 - self._alpha)
+        for lay, cache in zip(self._layers, self._layer_caches[1:]):
+            x = run_linears(cache, [lay], [Block(x, relu=True)], n_rows, res=x, res_a=a, res_b=b)
+        return run_linears(self._cache, [self._decoder], [Block(x, relu=True)], n_rows, final_act=final_act)
 
     def forward(self, x: Tensor, **ignore) -> Tensor:
         return self.forward_blocks([Block(x)], x.size(0))

@@ -124,8 +124,11 @@ class ModularGraphTCN(nn.Module, HyperparametersMixin):
             epi = dict(res=nn.functional.pad(xr[:, :nec], (0, hp.h_outdim - nec)).contiguous(),
                        res_a=math.sqrt(alpha_residue), res_b=math.sqrt(1 - alpha_residue))
         # H = (sqrt(a) residual + sqrt(1-a) p_cluster(h)) * _latent_normalization  (:290-298)
-        lat = self._latent_normalization.detach()
-        hh = self.p_cluster.forward_blocks([Block(h)], n, out_scale=lat, **epi)
+        if torch.is_grad_enabled() and (h.requires_grad or self._latent_normalization.requires_grad):
+            # the scale is a trainable scalar: its gradient comes from one elementwise product
+            hh = self.p_cluster.forward_blocks([Block(h)], n, **epi) * self._latent_normalization
+        else:
+            hh = self.p_cluster.forward_blocks([Block(h)], n, out_scale=self._latent_normalization.detach(), **epi)
         return {"W": w_unmasked, "H": hh, "B": beta.squeeze(), "ec_hit_mask": hit_mask, "ec_edge_mask": edge_mask}
 
 
@@ -138,6 +141,24 @@ class GraphTCN(nn.Module, HyperparametersMixin):
         self.save_hyperparameters()
         ec = ECForGraphTCN(node_indim=node_indim, edge_indim=edge_indim, hidden_dim=hidden_dim,
                            interaction_node_dim=h_dim, interaction_edge_dim=e_dim, L_ec=L_ec, alpha=alpha_ec)
+        hc_in = ResIN(node_dim=h_dim, edge_dim=e_dim, object_hidden_dim=hidden_dim,
+                      relational_hidden_dim=hidden_dim, alpha=alpha_hc, n_layers=L_hc)
+        self._gtcn = ModularGraphTCN(ec=ec, hc_in=hc_in, node_indim=node_indim, edge_indim=edge_indim,
+                                     h_dim=h_dim, e_dim=e_dim, h_outdim=h_outdim, hidden_dim=hidden_dim, **kwargs)
+
+    def forward(self, data) -> dict[str, Tensor | None]:
+        return self._gtcn.forward(data=data)
+
+
+class PreTrainedECGraphTCN(nn.Module, HyperparametersMixin):
+    def __init__(self, ec, *, node_indim: int, edge_indim: int, h_dim=5, e_dim=4, h_outdim=2, hidden_dim=40,
+                 L_hc=3, alpha_hc: float = 0.5, **kwargs):
+        """``ModularGraphTCN`` around a given (pre-trained) edge classifier ``ec`` — a module or a
+        ``{"class_path", "init_args"}`` dict — with a ``ResIN`` track condenser (reference :459-518,
+        the model of tests/test_configs/tc.yml); parameters under ``_gtcn.*``."""
+        super().__init__()
+        self.save_hyperparameters(ignore=["ec"])
+        ec = _obj_from_or_to_hparams(self, "ec", ec)
         hc_in = ResIN(node_dim=h_dim, edge_dim=e_dim, object_hidden_dim=hidden_dim,
                       relational_hidden_dim=hidden_dim, alpha=alpha_hc, n_layers=L_hc)
         self._gtcn = ModularGraphTCN(ec=ec, hc_in=hc_in, node_indim=node_indim, edge_indim=edge_indim,

@@ -253,6 +253,16 @@ int gtb_oc_potentials(const float* beta, const float* x, int32_t d, const int64_
                       const int32_t* alphas, int32_t k, float q_min, int64_t noise_threshold,
                       double* out /* [8], zeroed by caller */, void* stream);
 
+/* Gradients of the four sums above w.r.t. beta [n] and x [n, d] (what torch autograd derives for
+ * oc.py:282-336: cdist with a zero sub-gradient at distance 0, indexing by alphas, masked sums).
+ *   coef  float[4] on the device: upstream gradient of each loss term divided by its normaliser,
+ *         {attractive, repulsive, coward, noise}
+ *   gq    float[n] scratch (d loss / d q_j);  gbeta float[n], gx float[n, d]: outputs (overwritten) */
+int gtb_oc_potentials_grad(const float* beta, const float* x, int32_t d, const int64_t* object_id,
+                           const int32_t* obj_slot, int64_t n_nodes, const int32_t* alphas, int32_t k,
+                           float q_min, int64_t noise_threshold, const float* coef, float* gq,
+                           float* gbeta, float* gx, void* stream);
+
 /* ------------------------------------------------ radius-graph potentials (hinge, RG)
  * Replaces torch_cluster.radius_graph(x, r, batch, loop=False, max_num_neighbors) + the sums over
  * its edges (metrics/losses/metric_learning.py:93-112,47-52; metrics/losses/oc.py:46-69,115-117)

@@ -134,3 +134,140 @@ def test_edge_classifier_trains():
         w = m.forward_tensors(xc, eic, eac)["W"]
     acc = float(((w > 0.5) == yc).float().mean())
     assert acc > 0.55, acc
+
+
+# ------------------------------------------------------------------ GraphTCN: head, loss, training
+def _truth(n, gen, n_particles=40):
+    pid = torch.randint(0, n_particles, (n,), generator=gen)          # 0 = noise
+    pt_of = torch.rand(n_particles, generator=gen) * 2 + 0.1
+    eta_of = (torch.rand(n_particles, generator=gen) - 0.5) * 9
+    reco_of = torch.rand(n_particles, generator=gen) < 0.9
+    return pid, pt_of[pid], eta_of[pid], reco_of[pid]
+
+
+@pytest.mark.parametrize("d", [2, 8])
+def test_tiger_loss_gradients(d):
+    from gnn_tracking_b200.metrics.losses.oc import CondensationLossTiger
+    from oracle import losses_oracle as LO
+    gen = torch.Generator().manual_seed(21 + d)
+    n = 3000
+    pid, pt, eta, reco = _truth(n, gen, 120)
+    beta = torch.rand(n, generator=gen) * 0.9 + 0.05
+    x = torch.randn(n, d, generator=gen) * (0.6 if d == 2 else 0.3)
+    lw = {"attractive": 1.0, "repulsive": 0.7, "coward": 0.3, "noise": 0.2}
+    br, xr = beta.double().requires_grad_(), x.double().requires_grad_()
+    ref, extra = LO.condensation_tiger_loss(beta=br, x=xr, particle_id=pid, reconstructable=reco, pt=pt.double(),
+                                            eta=eta.double())
+    assert int(extra["n_rep"]) > 1000
+    sum(lw[k] * v for k, v in ref.items()).backward()
+    bc, xc = beta.cuda().requires_grad_(), x.cuda().requires_grad_()
+    out = CondensationLossTiger(lw_repulsive=0.7, lw_coward=0.3, lw_noise=0.2)(
+        beta=bc, x=xc, particle_id=pid.cuda(), reconstructable=reco.cuda(), pt=pt.cuda(), eta=eta.cuda())
+    for k, v in ref.items():
+        assert abs(float(out.loss_dct[k].detach()) - float(v)) <= 1e-5 * abs(float(v)) + 1e-7, k
+    out.loss.backward()
+    _check("beta", bc.grad, br.grad)
+    _check("x", xc.grad, xr.grad)
+
+
+@pytest.mark.parametrize("depth,alpha", [(1, 0.0), (3, 0.6)])
+def test_res_fcnn_backward(depth, alpha, impl):
+    from gnn_tracking_b200.models.mlp import ResFCNN
+    from oracle import in_oracle as O
+    gen = torch.Generator().manual_seed(31)
+    x = torch.randn(900, 14, generator=gen)
+    g = torch.randn(900, 5, generator=gen)
+    torch.manual_seed(6)
+    m = ResFCNN(in_dim=14, hidden_dim=40, out_dim=5, depth=depth, alpha=alpha, bias=depth > 1)
+    sd = {k: v.detach().double().requires_grad_() for k, v in m.state_dict().items()}
+    xr = x.double().requires_grad_()
+    (O.res_fcnn(xr, sd, "", alpha) * g.double()).sum().backward()
+    m = m.cuda()
+    xc = x.cuda().requires_grad_()
+    (m(xc) * g.cuda()).sum().backward()
+    _check("x", xc.grad, xr.grad)
+    for k, p in m.named_parameters():
+        _check(k, p.grad, sd[k].grad)
+
+
+class _Data:
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+def _tcn_case(seed, n=500, e=6000):
+    ei, x, ea, gen = _graph(n, e, 14, 4, seed=seed)
+    pid, pt, eta, reco = _truth(n, gen, 30)
+    return ei, x, ea, pid, pt, eta, reco
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(mask_orphan_nodes=True, use_ec_embeddings_for_hc=True, feed_edge_weights=True,
+                                             alpha_latent=0.3, n_embedding_coords=2)])
+def test_graph_tcn_training_step_gradients(kw, impl):
+    """One TC training step of the reference (training/tc.py: forward, tiger loss, backward) against
+    autograd through the float64 oracle.  The EC threshold is put into the widest gap of the oracle's
+    edge weights between their 15 % and 85 % quantiles so that both precisions keep the same edges."""
+    from gnn_tracking_b200.metrics.losses.oc import CondensationLossTiger
+    from gnn_tracking_b200.models.track_condensation_networks import GraphTCN
+    from oracle import in_oracle as O
+    from oracle import losses_oracle as LO
+    ei, x, ea, pid, pt, eta, reco = _tcn_case(12)
+    torch.manual_seed(7)
+    probe = GraphTCN(14, 4, hidden_dim=32, L_ec=2, L_hc=2, **kw)
+    sd0 = {k: v.detach().double() for k, v in probe.state_dict().items()}
+    w = O.ec_forward(x.double(), ei, ea.double(), sd0, "_gtcn.ec.")["W"].reshape(-1).sort().values
+    mid = w[int(0.15 * len(w)): int(0.85 * len(w))]
+    gap = int((mid[1:] - mid[:-1]).argmax())
+    thr = float((mid[gap] + mid[gap + 1]) / 2)
+    assert float(mid[gap + 1] - mid[gap]) > 1e-5
+
+    torch.manual_seed(7)
+    m = GraphTCN(14, 4, hidden_dim=32, L_ec=2, L_hc=2, ec_threshold=thr, **kw)
+    sd = {k: v.detach().double().requires_grad_() for k, v in m.state_dict().items()}
+    ref = O.graph_tcn_forward(x.double(), ei, ea.double(), sd, ec_threshold=thr, **kw)
+    rl, _ = LO.condensation_tiger_loss(beta=ref["B"], x=ref["H"], particle_id=pid, reconstructable=reco, pt=pt.double(),
+                                       eta=eta.double(), ec_hit_mask=ref["ec_hit_mask"])
+    (rl["attractive"] + 0.5 * rl["repulsive"] + 0.1 * rl["coward"]).backward()
+
+    m = m.cuda()
+    data = _Data(x=x.cuda(), edge_index=ei.cuda(), edge_attr=ea.cuda())
+    out = m(data)
+    assert torch.equal(out["ec_edge_mask"].cpu(), ref["ec_edge_mask"])
+    loss = CondensationLossTiger(lw_repulsive=0.5, lw_coward=0.1)(
+        beta=out["B"], x=out["H"], particle_id=pid.cuda(), reconstructable=reco.cuda(), pt=pt.cuda(), eta=eta.cuda(),
+        ec_hit_mask=out["ec_hit_mask"])
+    loss.loss.backward()
+    n_checked = 0
+    for k, p in m.named_parameters():
+        if sd[k].grad is None:       # not on the path of this configuration (e.g. the EC's output head)
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, k
+            continue
+        _check(k, p.grad, sd[k].grad, rtol=1e-3)  # cancellation-amplified, see the EC test above
+        n_checked += 1
+    assert n_checked >= 20
+
+
+def test_graph_tcn_trains():
+    """A few optimiser steps of the reference's TC recipe (tests/test_configs/tc.yml: PreTrainedECGraphTCN,
+    CondensationLossTiger, Adam) on the CUDA path: the loss goes down."""
+    from gnn_tracking_b200.metrics.losses.oc import CondensationLossTiger
+    from gnn_tracking_b200.models.edge_classifier import ECForGraphTCN
+    from gnn_tracking_b200.models.track_condensation_networks import PreTrainedECGraphTCN
+    ei, x, ea, pid, pt, eta, reco = _tcn_case(13, n=800, e=9000)
+    torch.manual_seed(8)
+    ec = ECForGraphTCN(node_indim=14, edge_indim=4, L_ec=2, hidden_dim=16)
+    m = PreTrainedECGraphTCN(ec, node_indim=14, edge_indim=4, hidden_dim=16, L_hc=2, ec_threshold=0.3).cuda()
+    opt = torch.optim.Adam(m.parameters(), lr=3e-3)
+    loss_fn = CondensationLossTiger(lw_repulsive=1.0)
+    data = _Data(x=x.cuda(), edge_index=ei.cuda(), edge_attr=ea.cuda())
+    truth = dict(particle_id=pid.cuda(), reconstructable=reco.cuda(), pt=pt.cuda(), eta=eta.cuda())
+    losses = []
+    for _ in range(40):
+        opt.zero_grad()
+        out = m(data)
+        loss = loss_fn(beta=out["B"], x=out["H"], ec_hit_mask=out["ec_hit_mask"], **truth).loss
+        loss.backward()
+        opt.step()
+        losses.append(float(loss.detach()))
+    assert all(l == l for l in losses), losses
+    assert losses[-1] < 0.9 * losses[0], losses
