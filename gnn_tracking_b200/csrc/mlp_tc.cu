@@ -448,15 +448,16 @@ __device__ __forceinline__ void tc_issue_mmas(uint32_t wbase, uint32_t bar_base,
 // ptxas keeps in uniform registers (no R2UR in front of every UTCHMMA).
 // `halves`: a 64-wide output is issued as two N = 32 chains with one commit each, output columns
 // 0..31 first: the epilogue of the first half then runs under the MMAs of the second.
+// `ktile`: first 32-wide K tile of the weights this 64-wide block multiplies (koff / 32).
 template <int TEAM, int L>
 __device__ __forceinline__ void tc_issue_mmas_k64(uint32_t wbase, uint32_t bar_base, const TcParams& p, bool first,
-                                                  bool halves) {
+                                                  bool halves, uint32_t ktile = 0) {
   constexpr uint32_t tmc = TEAM * TM_CTX;
   const uint32_t n = halves ? 32u : (uint32_t)p.npad[L];
   const uint32_t idesc = make_idesc_tf32(TC_TM, (int)n);
   const uint32_t tile16 = (uint32_t)p.npad[L] * 8u;
-  const uint64_t bd_hi = make_smem_desc_sw128(wbase + p.w_off[L][0]);
-  const uint64_t bd_lo = make_smem_desc_sw128(wbase + p.w_off[L][1]);
+  const uint64_t bd_hi = make_smem_desc_sw128(wbase + p.w_off[L][0]) + (uint64_t)(ktile * tile16);
+  const uint64_t bd_lo = make_smem_desc_sw128(wbase + p.w_off[L][1]) + (uint64_t)(ktile * tile16);
   if (elect_one()) {  // ptxas knows a single lane runs this branch: operands go to uniform registers once
 #pragma unroll 1
     for (uint32_t hf = 0; hf < (halves ? 2u : 1u); ++hf) {
@@ -482,11 +483,16 @@ __device__ __forceinline__ void tc_issue_mmas_k64(uint32_t wbase, uint32_t bar_b
 __device__ __forceinline__ void split_store8(uint32_t taddr_hi, uint32_t taddr_lo, const float (&v)[8]) {
   uint32_t hi[8], lo[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float h, l;
-    split_tf32_act(v[j], h, l);
-    hi[j] = __float_as_uint(h);
-    lo[j] = __float_as_uint(l);
+  for (int j = 0; j < 4; ++j) {
+    f32x2 h, l;
+    split_tf32_act2(pack2(v[2 * j], v[2 * j + 1]), h, l);
+    float a, b;
+    unpack2(h, a, b);
+    hi[2 * j] = __float_as_uint(a);
+    hi[2 * j + 1] = __float_as_uint(b);
+    unpack2(l, a, b);
+    lo[2 * j] = __float_as_uint(a);
+    lo[2 * j + 1] = __float_as_uint(b);
   }
   tmem_st8(taddr_hi, hi);
   tmem_st8(taddr_lo, lo);
@@ -495,14 +501,31 @@ __device__ __forceinline__ void split_store8(uint32_t taddr_hi, uint32_t taddr_l
 __device__ __forceinline__ void split_store16(uint32_t taddr_hi, uint32_t taddr_lo, const float (&v)[16]) {
   uint32_t hi[16], lo[16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    float h, l;
-    split_tf32_act(v[j], h, l);
-    hi[j] = __float_as_uint(h);
-    lo[j] = __float_as_uint(l);
+  for (int j = 0; j < 8; ++j) {
+    f32x2 h, l;
+    split_tf32_act2(pack2(v[2 * j], v[2 * j + 1]), h, l);
+    float a, b;
+    unpack2(h, a, b);
+    hi[2 * j] = __float_as_uint(a);
+    hi[2 * j + 1] = __float_as_uint(b);
+    unpack2(l, a, b);
+    lo[2 * j] = __float_as_uint(a);
+    lo[2 * j + 1] = __float_as_uint(b);
   }
   tmem_st16(taddr_hi, hi);
   tmem_st16(taddr_lo, lo);
+}
+
+// v[j] += x[j] on 16 values as 8 packed adds
+__device__ __forceinline__ void add16(float (&v)[16], const float4& x0, const float4& x1, const float4& x2, const float4& x3) {
+  const float4 xs[4] = {x0, x1, x2, x3};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const f32x2 a = add2(pack2(v[4 * q], v[4 * q + 1]), pack2(xs[q].x, xs[q].y));
+    const f32x2 b = add2(pack2(v[4 * q + 2], v[4 * q + 3]), pack2(xs[q].z, xs[q].w));
+    unpack2(a, v[4 * q], v[4 * q + 1]);
+    unpack2(b, v[4 * q + 2], v[4 * q + 3]);
+  }
 }
 
 #define TC_PROF(id)                                   \
@@ -548,21 +571,33 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
 #pragma unroll
   for (int q = 0; q < 4; ++q) crow[q] = q < p.n_iregs ? tc_copy_slot_row(p.ireg_c4n[q], wteam, lane) : -1;
   if (p.out_mode == 1) orow_slot = tc_copy_slot_row(p.out_c4n, wteam, lane);
-  int32_t ccur[4] = {0, 0, 0, 0}, cnext[4] = {0, 0, 0, 0};
-  int32_t rcur[3] = {0, 0, 0}, rnext[3] = {0, 0, 0};
-  {
-    const int tile0 = team_tile(p, team, 0);
-    if (tile0 < p.n_tiles) {
-      const uint32_t row0 = (uint32_t)tile0 * TC_TM;
-      const int rows_here = (int)min((int64_t)TC_TM, p.n_rows - (int64_t)row0);
+  // Three generations of index registers: the tile being computed (cur), the tile whose copies are
+  // being issued (next) and the tile after it (far), loaded at the top of a tile and first read a whole
+  // tile later: ptxas parks the scoreboard wait of a load at the next branch, so a load read within
+  // the same tile costs its full latency there (it did: ~10 % of the kernel, profiles/).
+  int32_t ccur[4], cnext[4], cfar[4], rcur[3], rnext[3], rfar[3], ocur = 0, onext = 0;
+  auto load_idx = [&](int tile_i, int32_t (&cdst)[4], int32_t (&rdst)[3], int32_t& odst) {
+    const bool have = tile_i < p.n_tiles;
+    const uint32_t row0i = have ? (uint32_t)tile_i * TC_TM : 0u;
+    const int rows_i = have ? (int)min((int64_t)TC_TM, p.n_rows - (int64_t)row0i) : 0;
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (crow[q] >= 0 && crow[q] < rows_here) ccur[q] = __ldg(p.ireg_ptr[q] + row0 + crow[q]);
-#pragma unroll
-      for (int q = 0; q < 3; ++q)
-        if (rarr[q] && r < rows_here) rcur[q] = __ldg(rarr[q] + row0 + r);
+    for (int q = 0; q < 4; ++q) {
+      int32_t v = 0;
+      if (crow[q] >= 0 && crow[q] < rows_i) v = __ldg(p.ireg_ptr[q] + row0i + crow[q]);
+      cdst[q] = v;
     }
-  }
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      int32_t v = 0;
+      if (rarr[q] && r < rows_i) v = __ldg(rarr[q] + row0i + r);
+      rdst[q] = v;
+    }
+    int32_t o = 0;
+    if (orow_slot >= 0 && orow_slot < rows_i) o = __ldg(p.out_index + row0i + orow_slot);
+    odst = o;
+  };
+  load_idx(team_tile(p, team, 0), ccur, rcur, ocur);
+  load_idx(team_tile(p, team, 1), cnext, rnext, onext);
   // ring bookkeeping without divisions: next item to issue (tile sequence, kind position, slot)
   int iss_t = 0, iss_k = 0, issued = 0, consumed = 0;
   uint32_t iss_slot = 0, cons_slot = 0;
@@ -628,22 +663,11 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
     const int rows_here = (int)min((int64_t)TC_TM, p.n_rows - (int64_t)row0);
     const bool live = r < rows_here;
     if (tt < TC_TM) sts_i32(segs + tt * 4, (live && p.seg_id) ? rcur[0] : -1);
-    // indices of the NEXT tile (consumed from the end of this tile on) and of this tile's output rows
-    int32_t ocur = 0;
-    {
-      const int tile_n = team_tile(p, team, t + 1);
-      if (tile_n < p.n_tiles) {
-        const uint32_t row0n = (uint32_t)tile_n * TC_TM;
-        const int rows_n = (int)min((int64_t)TC_TM, p.n_rows - (int64_t)row0n);
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if (crow[q] >= 0 && crow[q] < rows_n) cnext[q] = __ldg(p.ireg_ptr[q] + row0n + crow[q]);
-#pragma unroll
-        for (int q = 0; q < 3; ++q)
-          if (rarr[q] && r < rows_n) rnext[q] = __ldg(rarr[q] + row0n + r);
-      }
-      if (orow_slot >= 0 && orow_slot < rows_here) ocur = __ldg(p.out_index + row0 + orow_slot);
-    }
+    // Indices of the tile after the next one: issued right in front of the first accumulator wait
+    // of the tile (ptxas drains the scoreboard of a load at the next branch it meets, whatever the
+    // distance to the first use; there the drain runs under the MMAs), first read a tile from now.
+    int32_t ofar = 0;
+    auto load_far = [&]() { load_idx(team_tile(p, team, t + 2), cfar, rfar, ofar); };
     const float rscale = (p.row_scale && live) ? __ldg(p.row_scale + row0 + r) : 1.f;
 
     // ---------------- first Linear: one streamed block at a time through the TMEM A buffer
@@ -707,9 +731,9 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
       TC_PROF(2);
       if (wteam == 0) {  // whole warp, uniform operands (see tc_issue_mmas)
         tc_fence_after_sync();
-        if (W64 && ch.staged && c == 0) {
-          if (team == 0) tc_issue_mmas_k64<0, 0>(wbase, bar_base, p, true, halves0);
-          else           tc_issue_mmas_k64<1, 0>(wbase, bar_base, p, true, halves0);
+        if (W64 && ch.staged && (ch.koff & 31) == 0) {  // a 64-wide block starting on a K tile of the weights
+          if (team == 0) tc_issue_mmas_k64<0, 0>(wbase, bar_base, p, c == 0, halves0, (uint32_t)(ch.koff >> 5));
+          else           tc_issue_mmas_k64<1, 0>(wbase, bar_base, p, c == 0, halves0, (uint32_t)(ch.koff >> 5));
         } else {
           if (team == 0) tc_issue_mmas<0>(wbase, bar_base, p, 0, ch.koff, groups, c == 0);
           else           tc_issue_mmas<1>(wbase, bar_base, p, 0, ch.koff, groups, c == 0);
@@ -768,6 +792,7 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
         team_sync(team);
       }
       TC_PROF(7);
+      if (l == 0) load_far();
       wait_or_trap(mma_bar, mma_phase);  // every thread, also one without a column block
       mma_phase ^= 1;
       tc_fence_after_sync();
@@ -780,26 +805,27 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
         tmem_ld_wait();
         float v[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]) + bias[16 * b + j];
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
+        {
+          const float4* b4 = reinterpret_cast<const float4*>(bias + 16 * b);
+          add16(v, b4[0], b4[1], b4[2], b4[3]);
+        }
         if (l == 0) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 x = pre[bi * 4 + q];
-            v[4 * q + 0] += x.x; v[4 * q + 1] += x.y; v[4 * q + 2] += x.z; v[4 * q + 3] += x.w;
-          }
+          add16(v, pre[bi * 4 + 0], pre[bi * 4 + 1], pre[bi * 4 + 2], pre[bi * 4 + 3]);
 #pragma unroll
           for (int a = 0; a < 2; ++a) {
             if (add_sl[a] == 0u && add_row[a] == nullptr) continue;
+            float4 x[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const int c4 = 4 * b + q;
-              float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+              x[q] = make_float4(0.f, 0.f, 0.f, 0.f);
               if (W64 || c4 * 4 < p.ntrue[0]) {
-                if (add_sl[a]) x = lds128(add_sl[a] + (((uint32_t)c4 << 4) ^ rx));
-                else x = __ldg(reinterpret_cast<const float4*>(add_row[a]) + c4);
+                if (add_sl[a]) x[q] = lds128(add_sl[a] + (((uint32_t)c4 << 4) ^ rx));
+                else x[q] = __ldg(reinterpret_cast<const float4*>(add_row[a]) + c4);
               }
-              v[4 * q + 0] += x.x; v[4 * q + 1] += x.y; v[4 * q + 2] += x.z; v[4 * q + 3] += x.w;
             }
+            add16(v, x[0], x[1], x[2], x[3]);
           }
         }
 #pragma unroll
@@ -872,6 +898,7 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
       const int b0 = h * per, b1 = min(nb, b0 + per);
       // the last accumulator arrives in two halves when it was issued that way (see halves0 / hv_next)
       const bool hv = W64 && p.npad[last] == 64 && (last > 0 || halves0);
+      if (last == 0) load_far();
       wait_or_trap(mma_bar, mma_phase);
       mma_phase ^= 1;
       tc_fence_after_sync();
@@ -886,12 +913,19 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
         uint32_t acc[16];
         tmem_ld16(tm_lane + TM_D + 16 * b, acc);
         tmem_ld_wait();
+        float vv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) vv[j] = __uint_as_float(acc[j]);
+        {
+          const float4* b4 = reinterpret_cast<const float4*>(bias + 16 * b);
+          add16(vv, b4[0], b4[1], b4[2], b4[3]);
+        }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           float v[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            float x = __uint_as_float(acc[4 * q + j]) + bias[16 * b + 4 * q + j];
+            float x = vv[4 * q + j];
             if (p.final_act == GTB_ACT_RELU) x = fmaxf(x, 0.f);
             else if (p.final_act == GTB_ACT_SIGMOID_AFFINE) x = p.act_eps + (1.f - 2.f * p.act_eps) * (1.f / (1.f + expf(-x)));
             v[j] = x;
@@ -919,6 +953,7 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
         const uint32_t sp0 = osl + slot_off(rb, c);
         const uint32_t old4 = (uint32_t)p.out_ld * 4u, rld4 = (uint32_t)p.res_ld * 4u;
         const float* res0 = p.res ? row_ptr(p.res + (c << 2), row0 + rb, rld4) : nullptr;
+        const f32x2 resa2 = pack2(p.res_a, p.res_a), resb2 = pack2(p.res_b, p.res_b), osc2 = pack2(oscale, oscale);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int rr = rb + 16 * j;
@@ -926,14 +961,19 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
           if (p.out_mode == 1) orow = (uint32_t)__shfl_sync(0xffffffffu, ocur, 2 * j + (lane >> 4));
           if (rr < rows_here) {
             float4 v = lds128(sp0 + j * 4096);
-            if (touch) {
-              v.x *= p.res_b; v.y *= p.res_b; v.z *= p.res_b; v.w *= p.res_b;
+            if (touch) {  // (res_a res + res_b v) oscale, same operation order as the scalar paths
+              f32x2 lo2 = mul2(pack2(v.x, v.y), resb2), hi2 = mul2(pack2(v.z, v.w), resb2);
               if (p.res) {
                 const float4 q = __ldg(reinterpret_cast<const float4*>(row_ptr(res0, 16 * j, rld4)));
-                v.x = fmaf(p.res_a, q.x, v.x); v.y = fmaf(p.res_a, q.y, v.y);
-                v.z = fmaf(p.res_a, q.z, v.z); v.w = fmaf(p.res_a, q.w, v.w);
+                lo2 = fma2(resa2, pack2(q.x, q.y), lo2);
+                hi2 = fma2(resa2, pack2(q.z, q.w), hi2);
               }
-              v.x *= oscale; v.y *= oscale; v.z *= oscale; v.w *= oscale;
+              if (p.out_scale) {
+                lo2 = mul2(lo2, osc2);
+                hi2 = mul2(hi2, osc2);
+              }
+              unpack2(lo2, v.x, v.y);
+              unpack2(hi2, v.z, v.w);
               if (want_aggr) sts128(sp0 + j * 4096, v);
             }
             if (p.out) *reinterpret_cast<float4*>(const_cast<float*>(row_ptr(p.out + (c << 2), orow, old4))) = v;
@@ -1024,18 +1064,26 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
         for (int i = 0; i < 8; ++i)  // (rg0 + i) & 7 == i: rg0 is a multiple of 8
           v[i] = lds128(osl + (uint32_t)(rg0 + i) * 256u + (((uint32_t)c4 << 4) ^ ((uint32_t)i << 4)));
         int cur = sg[0];
-        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+        f32x2 s01 = pack2(0.f, 0.f), s23 = s01;
+        auto flush = [&](int seg) {
+          float4 sum;
+          unpack2(s01, sum.x, sum.y);
+          unpack2(s23, sum.z, sum.w);
+          red_add_v4(row_ptr(p.aggr + 4 * c4, (uint32_t)seg, al4), sum);
+        };
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           if (sg[i] < 0) break;  // rows past the end of the last tile
           if (sg[i] != cur) {
-            red_add_v4(row_ptr(p.aggr + 4 * c4, (uint32_t)cur, al4), sum);
+            flush(cur);
             cur = sg[i];
-            sum = make_float4(0.f, 0.f, 0.f, 0.f);
+            s01 = pack2(0.f, 0.f);
+            s23 = s01;
           }
-          sum.x += v[i].x; sum.y += v[i].y; sum.z += v[i].z; sum.w += v[i].w;
+          s01 = add2(s01, pack2(v[i].x, v[i].y));
+          s23 = add2(s23, pack2(v[i].z, v[i].w));
         }
-        red_add_v4(row_ptr(p.aggr + 4 * c4, (uint32_t)cur, al4), sum);
+        flush(cur);
       }
     } else if (want_aggr) {
       if (touch) team_sync(team);
@@ -1074,9 +1122,17 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
     consume_done();
     issue_next(t);  // the output slot is free again
 #pragma unroll
-    for (int q = 0; q < 4; ++q) ccur[q] = cnext[q];
+    for (int q = 0; q < 4; ++q) {
+      ccur[q] = cnext[q];
+      cnext[q] = cfar[q];
+    }
 #pragma unroll
-    for (int q = 0; q < 3; ++q) rcur[q] = rnext[q];
+    for (int q = 0; q < 3; ++q) {
+      rcur[q] = rnext[q];
+      rnext[q] = rfar[q];
+    }
+    ocur = onext;
+    onext = ofar;
     TC_PROF(17);
     if (PROF && prof_on) g_tc_prof[31] += 1;
   }

@@ -198,5 +198,49 @@ __device__ __forceinline__ void split_tf32_act(float v, float& hi, float& lo) {
   lo = (v - hi) * 1.000345266f;
 }
 
+// ---- packed fp32 pairs (FADD2 / FMUL2 on sm_100: one issue slot for two lanes of work; the tiles are
+// issue-bound, not FP32-pipe-bound).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// split_tf32_act on a pair in five packed instructions (2.5 per element instead of 4): the
+// round-to-nearest hi comes from Veltkamp's splitting with 2^13 + 1 -- g = fl(v (2^13 + 1)),
+// hi = fl(g - fl(g - v)) keeps the leading 24 - 13 = 11 significant bits of v, i.e. exactly a tf32 --
+// and lo = (v - hi)(1 + 2^-11.5) as above.  |v| < 2^114 (activations) cannot overflow g.
+// g is written as ONE fma (2^13 v + v, the same singly rounded value): ptxas contracts a packed
+// mul followed by a sub into FFMA2 even with explicit .rn, which would skip the rounding of g the
+// splitting lives on (hi would come out as v); an fma result is never contracted again.
+__device__ __forceinline__ void split_tf32_act2(f32x2 v, f32x2& hi, f32x2& lo) {
+  const f32x2 g = fma2(v, pack2(8192.f, 8192.f), v);
+  hi = sub2(g, sub2(g, v));
+  lo = mul2(sub2(v, hi), pack2(1.000345266f, 1.000345266f));
+}
+
 }  // namespace tc
 }  // namespace gtb

@@ -33,6 +33,8 @@ CASES = [
     ("W head 4x64 + 2 projected -> 64 -> 64 -> 1 sigmoid", 20000, [64, 64, 64, 64], 900, [64, 64, 1], {"sigmoid": True, "scatter": True}),
     ("residual + relu on load", 3000, [64, 64], 0, [64, 64, 64], {"res": True, "relu_in": True}),
     ("big: 1M rows, projected, aggr", 1000000, [64], 100000, [64, 64, 64], {"aggr": True, "scatter": True}),
+    ("big W head: 1M rows, 4x64 -> 64 -> 64 -> 1 sigmoid", 1000000, [64, 64, 64, 64], 0, [64, 64, 1], {"sigmoid": True}),
+    ("big encoder: 1M rows, 4 -> 64 -> 64 relu", 1000000, [4], 0, [64, 64], {"final_relu": True}),
 ]
 
 
