@@ -35,6 +35,10 @@ int dbscan(const float*, int, int64_t, float, int, unsigned char*, int*, int*, c
 int radius_pair_sum(const float*, int, int64_t, const int64_t*, const int64_t*, const unsigned char*, const float*, float, float,
                     float, float, int, int, double*, cudaStream_t);
 int edge_dist_pow_sum(const float*, int, const int64_t*, int64_t, const unsigned char*, float, double*, cudaStream_t);
+int radius_pair_sum_grad(const float*, int, int64_t, const int64_t*, const int64_t*, const unsigned char*, const float*, float,
+                         float, float, float, int, int, const float*, float*, float*, cudaStream_t);
+int edge_dist_pow_grad(const float*, int, const int64_t*, int64_t, const unsigned char*, float, const float*, float*,
+                       cudaStream_t);
 int ec_loss_grad(const float*, const void*, int, int64_t, const int64_t*, const float*, float, int, float, float, float,
                  const float*, float*, cudaStream_t);
 int rows_atb(const float*, int, const int32_t*, int, int, const float*, int, int, int64_t, float*, int, float*, cudaStream_t);
@@ -263,6 +267,19 @@ int gtb_radius_pair_sum_f32(const float* x, int32_t d, int64_t n, const int64_t*
                             int32_t max_num_neighbors, int32_t mode, double* out, void* stream) {
   return radius_pair_sum(x, d, n, batch, pid, src_flag, beta, q_min, r, p, eps, max_num_neighbors, mode, out,
                          static_cast<cudaStream_t>(stream));
+}
+
+int gtb_radius_pair_sum_grad_f32(const float* x, int32_t d, int64_t n, const int64_t* batch, const int64_t* pid,
+                                 const uint8_t* src_flag, const float* beta, float q_min, float r, float p, float eps,
+                                 int32_t max_num_neighbors, int32_t mode, const float* coef, float* gx, float* gq,
+                                 void* stream) {
+  return radius_pair_sum_grad(x, d, n, batch, pid, src_flag, beta, q_min, r, p, eps, max_num_neighbors, mode, coef, gx, gq,
+                              static_cast<cudaStream_t>(stream));
+}
+
+int gtb_edge_dist_pow_grad_f32(const float* x, int32_t d, const int64_t* edges, int64_t n_edges, const uint8_t* src_flag,
+                               float p, const float* coef, float* gx, void* stream) {
+  return edge_dist_pow_grad(x, d, edges, n_edges, src_flag, p, coef, gx, static_cast<cudaStream_t>(stream));
 }
 
 int gtb_edge_dist_pow_sum_f32(const float* x, int32_t d, const int64_t* edges, int64_t n_edges, const uint8_t* src_flag,

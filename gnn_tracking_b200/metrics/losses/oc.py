@@ -95,9 +95,6 @@ def condensation_loss_rg(*, beta: Tensor, x: Tensor, particle_id: Tensor, mask: 
     the radius-graph edges that start at a condensation point (``gtb_radius_pair_sum_f32`` mode 1:
     ``sqrt(1e-9 + d^2)``, neighbour cap), the noise term over ``particle_id == 0`` exactly."""
     from .metric_learning import radius_pair_sum
-    if torch.is_grad_enabled() and (beta.requires_grad or x.requires_grad):
-        raise NotImplementedError("the radius-graph condensation loss is forward-only in this build: call it under "
-                                  "torch.no_grad() (there is no silent autograd fallback)")
     tiger, extra = condensation_loss_tiger(beta=beta, x=x, object_id=particle_id, object_mask=mask, q_min=q_min)
     n = x.size(0)
     k = extra["alphas"].numel()

@@ -283,6 +283,18 @@ int gtb_radius_pair_sum_f32(const float* x, int32_t d, int64_t n, const int64_t*
 int gtb_edge_dist_pow_sum_f32(const float* x, int32_t d, const int64_t* edges, int64_t n_edges,
                               const uint8_t* src_flag, float p, double* out, void* stream);
 
+/* Gradients of the two sums above (what torch autograd derives for the reference's
+ * norm / pow / relu chain over the radius-graph and true edges, metric_learning.py:14-54, oc.py:46-69;
+ * d dist / d x = 0 at dist = 0).  coef: device float, the upstream gradient of the sum (already divided
+ * by the loss normaliser).  gx [n, d] and gq [n] (mode 1: d / d charge, q = atanh(beta)^2 + q_min)
+ * must be zero-filled (pair_sum) / are added onto (dist_pow); both kernels use atomics. */
+int gtb_radius_pair_sum_grad_f32(const float* x, int32_t d, int64_t n, const int64_t* batch, const int64_t* pid,
+                                 const uint8_t* src_flag, const float* beta, float q_min, float r, float p,
+                                 float eps, int32_t max_num_neighbors, int32_t mode, const float* coef,
+                                 float* gx, float* gq, void* stream);
+int gtb_edge_dist_pow_grad_f32(const float* x, int32_t d, const int64_t* edges, int64_t n_edges,
+                               const uint8_t* src_flag, float p, const float* coef, float* gx, void* stream);
+
 /* ----------------------------------------------------------------------- DBSCAN
  * One DBSCAN clustering of x [n, d] fp32 (d <= 16), replacing sklearn's radius_neighbors +
  * dbscan_inner as driven by DBSCANFastRescan.cluster (postprocessing/fastrescanner.py:40-66) inside the

@@ -111,3 +111,50 @@ def test_radius_losses_vs_oracle_seeded(cap):
                                       max_num_neighbors=cap)
     for k in ref:
         _close(got[k], ref[k], f"rg.{k}")
+
+
+@pytest.mark.parametrize("cap,p_attr,p_rep", [(256, 1.0, 1.0), (5, 2.0, 2.0)])
+def test_radius_loss_gradients(cap, p_attr, p_rep):
+    """Gradients of the hinge loss w.r.t. x and of the radius-graph condensation loss w.r.t. x and
+    beta (gtb_radius_pair_sum_grad_f32, gtb_edge_dist_pow_grad_f32, gtb_oc_potentials_grad) against
+    float64 autograd through the oracle; 2e-5 of the largest entry per tensor."""
+    from gnn_tracking_b200.metrics.losses.metric_learning import GraphConstructionHingeEmbeddingLoss as Hinge
+    from gnn_tracking_b200.metrics.losses.oc import condensation_loss_rg
+    from oracle import losses_oracle as L
+    gen = torch.Generator().manual_seed(23)
+    n = 2000
+    x = torch.randn(n, 3, generator=gen) * 1.2
+    pid = torch.randint(0, 200, (n,), generator=gen)
+    pt = (torch.rand(200, generator=gen) * 2)[pid]
+    eta = ((torch.rand(200, generator=gen) - 0.5) * 9)[pid]
+    reco = (torch.rand(200, generator=gen) < 0.9).long()[pid]
+    batch = (torch.arange(n) >= n // 2).long()
+    tei = torch.randint(0, n, (2, 3000), generator=gen)
+    beta = torch.rand(n, generator=gen).clamp(1e-2, 1 - 1e-2)
+
+    def check(name, got, ref):
+        got, ref = got.detach().cpu().double(), ref.detach().double()
+        scale = float(ref.abs().max())
+        err = float((got - ref).abs().max())
+        assert scale > 0 and err <= 2e-5 * scale + 1e-9, f"{name}: max|d|={err:.3e} scale={scale:.3e}"
+
+    xr = x.double().requires_grad_()
+    ref, _ = L.hinge_loss(x=xr, particle_id=pid, batch=batch, true_edge_index=tei, pt=pt, eta=eta, reconstructable=reco,
+                          max_num_neighbors=cap, r_emb=0.8, p_attr=p_attr, p_rep=p_rep)
+    (ref["attractive"] + 0.7 * ref["repulsive"]).backward()
+    xc = x.cuda().requires_grad_()
+    out = Hinge(max_num_neighbors=cap, r_emb=0.8, p_attr=p_attr, p_rep=p_rep, lw_repulsive=0.7)(
+        x=xc, particle_id=pid.cuda(), batch=batch.cuda(), true_edge_index=tei.cuda(), pt=pt.cuda(), eta=eta.cuda(),
+        reconstructable=reco.cuda())
+    out.loss.backward()
+    check("hinge x", xc.grad, xr.grad)
+
+    mask = L.good_node_mask(pt=pt, particle_id=pid, reconstructable=reco, eta=eta)
+    xr, br = x.double().requires_grad_(), beta.double().requires_grad_()
+    ref = L.condensation_rg(beta=br, x=xr, particle_id=pid, mask=mask, max_num_neighbors=cap)
+    (ref["attractive"] + 0.5 * ref["repulsive"] + 0.2 * ref["coward"] + 0.3 * ref["noise"]).backward()
+    xc, bc = x.cuda().requires_grad_(), beta.cuda().requires_grad_()
+    got, _ = condensation_loss_rg(beta=bc, x=xc, particle_id=pid.cuda(), mask=mask.cuda(), q_min=0.01, max_num_neighbors=cap)
+    (got["attractive"] + 0.5 * got["repulsive"] + 0.2 * got["coward"] + 0.3 * got["noise"]).backward()
+    check("rg x", xc.grad, xr.grad)
+    check("rg beta", bc.grad, br.grad)
