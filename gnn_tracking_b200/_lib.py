@@ -79,6 +79,8 @@ SIGNATURES = {
     "gtb_oc_alphas": (C.c_int, [_vp, _vp, _i64, _f32, _i32, _vp, _vp, _vp]),
     "gtb_oc_potentials": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _i64, _vp, _i32, _f32, _i64, _vp, _vp]),
     "gtb_radius_pair_sum_f32": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _i32, _i32, _vp, _vp]),
+    "gtb_radius_graph_count_f32": (C.c_int, [_vp, _i32, _i64, _vp, _f32, _i32, _i32, _vp, _vp]),
+    "gtb_radius_graph_fill_f32": (C.c_int, [_vp, _i32, _i64, _vp, _f32, _i32, _i32, _vp, _vp, _i64, _vp]),
     "gtb_radius_pair_sum_grad_f32": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "gtb_edge_dist_pow_grad_f32": (C.c_int, [_vp, _i32, _vp, _i64, _vp, _f32, _vp, _vp, _vp]),
     "gtb_edge_dist_pow_sum_f32": (C.c_int, [_vp, _i32, _vp, _i64, _vp, _f32, _vp, _vp]),

@@ -35,6 +35,9 @@ int dbscan(const float*, int, int64_t, float, int, unsigned char*, int*, int*, c
 int radius_pair_sum(const float*, int, int64_t, const int64_t*, const int64_t*, const unsigned char*, const float*, float, float,
                     float, float, int, int, double*, cudaStream_t);
 int edge_dist_pow_sum(const float*, int, const int64_t*, int64_t, const unsigned char*, float, double*, cudaStream_t);
+int radius_graph_count(const float*, int, int64_t, const int64_t*, float, int, int, int32_t*, cudaStream_t);
+int radius_graph_fill(const float*, int, int64_t, const int64_t*, float, int, int, const int64_t*, int64_t*, int64_t,
+                      cudaStream_t);
 int radius_pair_sum_grad(const float*, int, int64_t, const int64_t*, const int64_t*, const unsigned char*, const float*, float,
                          float, float, float, int, int, const float*, float*, float*, cudaStream_t);
 int edge_dist_pow_grad(const float*, int, const int64_t*, int64_t, const unsigned char*, float, const float*, float*,
@@ -267,6 +270,17 @@ int gtb_radius_pair_sum_f32(const float* x, int32_t d, int64_t n, const int64_t*
                             int32_t max_num_neighbors, int32_t mode, double* out, void* stream) {
   return radius_pair_sum(x, d, n, batch, pid, src_flag, beta, q_min, r, p, eps, max_num_neighbors, mode, out,
                          static_cast<cudaStream_t>(stream));
+}
+
+int gtb_radius_graph_count_f32(const float* x, int32_t d, int64_t n, const int64_t* batch, float r, int32_t max_num_neighbors,
+                               int32_t loop, int32_t* counts, void* stream) {
+  return radius_graph_count(x, d, n, batch, r, max_num_neighbors, loop, counts, static_cast<cudaStream_t>(stream));
+}
+
+int gtb_radius_graph_fill_f32(const float* x, int32_t d, int64_t n, const int64_t* batch, float r, int32_t max_num_neighbors,
+                              int32_t loop, const int64_t* offsets, int64_t* edge_index, int64_t n_edges, void* stream) {
+  return radius_graph_fill(x, d, n, batch, r, max_num_neighbors, loop, offsets, edge_index, n_edges,
+                           static_cast<cudaStream_t>(stream));
 }
 
 int gtb_radius_pair_sum_grad_f32(const float* x, int32_t d, int64_t n, const int64_t* batch, const int64_t* pid,

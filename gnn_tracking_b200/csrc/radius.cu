@@ -258,4 +258,83 @@ int edge_dist_pow_sum(const float* x, int d, const int64_t* edges, int64_t n_edg
   return GTB_OK;
 }
 
+// ---------------------------------------------------------------- materialised radius graph
+// torch_cluster.radius_graph as an edge list for callers outside the fused losses: pass 1 counts the
+// kept neighbours of every centre, the host prefix-sums the counts, pass 2 writes the edges grouped
+// by centre, neighbours ascending: row 0 = neighbour (source), row 1 = centre (target).
+template <bool FILL>
+__global__ void __launch_bounds__(RAD_T) radius_graph_kernel(const float* __restrict__ x, int d, int64_t n,
+                                                             const int64_t* __restrict__ batch, float r, int max_nb,
+                                                             int loop, int32_t* __restrict__ counts,
+                                                             const int64_t* __restrict__ offsets,
+                                                             int64_t* __restrict__ edge_index, int64_t n_edges) {
+  __shared__ float tx[RAD_MAXD][RAD_T];
+  __shared__ long long tb[RAD_T];
+  const int tid = threadIdx.x;
+  const float r2 = r * r;
+  const int64_t n_round = (n + RAD_T - 1) / RAD_T * RAD_T;
+  for (int64_t i0 = (int64_t)blockIdx.x * RAD_T; i0 < n_round; i0 += (int64_t)gridDim.x * RAD_T) {
+    const int64_t i = i0 + tid;
+    const bool have = i < n;
+    float xi[RAD_MAXD];
+#pragma unroll
+    for (int c = 0; c < RAD_MAXD; ++c) xi[c] = (have && c < d) ? __ldg(x + (size_t)i * d + c) : 0.f;
+    const long long batch_i = (have && batch) ? batch[i] : 0;
+    const int64_t off = (FILL && have) ? offsets[i] : 0;
+    int kept = 0;
+    for (int64_t j0 = 0; j0 < n; j0 += RAD_T) {
+      __syncthreads();
+      {
+        const int64_t j = j0 + tid;
+        const bool hj = j < n;
+        for (int c = 0; c < d; ++c) tx[c][tid] = hj ? __ldg(x + (size_t)j * d + c) : 0.f;
+        tb[tid] = (hj && batch) ? batch[j] : 0;
+      }
+      __syncthreads();
+      if (!have || kept >= max_nb) continue;
+      const int lim = (int)min((int64_t)RAD_T, n - j0);
+      for (int jj = 0; jj < lim && kept < max_nb; ++jj) {
+        float d2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < RAD_MAXD; ++c) {
+          if (c < d) {
+            const float t = xi[c] - tx[c][jj];
+            d2 = fmaf(t, t, d2);
+          }
+        }
+        if (d2 < r2 && (loop || j0 + jj != i) && tb[jj] == batch_i) {
+          if (FILL) {
+            edge_index[off + kept] = j0 + jj;
+            edge_index[n_edges + off + kept] = i;
+          }
+          ++kept;
+        }
+      }
+    }
+    if (!FILL && have) counts[i] = kept;
+  }
+}
+
+int radius_graph_count(const float* x, int d, int64_t n, const int64_t* batch, float r, int max_nb, int loop,
+                       int32_t* counts, cudaStream_t st) {
+  GTB_REQUIRE(x && counts && d >= 1 && d <= RAD_MAXD && max_nb >= 1, GTB_ERR_BAD_ARG,
+              "gtb_radius_graph_count_f32: bad arguments (dimension must be in [1, %d])", RAD_MAXD);
+  if (n == 0) return GTB_OK;
+  const int blocks = (int)imin64((n + RAD_T - 1) / RAD_T, (int64_t)kNumSMs * 4);
+  radius_graph_kernel<false><<<blocks, RAD_T, 0, st>>>(x, d, n, batch, r, max_nb, loop, counts, nullptr, nullptr, 0);
+  GTB_CHECK_LAUNCH("radius_graph_kernel<count>");
+  return GTB_OK;
+}
+
+int radius_graph_fill(const float* x, int d, int64_t n, const int64_t* batch, float r, int max_nb, int loop,
+                      const int64_t* offsets, int64_t* edge_index, int64_t n_edges, cudaStream_t st) {
+  GTB_REQUIRE(x && offsets && (edge_index || n_edges == 0) && d >= 1 && d <= RAD_MAXD && max_nb >= 1, GTB_ERR_BAD_ARG,
+              "gtb_radius_graph_fill_f32: bad arguments (dimension must be in [1, %d])", RAD_MAXD);
+  if (n == 0 || n_edges == 0) return GTB_OK;
+  const int blocks = (int)imin64((n + RAD_T - 1) / RAD_T, (int64_t)kNumSMs * 4);
+  radius_graph_kernel<true><<<blocks, RAD_T, 0, st>>>(x, d, n, batch, r, max_nb, loop, nullptr, offsets, edge_index, n_edges);
+  GTB_CHECK_LAUNCH("radius_graph_kernel<fill>");
+  return GTB_OK;
+}
+
 }  // namespace gtb

@@ -283,6 +283,18 @@ int gtb_radius_pair_sum_f32(const float* x, int32_t d, int64_t n, const int64_t*
 int gtb_edge_dist_pow_sum_f32(const float* x, int32_t d, const int64_t* edges, int64_t n_edges,
                               const uint8_t* src_flag, float p, double* out, void* stream);
 
+/* torch_cluster.radius_graph(x, r, batch, loop, max_num_neighbors) as an edge list (the un-vendored
+ * native op behind metrics/losses/oc.py:115-117, metric_learning.py:97-103, 232): strict dist < r, same
+ * batch entry, at most max_num_neighbors neighbours per centre (the lowest indices).  Two passes:
+ *   count: counts int32 [n] = kept neighbours per centre;
+ *   fill : offsets int64 [n] = exclusive prefix sum of counts, edge_index int64 [2, n_edges] with
+ *          row 0 = neighbour, row 1 = centre, grouped by centre, neighbours ascending. */
+int gtb_radius_graph_count_f32(const float* x, int32_t d, int64_t n, const int64_t* batch, float r,
+                               int32_t max_num_neighbors, int32_t loop, int32_t* counts, void* stream);
+int gtb_radius_graph_fill_f32(const float* x, int32_t d, int64_t n, const int64_t* batch, float r,
+                              int32_t max_num_neighbors, int32_t loop, const int64_t* offsets,
+                              int64_t* edge_index, int64_t n_edges, void* stream);
+
 /* Gradients of the two sums above (what torch autograd derives for the reference's
  * norm / pow / relu chain over the radius-graph and true edges, metric_learning.py:14-54, oc.py:46-69;
  * d dist / d x = 0 at dist = 0).  coef: device float, the upstream gradient of the sum (already divided

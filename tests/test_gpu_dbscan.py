@@ -68,3 +68,19 @@ def test_dbscan_full_size_properties():
     b = dbscan(x[perm], 0.2, 1)
     pairs = torch.unique(torch.stack([a[perm], b]), dim=1)
     assert pairs.size(1) == int(a.max()) + 1 == int(b.max()) + 1
+
+
+def test_fastrescan_equal_slowrescan():
+    """The reference's own pin (tests/test_fastrescanner.py:7-14) with the GPU class in place of the
+    sklearn-backed one."""
+    from sklearn.cluster import DBSCAN
+
+    from gnn_tracking_b200.postprocessing.dbscan import DBSCANFastRescan
+
+    x = np.random.default_rng(0).uniform(size=(100, 2)).astype(np.float32)
+    fr = DBSCANFastRescan(torch.from_numpy(x).cuda(), max_eps=0.15)
+    for eps in [0.1, 0.05]:
+        for min_pts in [1, 2]:
+            labels = fr.cluster(eps=eps, min_pts=min_pts).cpu().numpy()
+            labels2 = DBSCAN(eps=eps, min_samples=min_pts).fit_predict(x)
+            assert (labels == labels2).all()

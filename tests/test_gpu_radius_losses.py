@@ -158,3 +158,26 @@ def test_radius_loss_gradients(cap, p_attr, p_rep):
     (got["attractive"] + 0.5 * got["repulsive"] + 0.2 * got["coward"] + 0.3 * got["noise"]).backward()
     check("rg x", xc.grad, xr.grad)
     check("rg beta", bc.grad, br.grad)
+
+
+@pytest.mark.parametrize("cap,loop,with_batch", [(32, False, True), (4, False, False), (1000, True, True)])
+def test_radius_graph_edge_list(cap, loop, with_batch):
+    """The materialised radius graph against the oracle's restatement of torch_cluster.radius_graph:
+    identical edge list (integer output: bit-exact), including the neighbour cap and batch segments."""
+    from gnn_tracking_b200.cluster import radius_graph
+    from oracle import losses_oracle as L
+    gen = torch.Generator().manual_seed(5)
+    n = 1500
+    x = torch.randn(n, 3, generator=gen)
+    batch = (torch.arange(n) * 3 // n) if with_batch else None
+    ref = L.radius_graph(x, 0.5, batch=batch, max_num_neighbors=cap)
+    if loop:
+        # the oracle restates loop=False: add the self loops and restore the (centre, neighbour) order
+        ref = torch.cat([ref, torch.arange(n).repeat(2, 1)], 1)
+        order = torch.argsort(ref[1] * n + ref[0])
+        ref = ref[:, order]
+    got = radius_graph(x.cuda(), 0.5, batch=None if batch is None else batch.cuda(), loop=loop, max_num_neighbors=cap)
+    assert got.dtype == torch.int64 and torch.equal(got.cpu(), ref)
+    assert radius_graph(torch.zeros((0, 3), device="cuda"), 1.0).shape == (2, 0)
+    flipped = radius_graph(x.cuda(), 0.5, max_num_neighbors=cap, flow="target_to_source")
+    assert torch.equal(flipped.flip(0), radius_graph(x.cuda(), 0.5, max_num_neighbors=cap))
