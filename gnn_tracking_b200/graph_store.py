@@ -1,0 +1,204 @@
+"""Binary on-disk graph format with the destination-sorted plan stored next to the tensors, read
+through one pinned staging buffer and one host-to-device copy.
+
+The reference pickles PyG ``Data`` objects and loads one per step (``graph_construction/
+graph_builder.py:396-455``, ``utils/loading.py:97-113,219-239``): every step re-derives the
+scatter indices and pays a pageable host-to-device copy per tensor.  Here the writer (an offline
+converter, like the reference's graph builder) stores
+
+    header   : magic, JSON table {name: dtype, shape, offset} (offsets 4096-byte aligned)
+    payload  : x, edge_index, edge_attr, any per-node / per-edge truth tensors, and the plan of
+               ``plan.GraphPlan`` -- ``perm`` (stable argsort of ``edge_index[1]``), ``rowptr``,
+               ``src_sorted``, ``dst_sorted`` as int32
+
+and the reader brings the whole payload to the device with a single asynchronous copy and adopts the
+stored plan (``plan.adopt_plan``), so the first forward over the graph does not sort anything.
+"""
+from __future__ import annotations
+
+import json
+import struct
+from pathlib import Path
+from typing import Mapping
+
+import numpy as np
+import torch
+from torch import Tensor
+
+from .plan import GraphPlan, adopt_plan
+
+MAGIC = b"GTBGRAF1"
+ALIGN = 4096
+_PLAN_KEYS = ("plan.perm", "plan.rowptr", "plan.src_sorted", "plan.dst_sorted")
+
+
+class GraphData:
+    """Attribute bag with the fields the reference's models and losses read from a PyG ``Data``
+    (``x``, ``edge_index``, ``edge_attr``, ``y``, ``particle_id``, ``pt``, ...)."""
+
+    def __init__(self, **tensors):
+        self.__dict__.update(tensors)
+
+    def keys(self):
+        return [k for k in self.__dict__ if not k.startswith("_")]
+
+    @property
+    def num_nodes(self) -> int:
+        return self.x.size(0)
+
+    @property
+    def num_edges(self) -> int:
+        return self.edge_index.size(1)
+
+    def to(self, device, non_blocking: bool = False) -> "GraphData":
+        return GraphData(**{k: (v.to(device, non_blocking=non_blocking) if isinstance(v, Tensor) else v)
+                            for k, v in self.__dict__.items()})
+
+
+def host_plan(edge_index: np.ndarray, n_nodes: int) -> dict[str, np.ndarray]:
+    """The plan of ``gtb_plan_build`` computed by the offline writer: stable sort of the edges by
+    destination, CSR row pointers, sorted endpoints (int32)."""
+    src, dst = edge_index[0], edge_index[1]
+    if src.size and (min(src.min(), dst.min()) < 0 or max(src.max(), dst.max()) >= n_nodes):
+        raise IndexError("edge_index contains node indices outside [0, num_nodes)")
+    perm = np.argsort(dst, kind="stable").astype(np.int32)
+    rowptr = np.zeros(n_nodes + 1, dtype=np.int32)
+    np.cumsum(np.bincount(dst, minlength=n_nodes), out=rowptr[1:])
+    return {"plan.perm": perm, "plan.rowptr": rowptr, "plan.src_sorted": src[perm].astype(np.int32),
+            "plan.dst_sorted": dst[perm].astype(np.int32)}
+
+
+def write_graph(path, *, x: Tensor, edge_index: Tensor, edge_attr: Tensor, extras: Mapping[str, Tensor] | None = None,
+                with_plan: bool = True) -> None:
+    arrays: dict[str, np.ndarray] = {
+        "x": x.detach().cpu().contiguous().numpy(),
+        "edge_index": edge_index.detach().cpu().to(torch.int64).contiguous().numpy(),
+        "edge_attr": edge_attr.detach().cpu().contiguous().numpy(),
+    }
+    for k, v in (extras or {}).items():
+        if k in arrays or k.startswith("plan."):
+            raise ValueError(f"reserved name {k!r}")
+        arrays[k] = v.detach().cpu().contiguous().numpy()
+    if with_plan:
+        arrays.update(host_plan(arrays["edge_index"], arrays["x"].shape[0]))
+    table, off = {}, 0
+    for k, a in arrays.items():
+        if a.dtype == np.bool_:
+            a = arrays[k] = a.view(np.uint8)
+            table[k] = {"dtype": "bool", "shape": list(a.shape), "offset": off}
+        else:
+            table[k] = {"dtype": str(a.dtype), "shape": list(a.shape), "offset": off}
+        off = (off + a.nbytes + ALIGN - 1) // ALIGN * ALIGN
+    header = json.dumps({"arrays": table, "payload_bytes": off}).encode()
+    head_len = (len(MAGIC) + 8 + len(header) + ALIGN - 1) // ALIGN * ALIGN
+    with open(path, "wb") as f:
+        f.write(MAGIC + struct.pack("<II", len(header), head_len) + header)
+        f.write(b"\0" * (head_len - f.tell()))
+        for k, a in arrays.items():
+            f.seek(head_len + table[k]["offset"])
+            f.write(a.tobytes())
+        f.truncate(head_len + off)
+
+
+_DTYPES = {"float32": torch.float32, "float64": torch.float64, "int64": torch.int64, "int32": torch.int32,
+           "uint8": torch.uint8, "int8": torch.int8, "int16": torch.int16, "float16": torch.float16, "bool": torch.bool}
+
+
+def _read_host(path, pinned: bool):
+    """File -> (array table, one host buffer holding the payload)."""
+    with open(path, "rb") as f:
+        head = f.read(len(MAGIC) + 8)
+        if head[:len(MAGIC)] != MAGIC:
+            raise ValueError(f"{path}: not a gnn_tracking_b200 graph file")
+        n_json, head_len = struct.unpack("<II", head[len(MAGIC):])
+        meta = json.loads(f.read(n_json))
+        nbytes = int(meta["payload_bytes"])
+        host = torch.empty(max(nbytes, 1), dtype=torch.uint8, pin_memory=pinned)
+        f.seek(head_len)
+        got = f.readinto(memoryview(host.numpy())[:nbytes]) if nbytes else 0
+        if got != nbytes:
+            raise ValueError(f"{path}: truncated payload ({got} of {nbytes} bytes)")
+    return meta, host
+
+
+def _materialize(meta, host: Tensor, device: torch.device) -> GraphData:
+    """One asynchronous copy of the payload on the current stream, tensors as views of it, plan adopted."""
+    buf = host.to(device, non_blocking=True) if device.type == "cuda" else host
+    out: dict[str, Tensor] = {}
+    for k, m in meta["arrays"].items():
+        dt = _DTYPES[m["dtype"]]
+        n_el = int(np.prod(m["shape"])) if m["shape"] else 1
+        size = n_el * (1 if dt == torch.bool else torch.empty((), dtype=dt).element_size())
+        raw = buf[m["offset"]:m["offset"] + size]
+        out[k] = (raw.view(torch.bool) if dt == torch.bool else raw.view(dt)).reshape(m["shape"])
+    plan_parts = {k: out.pop(k) for k in _PLAN_KEYS if k in out}
+    data = GraphData(**out)
+    data._staging = host  # keeps the pinned buffer alive until the asynchronous copy has been consumed
+    if len(plan_parts) == len(_PLAN_KEYS) and device.type == "cuda":
+        n, e = data.x.size(0), data.edge_index.size(1)
+        adopt_plan(data.edge_index, n, GraphPlan(n, e, plan_parts["plan.perm"], plan_parts["plan.rowptr"],
+                                                 plan_parts["plan.src_sorted"], plan_parts["plan.dst_sorted"],
+                                                 torch.zeros(1, dtype=torch.int32, device=device)))
+    else:
+        data._plan_arrays = plan_parts
+    return data
+
+
+def read_graph(path, device: torch.device | str = "cuda", *, pinned: bool | None = None) -> GraphData:
+    """Load a graph written by ``write_graph``.  The payload is read into one (pinned, when the target
+    is a CUDA device) host buffer and copied with a single ``non_blocking`` transfer on the current
+    stream; tensors are views of that one device allocation.  The stored plan is adopted."""
+    device = torch.device(device)
+    pinned = device.type == "cuda" if pinned is None else pinned
+    meta, host = _read_host(path, pinned)
+    return _materialize(meta, host, device)
+
+
+class GraphLoader:
+    """Iterates over graph files one graph per step (the reference trains with ``batch_size=1``,
+    ``utils/loading.py:235``): a reader thread fills pinned staging buffers ``prefetch`` files ahead,
+    the consumer only issues the host-to-device copy."""
+
+    def __init__(self, paths, device: torch.device | str = "cuda", *, prefetch: int = 2, pinned: bool | None = None):
+        self.paths = [Path(p) for p in paths]
+        self.device = torch.device(device)
+        self.pinned = self.device.type == "cuda" if pinned is None else pinned
+        self.prefetch = max(1, int(prefetch))
+
+    def __len__(self) -> int:
+        return len(self.paths)
+
+    def __iter__(self):
+        import queue
+        import threading
+
+        q: queue.Queue = queue.Queue(maxsize=self.prefetch)
+        stop = threading.Event()
+
+        def reader():
+            try:
+                for p in self.paths:
+                    if stop.is_set():
+                        return
+                    q.put(_read_host(p, self.pinned))
+                q.put(None)
+            except BaseException as exc:  # noqa: BLE001 - re-raised in the consumer
+                q.put(exc)
+
+        th = threading.Thread(target=reader, daemon=True)
+        th.start()
+        try:
+            while True:
+                item = q.get()
+                if item is None:
+                    return
+                if isinstance(item, BaseException):
+                    raise item
+                yield _materialize(item[0], item[1], self.device)
+        finally:
+            stop.set()
+            while th.is_alive():  # unblock a reader waiting on a full queue
+                try:
+                    q.get_nowait()
+                except queue.Empty:
+                    th.join(timeout=0.05)

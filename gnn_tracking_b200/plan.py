@@ -105,5 +105,13 @@ def get_plan(edge_index: Tensor, n_nodes: int) -> GraphPlan:
     return plan
 
 
+def adopt_plan(edge_index: Tensor, n_nodes: int, plan: GraphPlan) -> None:
+    """Register a plan computed elsewhere (``graph_store.read_graph``: stored next to the graph by the
+    offline writer) for this ``edge_index`` tensor: ``get_plan`` returns it without sorting."""
+    if plan.n_edges != edge_index.size(1) or plan.n_nodes != n_nodes:
+        raise ValueError("plan does not match the graph")
+    _CACHE[id(edge_index)] = (weakref.ref(edge_index), edge_index._version, n_nodes, plan)
+
+
 def clear_plan_cache() -> None:
     _CACHE.clear()

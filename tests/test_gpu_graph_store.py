@@ -1,0 +1,38 @@
+"""graph_store.read_graph on the device: one pinned staging buffer, one copy, the stored plan adopted
+(bit-identical to gtb_plan_build) and used by the models without sorting."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_read_graph_adopts_plan(tmp_path):
+    from gnn_tracking_b200 import graph_store as gs
+    from gnn_tracking_b200 import ops
+    from gnn_tracking_b200.models.edge_classifier import ECForGraphTCN
+    from gnn_tracking_b200.plan import build_plan, clear_plan_cache, get_plan
+
+    gen = torch.Generator().manual_seed(3)
+    n, e = 3000, 40000
+    ei = torch.randint(0, n, (2, e), generator=gen)
+    x, ea = torch.randn(n, 14, generator=gen), torch.randn(e, 4, generator=gen)
+    path = tmp_path / "g.gtb"
+    gs.write_graph(path, x=x, edge_index=ei, edge_attr=ea, extras={"y": torch.rand(e, generator=gen) < 0.5})
+    clear_plan_cache()
+    d = gs.read_graph(path)
+    torch.cuda.synchronize()
+    assert d.x.is_cuda and torch.equal(d.x.cpu(), x) and torch.equal(d.edge_index.cpu(), ei) and d.y.dtype == torch.bool
+    before = ops.launch_count()
+    plan = get_plan(d.edge_index, n)          # adopted: no kernels
+    assert ops.launch_count() == before
+    ref = build_plan(ei.cuda(), n)
+    for k in ("perm", "rowptr", "src_sorted", "dst_sorted"):
+        assert torch.equal(getattr(plan, k), getattr(ref, k)), k
+    torch.manual_seed(0)
+    m = ECForGraphTCN(node_indim=14, edge_indim=4, L_ec=2, hidden_dim=32).cuda()
+    with torch.no_grad():
+        w_stored = m(d)["W"]
+        clear_plan_cache()
+        w_built = m(gs.GraphData(x=x.cuda(), edge_index=ei.cuda(), edge_attr=ea.cuda()))["W"]
+    # same kernels on the same plan; the per-destination sums use floating-point atomics, whose order varies
+    assert torch.allclose(w_stored, w_built, rtol=0, atol=1e-6)
