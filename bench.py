@@ -315,6 +315,36 @@ def run_ours(args) -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed_e2e_pipelined(steps, warmup):
+        """The loop a user of the loader writes: ``for data in DevicePrefetcher(host graphs): model(data)``.
+        Every step copies its own inputs from pinned host memory and reads its result back; the copy
+        of step k + 1 is in flight on the loader's side stream while step k computes.  One event pair
+        around all ``steps`` steps (pipeline fill, per-step L2 flush and result copies included)."""
+        from gnn_tracking_b200.graph_store import DevicePrefetcher, GraphData
+        host_graph = GraphData(x=hx, edge_index=hei, edge_attr=hea)
+
+        def run(k):
+            for data in DevicePrefetcher((host_graph for _ in range(k)), dev):
+                flush.zero_()
+                clear_plan_cache()
+                with torch.no_grad():
+                    out = model.forward_tensors(data.x, data.edge_index, data.edge_attr, halo=halo)
+                hw.copy_(out["W"], non_blocking=True)
+
+        run(warmup)
+        barrier()
+        s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        run(steps)
+        t.record()
+        barrier()
+        ms = s.elapsed_time(t)
+        if world > 1:
+            tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        return ms
+
     def timed(fn, steps, warmup):
         for _ in range(warmup):
             fn()
@@ -339,7 +369,8 @@ def run_ours(args) -> None:
 
     with ClockSampler(local) as clocks:
         ms, launches = timed(step_resident, args.steps, args.warmup)
-        ms_e2e, _ = timed(step_e2e, args.steps, max(1, args.warmup))
+        ms_e2e_serial, _ = timed(step_e2e, args.steps, max(1, args.warmup))
+        ms_e2e = timed_e2e_pipelined(args.steps, max(1, args.warmup))
 
     # ---- dominant kernel alone (rank 0's graph)
     dn, de = (HIDDEN, HIDDEN) if args.dims == "wide" else (5, 4)
@@ -381,7 +412,11 @@ def run_ours(args) -> None:
                    "l2": "flushed between timed iterations (256 MB write)", "multi_gpu": multi,
                    "impl": os.environ.get("GTB_IMPL", "auto")},
         "e2e": {"value": e2e_val, "unit": "edges/s", "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": hx.numel() * 4 + hei.numel() * 8 + hea.numel() * 4, "d2h_bytes_per_step": e * 4},
+                "h2d_bytes_per_step": hx.numel() * 4 + hei.numel() * 8 + hea.numel() * 4, "d2h_bytes_per_step": e * 4,
+                "how": "graph_store.DevicePrefetcher loop: every step copies its inputs from pinned host memory (side "
+                       "stream, one step ahead) and reads W back; one event pair around all steps, L2 flush inside",
+                "serial_value": n_total_edges * args.steps / (ms_e2e_serial * 1e-3),
+                "serial_ms_per_step": ms_e2e_serial / args.steps},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm",
                      "kernel": f"fused IN edge kernel ({k_impl}): gathered pre-projected node rows + relational MLP + scattered store + "

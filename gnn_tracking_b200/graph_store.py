@@ -13,6 +13,8 @@ converter, like the reference's graph builder) stores
 
 and the reader brings the whole payload to the device with a single asynchronous copy and adopts the
 stored plan (``plan.adopt_plan``), so the first forward over the graph does not sort anything.
+``DevicePrefetcher`` / ``GraphLoader`` issue that copy for the next graph on a side stream while the
+caller computes on the current one.
 """
 from __future__ import annotations
 
@@ -52,7 +54,7 @@ class GraphData:
 
     def to(self, device, non_blocking: bool = False) -> "GraphData":
         return GraphData(**{k: (v.to(device, non_blocking=non_blocking) if isinstance(v, Tensor) else v)
-                            for k, v in self.__dict__.items()})
+                            for k, v in self.__dict__.items() if not k.startswith("_")})
 
 
 def host_plan(edge_index: np.ndarray, n_nodes: int) -> dict[str, np.ndarray]:
@@ -154,10 +156,61 @@ def read_graph(path, device: torch.device | str = "cuda", *, pinned: bool | None
     return _materialize(meta, host, device)
 
 
+class DevicePrefetcher:
+    """Yields device-resident graphs from an iterable of host-side ones, with the host-to-device
+    copy of graph k + 1 issued on a side stream BEFORE graph k is handed to the caller, so the copy
+    runs under the caller's kernels for graph k (double buffering; the reference's DataLoader +
+    ``.to(device)`` copies in line with the step).  Items are ``GraphData`` objects of (pinned) host
+    tensors or the ``(table, staging buffer)`` pairs of ``GraphLoader``."""
+
+    def __init__(self, source, device: torch.device | str = "cuda", *, depth: int = 1):
+        self.source = source
+        self.device = torch.device(device)
+        self.depth = max(1, int(depth))
+
+    def _issue(self, item, stream):
+        with torch.cuda.stream(stream):
+            if isinstance(item, GraphData):
+                data = item.to(self.device, non_blocking=True)
+            else:
+                data = _materialize(item[0], item[1], self.device)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+        return data, ev
+
+    def __iter__(self):
+        from collections import deque
+        if self.device.type != "cuda":
+            for item in self.source:
+                yield item if isinstance(item, GraphData) else _materialize(item[0], item[1], self.device)
+            return
+        stream = torch.cuda.Stream(self.device)
+        it = iter(self.source)
+        inflight: deque = deque()
+
+        def top_up():
+            while len(inflight) <= self.depth:
+                try:
+                    inflight.append(self._issue(next(it), stream))
+                except StopIteration:
+                    return
+
+        top_up()
+        while inflight:
+            data, ev = inflight.popleft()
+            top_up()  # the next copy is in flight before the caller launches work on this graph
+            cur = torch.cuda.current_stream(self.device)
+            cur.wait_event(ev)
+            for v in data.__dict__.values():
+                if isinstance(v, Tensor) and v.is_cuda:
+                    v.record_stream(cur)  # allocated on the side stream, used (and freed) on the caller's
+            yield data
+
+
 class GraphLoader:
     """Iterates over graph files one graph per step (the reference trains with ``batch_size=1``,
-    ``utils/loading.py:235``): a reader thread fills pinned staging buffers ``prefetch`` files ahead,
-    the consumer only issues the host-to-device copy."""
+    ``utils/loading.py:235``): a reader thread fills pinned staging buffers ``prefetch`` files ahead
+    and a ``DevicePrefetcher`` keeps the copy of the next graph in flight under the current step."""
 
     def __init__(self, paths, device: torch.device | str = "cuda", *, prefetch: int = 2, pinned: bool | None = None):
         self.paths = [Path(p) for p in paths]
@@ -168,7 +221,7 @@ class GraphLoader:
     def __len__(self) -> int:
         return len(self.paths)
 
-    def __iter__(self):
+    def _host_items(self):
         import queue
         import threading
 
@@ -194,7 +247,7 @@ class GraphLoader:
                     return
                 if isinstance(item, BaseException):
                     raise item
-                yield _materialize(item[0], item[1], self.device)
+                yield item
         finally:
             stop.set()
             while th.is_alive():  # unblock a reader waiting on a full queue
@@ -202,3 +255,6 @@ class GraphLoader:
                     q.get_nowait()
                 except queue.Empty:
                     th.join(timeout=0.05)
+
+    def __iter__(self):
+        return iter(DevicePrefetcher(self._host_items(), self.device))

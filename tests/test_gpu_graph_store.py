@@ -36,3 +36,35 @@ def test_read_graph_adopts_plan(tmp_path):
         w_built = m(gs.GraphData(x=x.cuda(), edge_index=ei.cuda(), edge_attr=ea.cuda()))["W"]
     # same kernels on the same plan; the per-destination sums use floating-point atomics, whose order varies
     assert torch.allclose(w_stored, w_built, rtol=0, atol=1e-6)
+
+
+def test_prefetched_graphs_give_the_same_results(tmp_path):
+    """DevicePrefetcher (pinned host graphs) and GraphLoader (files): the copy of the next graph runs on
+    a side stream under the current forward; outputs equal those of plain resident inputs."""
+    from gnn_tracking_b200 import graph_store as gs
+    from gnn_tracking_b200.models.edge_classifier import ECForGraphTCN
+    from gnn_tracking_b200.plan import clear_plan_cache
+
+    torch.manual_seed(1)
+    m = ECForGraphTCN(node_indim=14, edge_indim=4, L_ec=2, hidden_dim=32).cuda()
+    graphs, paths, want = [], [], []
+    for i in range(5):
+        gen = torch.Generator().manual_seed(10 + i)
+        n, e = 2000 + 100 * i, 30000 + 1000 * i
+        g = dict(x=torch.randn(n, 14, generator=gen), edge_index=torch.randint(0, n, (2, e), generator=gen),
+                 edge_attr=torch.randn(e, 4, generator=gen))
+        graphs.append(gs.GraphData(**{k: v.pin_memory() for k, v in g.items()}))
+        paths.append(tmp_path / f"g{i}.gtb")
+        gs.write_graph(paths[-1], **g)
+        with torch.no_grad():
+            want.append(m(gs.GraphData(**{k: v.cuda() for k, v in g.items()}))["W"].clone())
+    for source in (gs.DevicePrefetcher(graphs), gs.GraphLoader(paths, prefetch=2)):
+        clear_plan_cache()
+        got = []
+        with torch.no_grad():
+            for data in source:
+                got.append(m(data)["W"].clone())
+        torch.cuda.synchronize()
+        assert len(got) == 5
+        for a, b in zip(got, want):
+            assert torch.allclose(a, b, rtol=0, atol=1e-6)
