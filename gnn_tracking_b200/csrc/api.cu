@@ -31,7 +31,7 @@ int fused_mlp_tc(const gtb_mlp_desc_t&, cudaStream_t);
 int tc_timeout_flag(int*);
 int oc_potentials_grad(const float*, const float*, int32_t, const int64_t*, const int32_t*, int64_t, const int32_t*, int32_t,
                        float, int64_t, const float*, float*, float*, float*, cudaStream_t);
-int dbscan(const float*, int, int64_t, float, int, unsigned char*, int*, int*, cudaStream_t);
+int dbscan(const float*, int, int64_t, double, int, unsigned char*, int*, int*, cudaStream_t);
 int radius_pair_sum(const float*, int, int64_t, const int64_t*, const int64_t*, const unsigned char*, const float*, float, float,
                     float, float, int, int, double*, cudaStream_t);
 int edge_dist_pow_sum(const float*, int, const int64_t*, int64_t, const unsigned char*, float, double*, cudaStream_t);
@@ -308,7 +308,7 @@ int gtb_oc_potentials_grad(const float* beta, const float* x, int32_t d, const i
                             static_cast<cudaStream_t>(stream));
 }
 
-int gtb_dbscan_f32(const float* x, int32_t d, int64_t n, float eps, int32_t min_pts, uint8_t* core, int32_t* parent,
+int gtb_dbscan_f32(const float* x, int32_t d, int64_t n, double eps, int32_t min_pts, uint8_t* core, int32_t* parent,
                    int32_t* root, void* stream) {
   return dbscan(x, d, n, eps, min_pts, core, parent, root, static_cast<cudaStream_t>(stream));
 }

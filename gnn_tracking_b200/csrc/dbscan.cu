@@ -157,12 +157,12 @@ static void db_launch(int blocks, cudaStream_t st, const float* x, int d, int64_
   dbscan_kernel<D><<<blocks, DB_T, 0, st>>>(x, d, n, eps2, min_pts, phase, core, parent, root);
 }
 
-int dbscan(const float* x, int d, int64_t n, float eps, int min_pts, unsigned char* core, int* parent, int* root,
+int dbscan(const float* x, int d, int64_t n, double eps, int min_pts, unsigned char* core, int* parent, int* root,
            cudaStream_t st) {
   GTB_REQUIRE(x && core && parent && root && d >= 1 && d <= DB_MAXD && n < (1ll << 31) - 1 && min_pts >= 1, GTB_ERR_BAD_ARG,
               "gtb_dbscan_f32: bad arguments (dimension must be in [1, %d])", DB_MAXD);
   if (n == 0) return GTB_OK;
-  const double eps2 = (double)eps * (double)eps;
+  const double eps2 = eps * eps;
   const int blocks = (int)imin64((n + DB_T - 1) / DB_T, (int64_t)kNumSMs * 4);
   for (int phase = 0; phase < 3; ++phase) {
     if (d <= 4) db_launch<4>(blocks, st, x, d, n, eps2, min_pts, phase, core, parent, root);

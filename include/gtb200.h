@@ -316,7 +316,7 @@ int gtb_edge_dist_pow_grad_f32(const float* x, int32_t d, const int64_t* edges, 
  *   parent int32 [n]: scratch (union-find forest of the core samples, rooted at the lowest index)
  *   root   int32 [n]: lowest core index of the point's cluster; border points: the smallest adjacent
  *                     root; noise: -1.  sklearn's label = rank of `root` among the distinct roots. */
-int gtb_dbscan_f32(const float* x, int32_t d, int64_t n, float eps, int32_t min_pts,
+int gtb_dbscan_f32(const float* x, int32_t d, int64_t n, double eps, int32_t min_pts,
                    uint8_t* core, int32_t* parent, int32_t* root, void* stream);
 
 /* inv_norm[r] = 1 / max(||cat_s src_s[r]||_2, eps): torch.nn.functional.normalize(x, p=2, dim=1,

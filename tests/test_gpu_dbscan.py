@@ -84,3 +84,32 @@ def test_fastrescan_equal_slowrescan():
             labels = fr.cluster(eps=eps, min_pts=min_pts).cpu().numpy()
             labels2 = DBSCAN(eps=eps, min_samples=min_pts).fit_predict(x)
             assert (labels == labels2).all()
+
+
+def test_graph_tcn_latent_space_clustering():
+    """BASELINE config 5 in small: GraphTCN forward on the CUDA path, then the DBSCAN trials of the
+    hyper-parameter scan on the device-resident latent coordinates H; labels equal sklearn's on the
+    same H (dbscanscanner.py:160-177 copies H to the host first)."""
+    from sklearn.cluster import DBSCAN
+
+    from gnn_tracking_b200.models.track_condensation_networks import GraphTCN
+    from gnn_tracking_b200.postprocessing.dbscan import DBSCANFastRescan
+
+    gen = torch.Generator().manual_seed(4)
+    n, e = 4000, 50000
+    data = type("D", (), {})()
+    data.x = torch.randn(n, 14, generator=gen).cuda()
+    data.edge_index = torch.randint(0, n, (2, e), generator=gen).cuda()
+    data.edge_attr = torch.randn(e, 4, generator=gen).cuda()
+    torch.manual_seed(2)
+    m = GraphTCN(14, 4, hidden_dim=32, L_ec=2, L_hc=2, h_outdim=3, ec_threshold=0.0).cuda()
+    with torch.no_grad():
+        h = m(data)["H"]
+    assert h.shape == (n, 3)
+    spread = float(h.std())
+    scanner = DBSCANFastRescan(h, max_eps=1.0)
+    hc = h.cpu().numpy()
+    for eps, min_pts in [(0.05 * spread, 1), (0.1 * spread, 2), (0.3 * spread, 4)]:
+        got = scanner.cluster(eps=eps, min_pts=min_pts).cpu().numpy()
+        want = DBSCAN(eps=eps, min_samples=min_pts).fit_predict(hc)
+        assert np.array_equal(got, want), (eps, min_pts)
