@@ -140,3 +140,25 @@ def test_install_patches_the_reference_package():
             mod = importlib.import_module(ref_mod)
             for k, v in attrs.items():
                 setattr(mod, k, v)
+
+
+def test_loss_wrappers_host_logic():
+    """DummyMultiLoss / LossClones (reference metrics/losses/__init__.py:44-131) are host logic."""
+    import torch
+
+    from gnn_tracking_b200.metrics.losses import DummyMultiLoss, LossClones
+
+    r = DummyMultiLoss()(x=torch.arange(4.0), other=1)
+    assert float(r.loss) == 6.0 and list(r.loss_dct) == ["dummy"]
+
+    seen = []
+
+    class Probe(torch.nn.Module):
+        def forward(self, *, w, y, extra, **kw):
+            seen.append(sorted(kw))
+            return (w - y).sum() + extra
+
+    out = LossClones(Probe())(w_1=torch.ones(2), y_1=torch.zeros(2), w_0=torch.zeros(2), y_0=torch.zeros(2), extra=1.0,
+                              w=torch.full((2,), 9.0))
+    assert list(out) == ["0", "1"] and float(out["0"]) == 1.0 and float(out["1"]) == 3.0
+    assert seen[0] == ["w_1", "y_1"] and seen[1] == ["w_0", "y_0"]  # the other clone's tensors pass through renamed-free
