@@ -13,8 +13,23 @@ namespace gtb {
 constexpr int ATB_ROWS = 64;     // rows per staged tile
 constexpr int ATB_THREADS = 256;
 
-// A tile [64][KA] and B tile [64][NB] in shared memory (KA, NB <= 64, zero padded to 64);
-// thread (ki = tid >> 4, nj = tid & 15) owns the 4 x 4 block out[4 ki .. , 4 nj ..].
+typedef unsigned long long atb_f32x2;
+__device__ __forceinline__ atb_f32x2 atb_pack2(float a, float b) {
+  atb_f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ atb_f32x2 atb_fma2(atb_f32x2 a, atb_f32x2 b, atb_f32x2 c) {
+  atb_f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
+// A tile [64][KA] and B tile [64][NB] in shared memory (KA, NB <= 64, zero padded to 64).  Two
+// groups of 128 threads take the even / odd rows of a tile; thread (ki = t >> 4, nj = t & 15) of a
+// group owns the 8 x 4 block out[8 ki .., 4 nj ..] as packed pairs: per row 3 x LDS.128 and
+// 16 x FFMA2 (a_i broadcast against the pairs (b0, b1), (b2, b3); ptxas folds the broadcast into the
+// instruction's scalar operand), i.e. 19 issue slots for 32 multiply-adds.
 __global__ void __launch_bounds__(ATB_THREADS) rows_atb_kernel(const float* __restrict__ A, int a_ld,
                                                                const int32_t* __restrict__ a_index, int a_relu, int ka,
                                                                const float* __restrict__ B, int b_ld, int nb,
@@ -22,52 +37,83 @@ __global__ void __launch_bounds__(ATB_THREADS) rows_atb_kernel(const float* __re
                                                                float* __restrict__ colsum) {
   __shared__ __align__(16) float As[ATB_ROWS][68];
   __shared__ __align__(16) float Bs[ATB_ROWS][68];
-  const int tid = threadIdx.x, ki = tid >> 4, nj = tid & 15;
-  float acc[4][4];
+  const int tid = threadIdx.x, grp = tid >> 7, ki = (tid & 127) >> 4, nj = tid & 15;
+  atb_f32x2 acc[8][2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = atb_pack2(0.f, 0.f);
   float csum = 0.f;  // column tid of B (tid < nb)
+  const bool vec_a = (ka & 3) == 0 && (a_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0;
+  const bool vec_b = (nb & 3) == 0 && (b_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0;
   const int64_t n_tiles = (n_rows + ATB_ROWS - 1) / ATB_ROWS;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t row0 = tile * ATB_ROWS;
     const int rows_here = (int)min((int64_t)ATB_ROWS, n_rows - row0);
-    for (int i = tid; i < ATB_ROWS * 64; i += ATB_THREADS) {
-      const int r = i >> 6, c = i & 63;
-      float a = 0.f, b = 0.f;
-      if (r < rows_here) {
-        if (c < ka) {
+    if (vec_a) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = tid + j * ATB_THREADS, r = i >> 4, c = (i & 15) << 2;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < rows_here && c < ka) {
+          const int64_t ar = a_index ? (int64_t)__ldg(a_index + row0 + r) : row0 + r;
+          a = __ldg(reinterpret_cast<const float4*>(A + (size_t)ar * a_ld + c));
+          if (a_relu) a = make_float4(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f), fmaxf(a.z, 0.f), fmaxf(a.w, 0.f));
+        }
+        *reinterpret_cast<float4*>(&As[r][c]) = a;
+      }
+    } else {
+      for (int i = tid; i < ATB_ROWS * 64; i += ATB_THREADS) {
+        const int r = i >> 6, c = i & 63;
+        float a = 0.f;
+        if (r < rows_here && c < ka) {
           const int64_t ar = a_index ? (int64_t)__ldg(a_index + row0 + r) : row0 + r;
           a = __ldg(A + (size_t)ar * a_ld + c);
           if (a_relu) a = fmaxf(a, 0.f);
         }
-        if (c < nb) b = __ldg(B + (size_t)(row0 + r) * b_ld + c);
+        As[r][c] = a;
       }
-      As[r][c] = a;
-      Bs[r][c] = b;
+    }
+    if (vec_b) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = tid + j * ATB_THREADS, r = i >> 4, c = (i & 15) << 2;
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < rows_here && c < nb) b = __ldg(reinterpret_cast<const float4*>(B + (size_t)(row0 + r) * b_ld + c));
+        *reinterpret_cast<float4*>(&Bs[r][c]) = b;
+      }
+    } else {
+      for (int i = tid; i < ATB_ROWS * 64; i += ATB_THREADS) {
+        const int r = i >> 6, c = i & 63;
+        Bs[r][c] = (r < rows_here && c < nb) ? __ldg(B + (size_t)(row0 + r) * b_ld + c) : 0.f;
+      }
     }
     __syncthreads();
-#pragma unroll 8
-    for (int r = 0; r < ATB_ROWS; ++r) {
-      const float4 a = *reinterpret_cast<const float4*>(&As[r][4 * ki]);
+#pragma unroll 4
+    for (int r = grp; r < ATB_ROWS; r += 2) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[r][8 * ki]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[r][8 * ki + 4]);
       const float4 b = *reinterpret_cast<const float4*>(&Bs[r][4 * nj]);
-      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const atb_f32x2 b01 = atb_pack2(b.x, b.y), b23 = atb_pack2(b.z, b.w);
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      for (int i = 0; i < 8; ++i) {
+        const atb_f32x2 aa = atb_pack2(av[i], av[i]);
+        acc[i][0] = atb_fma2(aa, b01, acc[i][0]);
+        acc[i][1] = atb_fma2(aa, b23, acc[i][1]);
+      }
     }
     if (colsum != nullptr && tid < nb)
       for (int r = 0; r < rows_here; ++r) csum += Bs[r][tid];
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int k = 4 * ki + i, n = 4 * nj + j;
-      if (k < ka && n < nb) atomicAdd(out + (size_t)k * out_ld + n, acc[i][j]);
+    for (int h = 0; h < 2; ++h) {
+      float v0, v1;
+      asm("mov.b64 {%0, %1}, %2;" : "=f"(v0), "=f"(v1) : "l"(acc[i][h]));
+      const int k = 8 * ki + i, n = 4 * nj + 2 * h;
+      if (k < ka && n < nb) atomicAdd(out + (size_t)k * out_ld + n, v0);
+      if (k < ka && n + 1 < nb) atomicAdd(out + (size_t)k * out_ld + n + 1, v1);
     }
   if (colsum != nullptr && tid < nb) atomicAdd(colsum + tid, csum);
 }
