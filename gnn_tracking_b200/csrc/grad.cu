@@ -124,7 +124,9 @@ int rows_atb(const float* A, int a_ld, const int32_t* a_index, int a_relu, int k
               GTB_ERR_BAD_ARG, "gtb_rows_atb_f32: widths must be in [1, 64] (got %d x %d)", ka, nb);
   if (n_rows == 0) return GTB_OK;
   const int64_t n_tiles = (n_rows + ATB_ROWS - 1) / ATB_ROWS;
-  const int grid = (int)imin64(n_tiles, (int64_t)kNumSMs * 4);
+  // every CTA ends with 64 x 64 atomics onto the same addresses: at least 16 tiles per CTA, and no
+  // more CTAs than are resident at once (2 per SM at 122 registers)
+  const int grid = (int)imin64((n_tiles + 15) / 16, (int64_t)kNumSMs * 2);
   rows_atb_kernel<<<grid, ATB_THREADS, 0, st>>>(A, a_ld, a_index, a_relu, ka, B, b_ld, nb, n_rows, out, out_ld, colsum);
   GTB_CHECK_LAUNCH("rows_atb_kernel");
   return GTB_OK;
