@@ -195,6 +195,12 @@ class DevicePrefetcher:
                 except StopIteration:
                     return
 
+        # Back-pressure: kernel launches are asynchronous, so an unthrottled host would enqueue many
+        # steps ahead of the GPU; every graph in that backlog pins its own device buffers (they are only
+        # reusable once the step that read them has run), and the allocator answers with cudaMalloc calls
+        # in the middle of the loop.  The host therefore never gets more than depth + 1 finished-enqueuing
+        # steps ahead of the GPU.
+        done: deque = deque()
         top_up()
         while inflight:
             data, ev = inflight.popleft()
@@ -205,6 +211,12 @@ class DevicePrefetcher:
                 if isinstance(v, Tensor) and v.is_cuda:
                     v.record_stream(cur)  # allocated on the side stream, used (and freed) on the caller's
             yield data
+            del data
+            step_done = torch.cuda.Event()
+            step_done.record(torch.cuda.current_stream(self.device))  # the caller's work on this graph is enqueued
+            done.append(step_done)
+            if len(done) > self.depth + 1:
+                done.popleft().synchronize()
 
 
 class GraphLoader:
