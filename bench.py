@@ -370,7 +370,9 @@ def run_ours(args) -> None:
     with ClockSampler(local) as clocks:
         ms, launches = timed(step_resident, args.steps, args.warmup)
         ms_e2e_serial, _ = timed(step_e2e, args.steps, max(1, args.warmup))
-        ms_e2e = timed_e2e_pipelined(args.steps, max(1, args.warmup))
+    # outside the sampler: an nvidia-smi query takes ~100 ms and holds up kernel launches while it runs; the
+    # legs above ride through that on their launch backlog, the throttled loader loop (two steps ahead) cannot
+    ms_e2e = timed_e2e_pipelined(args.steps, max(1, args.warmup))
 
     # ---- dominant kernel alone (rank 0's graph)
     dn, de = (HIDDEN, HIDDEN) if args.dims == "wide" else (5, 4)
