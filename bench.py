@@ -109,6 +109,24 @@ class ClockSampler:
         self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
 
     def _run(self):
+        # NVML in-process when the bindings are there (microseconds per query); the nvidia-smi
+        # subprocess (~100 ms per query, and it holds up kernel launches while it runs) otherwise
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = [0x8, 0x40, 0x20, 0x4]  # hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            while not self._stop.is_set():
+                r = int(get_reasons(h))
+                self.samples.append([str(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), str(mx)]
+                                    + ["Active" if r & b else "Not Active" for b in bits])
+                self._stop.wait(0.005)
+            return
+        except Exception:  # noqa: BLE001 - no NVML bindings / no permission: fall back to the CLI
+            pass
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
