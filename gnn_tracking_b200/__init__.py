@@ -26,6 +26,8 @@ _PATCHES = {
                                        "HaughtyFocalLoss": ("metrics.losses.ec", "HaughtyFocalLoss")},
     "gnn_tracking.metrics.losses.oc": {"CondensationLossTiger": ("metrics.losses.oc", "CondensationLossTiger"),
                                        "CondensationLossRG": ("metrics.losses.oc", "CondensationLossRG")},
+    "gnn_tracking.postprocessing.fastrescanner": {"DBSCANFastRescan": ("postprocessing.dbscan", "DBSCANFastRescan")},
+    "gnn_tracking.postprocessing.dbscanscanner": {"DBSCANFastRescan": ("postprocessing.dbscan", "DBSCANFastRescan")},
     "gnn_tracking.metrics.losses.metric_learning": {
         "GraphConstructionHingeEmbeddingLoss": ("metrics.losses.metric_learning", "GraphConstructionHingeEmbeddingLoss")},
 }

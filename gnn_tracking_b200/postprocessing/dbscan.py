@@ -41,13 +41,21 @@ def dbscan(x: Tensor, eps: float = 1.0, min_samples: int = 1) -> Tensor:
 
 class DBSCANFastRescan:
     """Interface of the reference class (fastrescanner.py:6-66): ``cluster(eps, min_pts)`` for many
-    trials over the same points.  ``x`` stays on the device; ``max_eps`` is accepted for
-    compatibility (no neighbour graph is cached: a trial is a few milliseconds)."""
+    trials over the same points.  ``x`` is a CUDA tensor (labels come back as a CUDA int64 tensor) or,
+    as the reference's scanner passes it (dbscanscanner.py:160-165), a numpy array: it is moved to
+    the device once and every trial returns a numpy label array like the reference.  ``max_eps`` and
+    ``n_jobs`` are accepted for compatibility (no neighbour graph is cached: a trial is a few
+    milliseconds)."""
 
-    def __init__(self, x: Tensor, max_eps: float = 1.0, *, n_jobs: int | None = None):
+    def __init__(self, x, max_eps: float = 1.0, *, n_jobs: int | None = None):
+        self._numpy = not isinstance(x, Tensor)
+        if self._numpy:
+            import numpy as np
+            x = torch.from_numpy(np.ascontiguousarray(x)).to("cuda")
         ops.require_cuda(x)
         self.x = x.detach().to(torch.float32).contiguous()
         self._max_eps = max_eps
 
-    def cluster(self, eps: float = 1.0, min_pts: int = 1) -> Tensor:
-        return dbscan(self.x, eps, min_pts)
+    def cluster(self, eps: float = 1.0, min_pts: int = 1):
+        labels = dbscan(self.x, eps, min_pts)
+        return labels.cpu().numpy() if self._numpy else labels

@@ -123,10 +123,16 @@ def test_install_patches_the_reference_package():
     import importlib
     saved = {}
     for ref_mod, attrs in gnn_tracking_b200._PATCHES.items():
-        mod = importlib.import_module(ref_mod)
+        try:
+            mod = importlib.import_module(ref_mod)
+        except ModuleNotFoundError as exc:  # a third-party dependency of that reference module is not installed here
+            assert not exc.name.startswith("gnn_tracking"), exc
+            continue
         saved[ref_mod] = {k: getattr(mod, k) for k in attrs}
     try:
-        done = gnn_tracking_b200.install(strict=True)
+        done = gnn_tracking_b200.install()
+        assert {f"{m}.{k}" for m, attrs in saved.items() for k in attrs} <= set(done)
+        assert "gnn_tracking.postprocessing.fastrescanner.DBSCANFastRescan" in done
         assert "gnn_tracking.models.resin.InteractionNetwork" in done
         import gnn_tracking.models.resin as ref_resin
         import gnn_tracking.models.track_condensation_networks as ref_tcn

@@ -78,10 +78,11 @@ def test_fastrescan_equal_slowrescan():
     from gnn_tracking_b200.postprocessing.dbscan import DBSCANFastRescan
 
     x = np.random.default_rng(0).uniform(size=(100, 2)).astype(np.float32)
-    fr = DBSCANFastRescan(torch.from_numpy(x).cuda(), max_eps=0.15)
+    fr = DBSCANFastRescan(x, max_eps=0.15)  # numpy in, numpy out: the way the reference's scanner calls it
     for eps in [0.1, 0.05]:
         for min_pts in [1, 2]:
-            labels = fr.cluster(eps=eps, min_pts=min_pts).cpu().numpy()
+            labels = fr.cluster(eps=eps, min_pts=min_pts)
+            assert isinstance(labels, np.ndarray)
             labels2 = DBSCAN(eps=eps, min_samples=min_pts).fit_predict(x)
             assert (labels == labels2).all()
 
