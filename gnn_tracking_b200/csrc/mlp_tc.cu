@@ -69,7 +69,7 @@ struct TcParams {
   int64_t n_rows;
   int32_t n_tiles, n_chunks, n_adds, n_layers, ring, ipt, n_teams;
   int8_t items[TC_MAXITEMS + 1];  // per tile, in consumption order: chunk c -> c, add a -> 64 + a, output tile -> -1
-  // row indices of the gather copies travel in registers, fetched one tile ahead by the lanes that
+  // row indices of the gather copies travel in registers, fetched two tiles ahead by the lanes that
   // will use them (no exposed index latency, no shared memory): per item the register slot
   // (TC_IDX_IDENTITY: rows are the tile's own rows, TC_IDX_GLOBAL: irregular width, read on use)
   int8_t item_ireg[TC_MAXITEMS + 1];
@@ -563,8 +563,8 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
   long long prof_t = prof_on ? clock64() : 0;
 
   // ---- row indices: copy-type (per warp slot, see tc_copy_slot_row) and row-type (per row owner;
-  // arrays: 0 = segment ids, 1 / 2 = directly read pre-projected blocks), first tile now, then
-  // always one tile ahead
+  // arrays: 0 = segment ids, 1 / 2 = directly read pre-projected blocks), the first two tiles now, then
+  // always two tiles ahead (see load_idx)
   const int32_t* rarr[3] = {p.seg_id, (p.n_adds > 0 && !p.add[0].staged) ? p.add[0].index : nullptr,
                             (p.n_adds > 1 && !p.add[1].staged) ? p.add[1].index : nullptr};
   int crow[4], orow_slot = -1;
