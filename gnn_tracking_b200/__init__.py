@@ -15,12 +15,14 @@ _PATCHES = {
     "gnn_tracking.models.resin": {"InteractionNetwork": ("models.interaction_network", "InteractionNetwork"),
                                   "ResIN": ("models.resin", "ResIN")},
     "gnn_tracking.models.mlp": {"MLP": ("models.mlp", "MLP"), "ResFCNN": ("models.mlp", "ResFCNN")},
-    "gnn_tracking.models.edge_classifier": {"ECForGraphTCN": ("models.edge_classifier", "ECForGraphTCN")},
+    "gnn_tracking.models.edge_classifier": {"ECForGraphTCN": ("models.edge_classifier", "ECForGraphTCN"),
+                                            "PerfectEdgeClassification": ("models.edge_classifier", "PerfectEdgeClassification")},
     "gnn_tracking.models.track_condensation_networks": {
         "IN": ("models.interaction_network", "InteractionNetwork"),
         "ModularGraphTCN": ("models.track_condensation_networks", "ModularGraphTCN"),
         "GraphTCN": ("models.track_condensation_networks", "GraphTCN"),
-        "PreTrainedECGraphTCN": ("models.track_condensation_networks", "PreTrainedECGraphTCN")},
+        "PreTrainedECGraphTCN": ("models.track_condensation_networks", "PreTrainedECGraphTCN"),
+        "PerfectECGraphTCN": ("models.track_condensation_networks", "PerfectECGraphTCN")},
     "gnn_tracking.metrics.losses.ec": {"EdgeWeightBCELoss": ("metrics.losses.ec", "EdgeWeightBCELoss"),
                                        "EdgeWeightFocalLoss": ("metrics.losses.ec", "EdgeWeightFocalLoss"),
                                        "HaughtyFocalLoss": ("metrics.losses.ec", "HaughtyFocalLoss")},

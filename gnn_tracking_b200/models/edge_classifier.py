@@ -3,6 +3,9 @@ models/edge_classifier.py:15-121): encoders -> ResIN -> W head, each a fused
 kernel over the shared destination-sorted plan."""
 from __future__ import annotations
 
+import math
+
+import torch
 from torch import Tensor, nn
 
 from .. import ops
@@ -67,3 +70,28 @@ class ECForGraphTCN(nn.Module, HyperparametersMixin):
         blocks += [Block(t, plan.perm, unique_index=True) for t in (eas if self.hparams.use_intermediate_edge_embeddings else [ea])]
         w = self.W.forward_blocks(blocks, e, final_act=ACT_SIGMOID_AFFINE, act_eps=0.001, out_index=plan.perm)
         return {"W": w.squeeze(), "node_embedding": h, "edge_embedding": ea}
+
+
+class PerfectEdgeClassification(nn.Module, HyperparametersMixin):
+    def __init__(self, tpr=1.0, tnr=1.0, false_below_pt=0.0):
+        """Truth-based edge "classifier" (reference edge_classifier.py:124-165): ``W`` is ``data.y``
+        with true edges kept at rate ``tpr`` and false edges turned true at rate ``1 - tnr``, then
+        everything with ``data.pt < false_below_pt`` set to false.  A few elementwise draws on the
+        caller's device: no kernel of the path is involved."""
+        super().__init__()
+        self.save_hyperparameters()
+        assert 0.0 <= tpr <= 1.0
+        assert 0.0 <= tnr <= 1.0
+        self.tpr, self.tnr, self.false_below_pt = tpr, tnr, false_below_pt
+
+    def forward(self, data) -> dict[str, Tensor]:
+        r = data.y.bool()
+        if not math.isclose(self.tpr, 1.0):
+            true_mask = r.detach().clone()
+            r[true_mask] = torch.rand(int(true_mask.sum()), device=r.device) <= self.tpr
+        if not math.isclose(self.tnr, 1.0):
+            false_mask = (~r).detach().clone()
+            r[false_mask] = ~(torch.rand(int(false_mask.sum()), device=r.device) <= self.tnr)
+        if self.false_below_pt > 0.0:
+            r[data.pt < self.false_below_pt] = False
+        return {"W": r.float()}  # float like a trained classifier's output (and what BCE expects)

@@ -17,7 +17,7 @@ from .. import ops
 from .._hparams import HyperparametersMixin
 from ..ops import ACT_RELU, ACT_SIGMOID_AFFINE, Block
 from ..plan import build_plan, get_plan
-from .edge_classifier import ECForGraphTCN
+from .edge_classifier import ECForGraphTCN, PerfectEdgeClassification
 from .mlp import MLP, ResFCNN
 from .resin import ResIN
 
@@ -159,6 +159,23 @@ class PreTrainedECGraphTCN(nn.Module, HyperparametersMixin):
         super().__init__()
         self.save_hyperparameters(ignore=["ec"])
         ec = _obj_from_or_to_hparams(self, "ec", ec)
+        hc_in = ResIN(node_dim=h_dim, edge_dim=e_dim, object_hidden_dim=hidden_dim,
+                      relational_hidden_dim=hidden_dim, alpha=alpha_hc, n_layers=L_hc)
+        self._gtcn = ModularGraphTCN(ec=ec, hc_in=hc_in, node_indim=node_indim, edge_indim=edge_indim,
+                                     h_dim=h_dim, e_dim=e_dim, h_outdim=h_outdim, hidden_dim=hidden_dim, **kwargs)
+
+    def forward(self, data) -> dict[str, Tensor | None]:
+        return self._gtcn.forward(data=data)
+
+
+class PerfectECGraphTCN(nn.Module, HyperparametersMixin):
+    def __init__(self, *, node_indim: int, edge_indim: int, h_dim=5, e_dim=4, h_outdim=2, hidden_dim=40, L_hc=3,
+                 alpha_hc: float = 0.5, ec_tpr=1.0, ec_tnr=1.0, **kwargs):
+        """``ModularGraphTCN`` behind a truth-based edge classifier with the given true-positive /
+        true-negative rates (reference :389-456)."""
+        super().__init__()
+        self.save_hyperparameters()
+        ec = PerfectEdgeClassification(tpr=ec_tpr, tnr=ec_tnr)
         hc_in = ResIN(node_dim=h_dim, edge_dim=e_dim, object_hidden_dim=hidden_dim,
                       relational_hidden_dim=hidden_dim, alpha=alpha_hc, n_layers=L_hc)
         self._gtcn = ModularGraphTCN(ec=ec, hc_in=hc_in, node_indim=node_indim, edge_indim=edge_indim,

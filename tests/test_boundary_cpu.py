@@ -168,3 +168,22 @@ def test_loss_wrappers_host_logic():
                               w=torch.full((2,), 9.0))
     assert list(out) == ["0", "1"] and float(out["0"]) == 1.0 and float(out["1"]) == 3.0
     assert seen[0] == ["w_1", "y_1"] and seen[1] == ["w_0", "y_0"]  # the other clone's tensors pass through renamed-free
+
+
+def test_perfect_edge_classification():
+    """The reference's own cases (tests/test_edge_classifier.py:18-39); host logic, runs on any device."""
+    import torch
+
+    from gnn_tracking_b200.models.edge_classifier import PerfectEdgeClassification
+
+    class MockData:
+        def __init__(self, y, pt=None):
+            self.y = torch.Tensor(y)
+            self.pt = torch.Tensor(pt) if pt is not None else torch.full_like(self.y, 0.5)
+
+    y = [True, False, True, False]
+    assert (PerfectEdgeClassification().forward(MockData(y))["W"] == torch.Tensor(y)).all()
+    w = PerfectEdgeClassification(false_below_pt=0.5).forward(MockData(y, pt=[0, 0, 1, 1]))["W"]
+    assert (w == torch.Tensor([False, False, True, False])).all()
+    torch.manual_seed(0)
+    assert 35 < PerfectEdgeClassification(tpr=0.5).forward(MockData(torch.full((100,), True)))["W"].sum() < 65

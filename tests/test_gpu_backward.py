@@ -271,3 +271,56 @@ def test_graph_tcn_trains():
         losses.append(float(loss.detach()))
     assert all(l == l for l in losses), losses
     assert losses[-1] < 0.9 * losses[0], losses
+
+
+_TRAIN_CASES = [
+    ("graphtcn", {}, {}),
+    ("graphtcn", {}, {"mask_orphan_nodes": True}),
+    ("graphtcn", {}, {"mask_orphan_nodes": True, "use_ec_embeddings_for_hc": True}),
+    ("pretrainedec", {}, {}),
+    ("pretrainedec", {"residual_type": "skip2"}, {}),
+    ("pretrainedec", {"residual_type": "skip_top"}, {}),
+    ("pretrainedec", {"use_intermediate_edge_embeddings": False}, {}),
+    ("pretrainedec", {"use_intermediate_edge_embeddings": False, "use_node_embedding": False}, {}),
+    ("pretrainedec", {"use_node_embedding": False}, {}),
+    ("pretrainedec", {}, {"use_ec_embeddings_for_hc": True}),
+    ("perfectec", {}, {}),
+]
+
+
+@pytest.mark.parametrize("kind,ec_params,tc_params", _TRAIN_CASES)
+def test_train_matrix_of_the_reference(kind, ec_params, tc_params):
+    """The model matrix of the reference's tests/test_tcn_training.py:33-150 (tiny widths: hidden_dim = 2,
+    h_dim = 2, two layers) through two optimiser steps with the tiger loss on the CUDA path: finite
+    losses, finite gradients on every parameter the loss reaches, parameters move.  (The heterogeneous
+    node encoder case is outside the path.)"""
+    from gnn_tracking_b200.metrics.losses.oc import CondensationLossTiger
+    from gnn_tracking_b200.models.edge_classifier import ECForGraphTCN
+    from gnn_tracking_b200.models.track_condensation_networks import GraphTCN, PerfectECGraphTCN, PreTrainedECGraphTCN
+    ei, x, ea, pid, pt, eta, reco = _tcn_case(31, n=400, e=5000)
+    torch.manual_seed(11)
+    if kind == "graphtcn":
+        m = GraphTCN(14, 4, h_dim=2, hidden_dim=2, L_ec=2, L_hc=2, ec_threshold=0.3, **tc_params)
+    elif kind == "pretrainedec":
+        ec = ECForGraphTCN(node_indim=14, edge_indim=4, hidden_dim=2, L_ec=2, **ec_params)
+        m = PreTrainedECGraphTCN(ec, node_indim=14, edge_indim=4, hidden_dim=2, L_hc=2, ec_threshold=0.3, **tc_params)
+    else:
+        m = PerfectECGraphTCN(node_indim=14, edge_indim=4, hidden_dim=2, L_hc=2, ec_tpr=0.8, ec_tnr=0.4, **tc_params)
+    m = m.cuda()
+    data = _Data(x=x.cuda(), edge_index=ei.cuda(), edge_attr=ea.cuda(), y=(pid[ei[0]] == pid[ei[1]]).cuda(), pt=pt.cuda())
+    truth = dict(particle_id=pid.cuda(), reconstructable=reco.cuda(), pt=pt.cuda(), eta=eta.cuda())
+    loss_fn = CondensationLossTiger(lw_repulsive=1.0)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    before = {k: p.detach().clone() for k, p in m.named_parameters()}
+    for _ in range(2):
+        opt.zero_grad()
+        out = m(data)
+        loss = loss_fn(beta=out["B"], x=out["H"], ec_hit_mask=out["ec_hit_mask"], **truth).loss
+        assert bool(torch.isfinite(loss)), float(loss)
+        loss.backward()
+        reached = [k for k, p in m.named_parameters() if p.grad is not None]
+        assert reached, "no parameter received a gradient"
+        for k, p in m.named_parameters():
+            assert p.grad is None or bool(torch.isfinite(p.grad).all()), k
+        opt.step()
+    assert any(not torch.equal(before[k], p.detach()) for k, p in m.named_parameters())
