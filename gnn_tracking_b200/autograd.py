@@ -19,7 +19,7 @@ import torch
 from torch import Tensor
 
 from . import ops
-from .ops import ACT_NONE, ACT_RELU, ACT_SIGMOID_AFFINE, Block
+from .ops import ACT_RELU, ACT_SIGMOID_AFFINE, Block
 
 
 class _BwdPacks:

@@ -6,7 +6,6 @@ e_tilde)`` in the caller's edge order -- computed by two fused kernels over a
 destination-sorted plan instead of PyG's gather / cat / addmm / scatter_add chain."""
 from __future__ import annotations
 
-import torch
 from torch import Tensor, nn
 
 from .. import ops
