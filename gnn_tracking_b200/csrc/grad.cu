@@ -30,7 +30,7 @@ __device__ __forceinline__ atb_f32x2 atb_fma2(atb_f32x2 a, atb_f32x2 b, atb_f32x
 // group owns the 8 x 4 block out[8 ki .., 4 nj ..] as packed pairs: per row 3 x LDS.128 and
 // 16 x FFMA2 (a_i broadcast against the pairs (b0, b1), (b2, b3); ptxas folds the broadcast into the
 // instruction's scalar operand), i.e. 19 issue slots for 32 multiply-adds.
-__global__ void __launch_bounds__(ATB_THREADS) rows_atb_kernel(const float* __restrict__ A, int a_ld,
+__global__ void __launch_bounds__(ATB_THREADS, 3) rows_atb_kernel(const float* __restrict__ A, int a_ld,
                                                                const int32_t* __restrict__ a_index, int a_relu, int ka,
                                                                const float* __restrict__ B, int b_ld, int nb,
                                                                int64_t n_rows, float* __restrict__ out, int out_ld,
@@ -125,8 +125,8 @@ int rows_atb(const float* A, int a_ld, const int32_t* a_index, int a_relu, int k
   if (n_rows == 0) return GTB_OK;
   const int64_t n_tiles = (n_rows + ATB_ROWS - 1) / ATB_ROWS;
   // every CTA ends with 64 x 64 atomics onto the same addresses: at least 16 tiles per CTA, and no
-  // more CTAs than are resident at once (2 per SM at 122 registers)
-  const int grid = (int)imin64((n_tiles + 15) / 16, (int64_t)kNumSMs * 2);
+  // more CTAs than are resident at once (3 per SM: __launch_bounds__(256, 3) -> 79 registers, no spills)
+  const int grid = (int)imin64((n_tiles + 15) / 16, (int64_t)kNumSMs * 3);
   rows_atb_kernel<<<grid, ATB_THREADS, 0, st>>>(A, a_ld, a_index, a_relu, ka, B, b_ld, nb, n_rows, out, out_ld, colsum);
   GTB_CHECK_LAUNCH("rows_atb_kernel");
   return GTB_OK;
