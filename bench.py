@@ -213,7 +213,7 @@ def run_reference(args) -> None:
         "e2e": {"value": val, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # -------------------------------------------------------------------------- ours
@@ -422,9 +422,8 @@ def run_ours(args) -> None:
         traffic = json.loads(tf.read_text()).get(f"{args.dims}_{k_impl}")
 
     value = n_total_edges * args.steps / (ms * 1e-3)
-    # two end-to-end loops are timed (serial copy -> compute -> read back, and the prefetching loader);
-    # the overlap of the loader's copies with compute varies from run to run on these boxes
-    # (2.2 .. 3.5 ms/step measured), so the line carries both and `value` is the faster of the two
+    # two end-to-end loops are timed (serial copy -> compute -> read back, and the prefetching loader at
+    # N = 1); the line carries both and `value` is the faster of the two
     e2e_serial_val = n_total_edges * args.steps / (ms_e2e_serial * 1e-3)
     e2e_pipelined_val = n_total_edges * args.steps / (ms_e2e * 1e-3) if ms_e2e is not None else None
     e2e_val = max(e2e_pipelined_val or 0.0, e2e_serial_val)
@@ -461,12 +460,31 @@ def run_ours(args) -> None:
         line["cpu_baseline"] = {"value": e / t_cpu, "unit": "edges/s", "cores": threads, "kind": "port",
                                 "sample": "same full graph, 1 warm-up + 3 forwards, median",
                                 "ms_per_step": t_cpu * 1e3}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def emit(line: dict) -> None:
+    """The ONE line of stdout (libraries' banners, e.g. NCCL's version line, went to stderr)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main() -> None:
+    global _RESULT_FD
+    # keep file descriptor 1 for the result line only: native libraries that print to stdout (NCCL with
+    # NCCL_DEBUG=VERSION prints "NCCL version ...") are pointed at stderr
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

@@ -156,6 +156,18 @@ def read_graph(path, device: torch.device | str = "cuda", *, pinned: bool | None
     return _materialize(meta, host, device)
 
 
+_SIDE_STREAMS: dict = {}
+
+
+def _side_stream(device: torch.device) -> "torch.cuda.Stream":
+    """One copy stream per device for every prefetcher: the caching allocator keeps a block pool per
+    stream, so a fresh stream per loop would start every epoch with cudaMalloc calls."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device)
+    return _SIDE_STREAMS[key]
+
+
 class DevicePrefetcher:
     """Yields device-resident graphs from an iterable of host-side ones, with the host-to-device
     copy of graph k + 1 issued on a side stream BEFORE graph k is handed to the caller, so the copy
@@ -184,7 +196,7 @@ class DevicePrefetcher:
             for item in self.source:
                 yield item if isinstance(item, GraphData) else _materialize(item[0], item[1], self.device)
             return
-        stream = torch.cuda.Stream(self.device)
+        stream = _side_stream(self.device)
         it = iter(self.source)
         inflight: deque = deque()
 
