@@ -159,9 +159,9 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------- CPU legs
-def cpu_forward_time(g: dict, dims: str, reps: int, warm: int) -> tuple[float, int]:
+def cpu_forward_time(g: dict, dims: str, reps: int, warm: int) -> tuple[float, int, dict]:
     """The CPU restatement of the reference forward (oracle/in_oracle.py, pinned to the
-    reference's own classes) on all host threads; returns (median seconds, threads)."""
+    reference's own classes) on all host threads; returns (median seconds, threads, outputs)."""
     from oracle import in_oracle as O
     from gnn_tracking_b200.models.edge_classifier import ECForGraphTCN
     threads = os.cpu_count() or 1
@@ -172,19 +172,36 @@ def cpu_forward_time(g: dict, dims: str, reps: int, warm: int) -> tuple[float, i
     with torch.no_grad():
         for i in range(warm + reps):
             t0 = time.perf_counter()
-            O.ec_forward(g["x"], g["edge_index"], g["edge_attr"], sd)
+            ref = O.ec_forward(g["x"], g["edge_index"], g["edge_attr"], sd)
             if i >= warm:
                 ts.append(time.perf_counter() - t0)
-    return statistics.median(ts), threads
+    return statistics.median(ts), threads, ref
+
+
+def parity_report(out: dict, ref: dict, what: str, tol: float = 1e-5) -> dict:
+    """max |GPU - oracle| per output of the edge classifier (edge_classifier.py:89-121) at
+    tol * max(1, max|oracle|); a mismatch fails the run: a fast kernel with different results is not done."""
+    rep = {}
+    for k in ("W", "node_embedding", "edge_embedding"):
+        r = ref[k].float()
+        o = out[k].detach().float().cpu().reshape(r.shape)
+        err = float((o - r).abs().max()) if r.numel() else 0.0
+        scale = max(1.0, float(r.abs().max())) if r.numel() else 1.0
+        rep[k] = err / scale
+        if not err <= tol * scale:
+            raise SystemExit(f"PARITY FAILURE ({what}): {k} max|err| {err:.3e} > {tol:g} * {scale:.3g}")
+    return rep
 
 
 def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # the same full graph as the GPU arm (about 1 s per forward on 16 host threads: 25 steps stay well
+    # inside "a few minutes"); only an explicitly long run is cut down
     n, e = N_NODES, N_EDGES
-    sample = "full graph per step"
-    if args.steps + args.warmup > 16:  # keep the whole run within a few minutes
+    sample = "same full graph per step"
+    if args.steps + args.warmup > 120:
         n, e = N_NODES // 4, N_EDGES // 4
         sample = "quarter-size graph (25k nodes / 250k edges) per step"
     g = make_graph(n, e)
@@ -300,6 +317,7 @@ def run_ours(args) -> None:
         halo = HaloExchange(shard.to(dev))
         n_total_edges = gg["n_edges"]
         halo_frac = shard.n_halo / max(1, shard.n_owned)
+        gg_full = gg if rank == 0 else None  # rank 0 checks its shard against the single-GPU forward below
         del gg
     else:
         # independent graphs: every rank owns one full graph per step (as the reference trains with
@@ -332,6 +350,23 @@ def run_ours(args) -> None:
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    multi_parity = None
+    if partitioned:
+        # multi-GPU parity inside the driver-run command: the partitioned forward of rank 0's shard against
+        # the single-GPU forward of the WHOLE graph on rank 0 (same kernels, no halo), 1e-5 * scale
+        out_p = step_resident()
+        barrier()
+        if rank == 0:
+            with torch.no_grad():
+                full = model.forward_tensors(gg_full["x"].to(dev), gg_full["edge_index"].to(dev), gg_full["edge_attr"].to(dev))
+            ids = shard.edge_ids.to(dev)
+            ref = {"W": full["W"][ids].cpu(), "edge_embedding": full["edge_embedding"][ids].cpu(),
+                   "node_embedding": full["node_embedding"][shard.node_lo:shard.node_hi].cpu()}
+            multi_parity = parity_report(out_p, ref, f"partitioned x{world} vs single GPU")
+            del full, ref, gg_full
+            torch.cuda.empty_cache()
+        barrier()
 
     def timed_e2e_pipelined(steps, warmup):
         """The loop a user of the loader writes: ``for data in DevicePrefetcher(host graphs): model(data)``.
@@ -455,11 +490,17 @@ def run_ours(args) -> None:
                      "algorithmic_bytes_per_launch": alg, "kernel_ms": k_ms, "peak_source": peak_src},
         "clocks": clocks.summary(),
     }
+    if multi_parity is not None:
+        line["parity"] = {"vs": "single-GPU forward of the whole graph on rank 0 (rank 0's shard)", "tol": 1e-5,
+                          "max_err_over_scale": multi_parity}
     if world == 1 and not args.no_cpu:
-        t_cpu, threads = cpu_forward_time(g, args.dims, reps=3, warm=1)
+        t_cpu, threads, ref = cpu_forward_time(g, args.dims, reps=3, warm=1)
         line["cpu_baseline"] = {"value": e / t_cpu, "unit": "edges/s", "cores": threads, "kind": "port",
                                 "sample": "same full graph, 1 warm-up + 3 forwards, median",
                                 "ms_per_step": t_cpu * 1e3}
+        # full-size parity: the GPU forward of the bench graph against the oracle's, same weights
+        line["parity"] = {"vs": "oracle/in_oracle.py on the same full graph and weights", "tol": 1e-5,
+                          "max_err_over_scale": parity_report(step_resident(), ref, "full-size bench graph")}
     emit(line)
     if world > 1:
         dist.destroy_process_group()

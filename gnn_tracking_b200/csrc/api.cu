@@ -28,6 +28,9 @@ int fused_mlp_ffma(const gtb_mlp_desc_t&, cudaStream_t);
 size_t tc_packed_bytes(int, const int32_t*, int, const int32_t*);
 int pack_tc(int, const int32_t*, int, const int32_t*, const float* const*, const float* const*, void*, cudaStream_t);
 int fused_mlp_tc(const gtb_mlp_desc_t&, cudaStream_t);
+int in_edge_ws(const gtb_mlp_desc_t&, cudaStream_t, bool*);
+int ew_fault_flag(int*);
+int ew_profile(int, long long*);
 int tc_timeout_flag(int*);
 int oc_potentials_grad(const float*, const float*, int32_t, const int64_t*, const int32_t*, int64_t, const int32_t*, int32_t,
                        float, int64_t, const float*, float*, float*, float*, cudaStream_t);
@@ -98,8 +101,21 @@ extern "C" {
 int gtb_version(void) { return 100; }
 const char* gtb_last_error(void) { return g_err; }
 
-int gtb_debug_tc_timeout(int* flag) { return tc_timeout_flag(flag); }
-int gtb_debug_tc_profile(int enable, long long* out32) { return tc_profile(enable, out32); }
+int gtb_debug_tc_timeout(int* flag) {
+  int a = 0, b = 0;
+  int rc = tc_timeout_flag(&a);
+  if (rc == GTB_OK) rc = ew_fault_flag(&b);
+  *flag = a ? a : (b ? 16 + b : 0);
+  return rc;
+}
+int gtb_debug_tc_profile(int enable, long long* out32) {
+  // bit 0: the generic tcgen05 tiles, bit 1: the warp-specialised edge kernel (reads: enable == 2 selects it)
+  if (out32 == nullptr) {
+    const int rc = tc_profile(enable & 1, nullptr);
+    return rc != GTB_OK ? rc : ew_profile((enable >> 1) & 1, nullptr);
+  }
+  return enable == 2 ? ew_profile(0, out32) : tc_profile(enable, out32);
+}
 
 int gtb_arch_ok(int device) {
   cudaDeviceProp p;
@@ -160,7 +176,13 @@ int gtb_fused_mlp_f32(const gtb_mlp_desc_t* desc, void* stream) {
   if (rc) return rc;
   GTB_REQUIRE(desc->impl == GTB_IMPL_FFMA || desc->impl == GTB_IMPL_TCGEN05, GTB_ERR_BAD_ARG,
               "gtb_fused_mlp_f32: impl must name the layout the weights were packed for");
-  if (desc->impl == GTB_IMPL_TCGEN05) return fused_mlp_tc(*desc, static_cast<cudaStream_t>(stream));
+  if (desc->impl == GTB_IMPL_TCGEN05) {
+    // the wide Interaction-Network edge shape has its own warp-specialised kernel (edge_ws.cu)
+    bool handled = false;
+    const int rc = in_edge_ws(*desc, static_cast<cudaStream_t>(stream), &handled);
+    if (rc != GTB_OK || handled) return rc;
+    return fused_mlp_tc(*desc, static_cast<cudaStream_t>(stream));
+  }
   return fused_mlp_ffma(*desc, static_cast<cudaStream_t>(stream));
 }
 

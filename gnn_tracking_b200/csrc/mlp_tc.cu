@@ -253,39 +253,6 @@ constexpr int TC_TEAM = 256;
 __device__ __forceinline__ void team_sync(int team) {
   asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(TC_TEAM) : "memory");
 }
-__device__ __forceinline__ float4 lds128(uint32_t a) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
-  return v;
-}
-__device__ __forceinline__ void sts128(uint32_t a, const float4& v) {
-  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-__device__ __forceinline__ float lds32(uint32_t a) {
-  float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
-  return v;
-}
-__device__ __forceinline__ void sts32(uint32_t a, float v) {
-  asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
-}
-__device__ __forceinline__ int32_t lds_i32(uint32_t a) {
-  int32_t v;
-  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
-  return v;
-}
-__device__ __forceinline__ void sts_i32(uint32_t a, int32_t v) {
-  asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
-}
-// row `row` of a table with a row pitch of ld4 BYTES: one 32 x 32 -> 64-bit multiply-add
-__device__ __forceinline__ const float* row_ptr(const float* base, uint32_t row, uint32_t ld4) {
-  return reinterpret_cast<const float*>(reinterpret_cast<const char*>(base) + (uint64_t)row * ld4);
-}
-
-__device__ __forceinline__ void red_add_v4(const float* gaddr, const float4& v) {  // 16-byte aligned
-  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(gaddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-
 __device__ __forceinline__ uint32_t slot_off(int r, int c4) {  // 16-byte chunk c4 of row r
   return (uint32_t)(r * 256 + ((c4 ^ (r & 7)) << 4));
 }
@@ -394,19 +361,6 @@ __device__ __forceinline__ void tc_issue_item(const TcParams& p, int tile, int k
 // `if (tid == 0)` compiles to an ELECT / 6 x R2UR / UTCHMMA / BRA.U.ANY waterfall loop per MMA
 // (~150 cycles each, measured: profiles/r1_tc_mma_bench.log), 5x the 32 cycles the tensor core
 // needs for M = 128, N = 64, K = 8.  The TMEM base is 0 (checked at kernel start).
-__device__ __forceinline__ bool elect_one() {
-  uint32_t leader;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(leader));
-  return leader != 0;
-}
-__device__ __forceinline__ void mma_commit_addr(uint32_t bar_smem) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_smem) : "memory");
-}
-
 // three passes (small terms first: lo*hi, hi*lo, hi*hi) over `ksteps` K = 8 steps of one streamed
 // block (first Linear) or of a whole hidden Linear, then the commit onto the team's barrier
 template <int TEAM>
@@ -478,54 +432,6 @@ __device__ __forceinline__ void tc_issue_mmas_k64(uint32_t wbase, uint32_t bar_b
     }
   }
   __syncwarp();
-}
-
-__device__ __forceinline__ void split_store8(uint32_t taddr_hi, uint32_t taddr_lo, const float (&v)[8]) {
-  uint32_t hi[8], lo[8];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    f32x2 h, l;
-    split_tf32_act2(pack2(v[2 * j], v[2 * j + 1]), h, l);
-    float a, b;
-    unpack2(h, a, b);
-    hi[2 * j] = __float_as_uint(a);
-    hi[2 * j + 1] = __float_as_uint(b);
-    unpack2(l, a, b);
-    lo[2 * j] = __float_as_uint(a);
-    lo[2 * j + 1] = __float_as_uint(b);
-  }
-  tmem_st8(taddr_hi, hi);
-  tmem_st8(taddr_lo, lo);
-}
-
-__device__ __forceinline__ void split_store16(uint32_t taddr_hi, uint32_t taddr_lo, const float (&v)[16]) {
-  uint32_t hi[16], lo[16];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    f32x2 h, l;
-    split_tf32_act2(pack2(v[2 * j], v[2 * j + 1]), h, l);
-    float a, b;
-    unpack2(h, a, b);
-    hi[2 * j] = __float_as_uint(a);
-    hi[2 * j + 1] = __float_as_uint(b);
-    unpack2(l, a, b);
-    lo[2 * j] = __float_as_uint(a);
-    lo[2 * j + 1] = __float_as_uint(b);
-  }
-  tmem_st16(taddr_hi, hi);
-  tmem_st16(taddr_lo, lo);
-}
-
-// v[j] += x[j] on 16 values as 8 packed adds
-__device__ __forceinline__ void add16(float (&v)[16], const float4& x0, const float4& x1, const float4& x2, const float4& x3) {
-  const float4 xs[4] = {x0, x1, x2, x3};
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const f32x2 a = add2(pack2(v[4 * q], v[4 * q + 1]), pack2(xs[q].x, xs[q].y));
-    const f32x2 b = add2(pack2(v[4 * q + 2], v[4 * q + 3]), pack2(xs[q].z, xs[q].w));
-    unpack2(a, v[4 * q], v[4 * q + 1]);
-    unpack2(b, v[4 * q + 2], v[4 * q + 3]);
-  }
 }
 
 #define TC_PROF(id)                                   \

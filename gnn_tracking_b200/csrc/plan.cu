@@ -14,7 +14,9 @@ __global__ void plan_keys_kernel(const int64_t* __restrict__ edge_index, int64_t
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += stride) {
     const int64_t s = edge_index[e], t = edge_index[n_edges + e];
     if (s < 0 || s >= n_nodes || t < 0 || t >= n_nodes) atomicExch(status, 1);
-    keys[e] = (int32_t)t;
+    // out-of-range ids are reported through `status` and clamped: every kernel that walks the plan
+    // stays inside its tables (the host raises the reference's IndexError, plan.py)
+    keys[e] = (int32_t)max((int64_t)0, min(t, n_nodes - 1));
     vals[e] = (int32_t)e;
   }
 }
@@ -30,7 +32,7 @@ __global__ void plan_rowptr_kernel(const int32_t* __restrict__ dst_sorted, const
     const int64_t cur = (i == n_edges) ? n_nodes : min((int64_t)dst_sorted[i], n_nodes);
     for (int64_t n = max(prev, (int64_t)-1) + 1; n <= cur; ++n)
       if (n >= 0 && n <= n_nodes) rowptr[n] = (int32_t)i;
-    if (i < n_edges && src_sorted) src_sorted[i] = (int32_t)edge_index[perm[i]];
+    if (i < n_edges && src_sorted) src_sorted[i] = (int32_t)max((int64_t)0, min(edge_index[perm[i]], n_nodes - 1));
   }
 }
 

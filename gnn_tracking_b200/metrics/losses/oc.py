@@ -89,13 +89,18 @@ def condensation_loss_tiger(*, beta: Tensor, x: Tensor, object_id: Tensor, objec
 
 def condensation_loss_rg(*, beta: Tensor, x: Tensor, particle_id: Tensor, mask: Tensor, q_min: float,
                          radius_threshold: float = 1.0, max_num_neighbors: int = 256):
-    """``_radius_graph_condensation_loss`` (oc.py:87-161).  Condensation points, attraction and the
-    coward term are those of the tiger kernels (the most-charged hit of every particle of interest;
-    the reference's argsort-by-beta + first occurrence picks the same hit); the repulsion runs over
-    the radius-graph edges that start at a condensation point (``gtb_radius_pair_sum_f32`` mode 1:
-    ``sqrt(1e-9 + d^2)``, neighbour cap), the noise term over ``particle_id == 0`` exactly."""
+    """``_radius_graph_condensation_loss`` (oc.py:87-161).  The reference picks its condensation points
+    among the MASKED hits only (argsort of ``beta[mask]`` + first occurrence per particle, oc.py:33-43),
+    attracts the masked non-CP hits only (oc.py:75-84) and normalises with ``mask.sum()`` -- unlike the
+    tiger loss, whose objects own every hit carrying their id.  The tiger kernels give exactly that when
+    the hits outside the mask are taken out of their particle (object id -1: never an object of interest,
+    masked hits have ids > 0).  The repulsion runs over the radius-graph edges that start at a
+    condensation point (``gtb_radius_pair_sum_f32`` mode 1: ``sqrt(1e-9 + d^2)``, neighbour cap, the
+    ORIGINAL particle ids decide which pairs repel), the noise term over ``particle_id == 0`` exactly."""
     from .metric_learning import radius_pair_sum
-    tiger, extra = condensation_loss_tiger(beta=beta, x=x, object_id=particle_id, object_mask=mask, q_min=q_min)
+    mask = mask.to(torch.bool)
+    masked_id = torch.where(mask, particle_id, torch.full_like(particle_id, -1))
+    tiger, extra = condensation_loss_tiger(beta=beta, x=x, object_id=masked_id, object_mask=mask, q_min=q_min)
     n = x.size(0)
     k = extra["alphas"].numel()
     is_cp = torch.zeros(n, dtype=torch.bool, device=x.device)

@@ -14,7 +14,7 @@ from ..ops import ACT_RELU, ACT_SIGMOID_AFFINE, Block
 from ..plan import GraphPlan, get_plan
 from ..utils.asserts import assert_feat_dim
 from .mlp import MLP
-from .resin import ResIN
+from .resin import ResIN, has_sorted_edges
 
 
 class ECForGraphTCN(nn.Module, HyperparametersMixin):
@@ -59,15 +59,21 @@ class ECForGraphTCN(nn.Module, HyperparametersMixin):
         n, e = x.size(0), edge_attr.size(0)
         # encoders + the ReLU behind them (edge_classifier.py:102-103)
         h = self.ec_node_encoder.forward_blocks([Block(x)], n, final_act=ACT_RELU)
-        ea = self.ec_edge_encoder.forward_blocks([Block(edge_attr)], e, final_act=ACT_RELU)
-        h, ea, eas = self.ec_resin.forward_planned(h, plan, ea, halo=halo)
+        # The edge features live in the plan's destination-sorted order inside the model (the encoder
+        # gathers its 4 input columns through ``perm``): every layer then streams contiguous tiles.  Only
+        # the final embedding -- the one the caller sees -- is written back in the caller's order.
+        sorted_edges = len(self.ec_resin.network.layers) > 0
+        ea = self.ec_edge_encoder.forward_blocks(
+            [Block(edge_attr, plan.perm, unique_index=True) if sorted_edges else Block(edge_attr)], e, final_act=ACT_RELU)
+        h, ea, eas = self.ec_resin.forward_planned(h, plan, ea, halo=halo, sorted_edges=sorted_edges)
         # W head over cat[h[src], h[dst], e_0 .. e_L] (edge_classifier.py:108-117), walked in
         # dst-sorted order (h[dst] rows repeat) and written back in the caller's edge order
         blocks = []
         if self.hparams.use_node_embedding:
             blocks += [Block(h, plan.src_sorted, extend=None if halo is None else halo.extend),
                        Block(h, plan.dst_sorted, sorted_index=True)]
-        blocks += [Block(t, plan.perm, unique_index=True) for t in (eas if self.hparams.use_intermediate_edge_embeddings else [ea])]
+        blocks += [Block(t, None) if has_sorted_edges(t) else Block(t, plan.perm, unique_index=True)
+                   for t in (eas if self.hparams.use_intermediate_edge_embeddings else [ea])]
         w = self.W.forward_blocks(blocks, e, final_act=ACT_SIGMOID_AFFINE, act_eps=0.001, out_index=plan.perm)
         return {"W": w.squeeze(), "node_embedding": h, "edge_embedding": ea}
 

@@ -34,12 +34,17 @@ class InteractionNetwork(nn.Module, HyperparametersMixin):
 
     def forward_planned(self, x: Tensor, plan: GraphPlan, edge_attr: Tensor, *, relu_x: bool = False,
                         relu_e: bool = False, res: Tensor | None = None, res_a: float = 0.0,
-                        res_b: float = 1.0, halo=None) -> tuple[Tensor, Tensor]:
+                        res_b: float = 1.0, halo=None, e_sorted: bool = False,
+                        out_sorted: bool = False) -> tuple[Tensor, Tensor]:
         """One layer on a planned graph.  ``relu_*`` apply the activation on load (layers
         > 0 of a residual stack see relu(x), reference models/resin.py:104-105); ``res``
         fuses ``sqconvex_combination`` (resin.py:17-42) into the node kernel.  ``halo`` (a
         ``partition.HaloExchange``): ``x`` holds the owned nodes of a node-partitioned graph and
-        ``plan`` its local edges; the source rows other ranks own are exchanged once per layer."""
+        ``plan`` its local edges; the source rows other ranks own are exchanged once per layer.
+        ``e_sorted`` / ``out_sorted``: ``edge_attr`` is given / ``e_tilde`` is returned in the plan's
+        destination-sorted edge order instead of the caller's (row i = edge ``plan.perm[i]``): inside a
+        stack the edge features then stream as contiguous tiles, no gather or scatter through ``perm``
+        (the module-level ``forward`` never exposes that order)."""
         dev = ops.require_cuda(x, edge_attr)
         n, e = x.size(0), edge_attr.size(0)
         e_out = self.hparams.edge_outdim
@@ -49,8 +54,8 @@ class InteractionNetwork(nn.Module, HyperparametersMixin):
         # aggregate starts from zero: isolated nodes keep 0 (SumAggregation)
         e_tilde, aggr = self.relational_model.forward_blocks(
             [Block(x, plan.dst_sorted, relu_x, sorted_index=True), Block(x, plan.src_sorted, relu_x, extend=ext),
-             Block(edge_attr, plan.perm, relu_e, unique_index=True)],
-            e, out_index=plan.perm, aggr_rows=n, seg_id=plan.dst_sorted, rowptr=plan.rowptr)
+             Block(edge_attr, None, relu_e) if e_sorted else Block(edge_attr, plan.perm, relu_e, unique_index=True)],
+            e, out_index=None if out_sorted else plan.perm, aggr_rows=n, seg_id=plan.dst_sorted, rowptr=plan.rowptr)
         # update(): cat[x, aggr]  (interaction_network.py:92-103)
         x_tilde = self.object_model.forward_blocks([Block(x, None, relu_x), Block(aggr)], n,
                                                    res=res, res_a=res_a, res_b=res_b)

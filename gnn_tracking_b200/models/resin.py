@@ -23,6 +23,18 @@ def _res_coeffs(alpha: float) -> tuple[float, float] | None:
     return math.sqrt(alpha), math.sqrt(1.0 - alpha)
 
 
+def mark_sorted_edges(t: Tensor) -> Tensor:
+    """Tags an edge tensor whose rows follow the plan's destination-sorted edge order (row i = edge
+    ``plan.perm[i]``).  A plain attribute on the tensor object: it does not survive any torch op, so
+    only the very tensors produced inside ``forward_planned(sorted_edges=True)`` carry it."""
+    t._gtb_sorted_edges = True
+    return t
+
+
+def has_sorted_edges(t: Tensor) -> bool:
+    return getattr(t, "_gtb_sorted_edges", False)
+
+
 class ResidualNetwork(ABC, nn.Module):
     def __init__(self, layers: list[nn.Module], *, alpha: float = 0.5, collect_hidden_edge_embeds: bool = False):
         super().__init__()
@@ -33,21 +45,40 @@ class ResidualNetwork(ABC, nn.Module):
     def forward(self, x: Tensor, edge_index: Tensor, edge_attr: Tensor) -> tuple[Tensor, Tensor, list[Tensor] | None]:
         return self._forward(x, get_plan(edge_index, x.size(0)), edge_attr)
 
-    def forward_planned(self, x: Tensor, plan: GraphPlan, edge_attr: Tensor, halo=None):
+    def forward_planned(self, x: Tensor, plan: GraphPlan, edge_attr: Tensor, halo=None, sorted_edges: bool = False):
+        """``sorted_edges``: ``edge_attr`` is given in the plan's destination-sorted edge order and every
+        edge tensor of the stack EXCEPT the final one stays in that order (contiguous tiles instead of a
+        gather / scatter through ``perm`` per layer).  The final ``edge_attr`` is in the caller's order
+        as always; the entries of the returned ``edge_attrs`` list answer ``has_sorted_edges`` where
+        they are in sorted order."""
         self._halo = halo
+        self._sorted = sorted_edges and len(self.layers) > 0
+        self._calls_left = self._n_layer_calls()
         try:
+            if self._sorted:
+                edge_attr = mark_sorted_edges(edge_attr)
             return self._forward(x, plan, edge_attr)
         finally:
             self._halo = None
+            self._sorted = False
 
     _halo = None
+    _sorted = False
+    _calls_left = 0
+
+    def _n_layer_calls(self) -> int:
+        return len(self.layers)
 
     def _layer(self, i: int, x: Tensor, plan: GraphPlan, e: Tensor, *, first: bool, residue: Tensor | None):
         """IN layer i on (act(x), act(e)) with the residual onto the un-activated
         ``residue`` fused in; act = identity for the very first layer, else ReLU."""
         co = _res_coeffs(self._alpha) if residue is not None else None
         kw = {} if co is None else dict(res=residue, res_a=co[0], res_b=co[1])
-        return self.layers[i].forward_planned(x, plan, e, relu_x=not first, relu_e=not first, halo=self._halo, **kw)
+        self._calls_left -= 1
+        out_sorted = self._sorted and self._calls_left > 0  # the stack's final edge tensor: caller's order
+        xo, eo = self.layers[i].forward_planned(x, plan, e, relu_x=not first, relu_e=not first, halo=self._halo,
+                                                e_sorted=has_sorted_edges(e), out_sorted=out_sorted, **kw)
+        return xo, (mark_sorted_edges(eo) if out_sorted else eo)
 
     @abstractmethod
     def _forward(self, x: Tensor, plan: GraphPlan, edge_attr: Tensor):
@@ -80,6 +111,9 @@ class Skip2ResidualNetwork(ResidualNetwork):
         # parameter-free placeholders keep the reference's module tree
         self._node_batch_norms = nn.ModuleList([nn.Identity() for _ in layers])
         self._edge_batch_norms = nn.ModuleList([nn.Identity() for _ in layers])
+
+    def _n_layer_calls(self) -> int:
+        return 2 * max(len(self.layers) - 1, 0)
 
     def _forward(self, x, plan, edge_attr):
         edge_attrs = [edge_attr] if self._collect_hidden_edge_embeds else None
@@ -148,5 +182,5 @@ class ResIN(nn.Module, HyperparametersMixin):
     def forward(self, x: Tensor, edge_index: Tensor, edge_attr: Tensor):
         return self.network.forward(x, edge_index, edge_attr)
 
-    def forward_planned(self, x: Tensor, plan: GraphPlan, edge_attr: Tensor, halo=None):
-        return self.network.forward_planned(x, plan, edge_attr, halo=halo)
+    def forward_planned(self, x: Tensor, plan: GraphPlan, edge_attr: Tensor, halo=None, sorted_edges: bool = False):
+        return self.network.forward_planned(x, plan, edge_attr, halo=halo, sorted_edges=sorted_edges)

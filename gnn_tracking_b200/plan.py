@@ -26,7 +26,8 @@ class GraphPlan:
 
     def validate(self) -> None:
         """Host-synchronising range check (the reference would raise an
-        IndexError inside index_select)."""
+        IndexError inside index_select).  Without it the check is deferred: see ``_poll_status``."""
+        _forget_status(self.status)  # settled here: the deferred check must not raise it a second time
         if int(self.status.item()) != 0:
             raise IndexError("edge_index contains node indices outside [0, num_nodes)")
 
@@ -79,29 +80,45 @@ def build_plan(edge_index: Tensor, n_nodes: int) -> GraphPlan:
     check(lib().gtb_plan_build(ei.data_ptr(), n_nodes, e, perm.data_ptr(), rowptr.data_ptr(), src.data_ptr(),
                                dst.data_ptr(), status.data_ptr(), ws.data_ptr(), ws_bytes, ops.stream_ptr(dev)))
     ops._count(6)  # keys, radix-sort passes, rowptr
+    _defer_status_check(status)
     return GraphPlan(n_nodes, e, perm, rowptr, src, dst, status)
 
 
 # One plan per live edge_index tensor: all layers of a stack (and repeated forwards over the
-# same graph object) share it.  Keyed on identity + version so in-place edits invalidate it.
-_CACHE: dict[int, tuple[weakref.ref, int, int, GraphPlan]] = {}
+# same graph object) share it.  Keyed on identity + version so in-place edits invalidate it; the
+# entry dies with the tensor (weakref callback), so a long epoch through ``GraphLoader`` does not
+# keep stale graphs resident through their plans.
+_CACHE: dict[int, tuple[weakref.ref, int | None, int, GraphPlan]] = {}
+
+
+def _version(edge_index: Tensor) -> int | None:
+    """Inference tensors (``torch.inference_mode()``: Lightning's validation / test / predict
+    loops) do not track a version counter and cannot be mutated in place outside inference mode:
+    identity + shape is enough for them."""
+    return None if edge_index.is_inference() else edge_index._version
+
+
+def _remember(edge_index: Tensor, n_nodes: int, plan: GraphPlan) -> None:
+    key = id(edge_index)
+
+    def _drop(ref, key=key):
+        hit = _CACHE.get(key)
+        if hit is not None and hit[0] is ref:
+            del _CACHE[key]
+
+    _CACHE[key] = (weakref.ref(edge_index, _drop), _version(edge_index), n_nodes, plan)
 
 
 def get_plan(edge_index: Tensor, n_nodes: int) -> GraphPlan:
-    key = id(edge_index)
-    hit = _CACHE.get(key)
+    _poll_status()
+    hit = _CACHE.get(id(edge_index))
     if hit is not None:
         ref, version, n, plan = hit
-        if ref() is edge_index and version == edge_index._version and n == n_nodes \
+        if ref() is edge_index and version == _version(edge_index) and n == n_nodes \
                 and plan.n_edges == edge_index.size(1):
             return plan
     plan = build_plan(edge_index, n_nodes)
-    if len(_CACHE) > 64:
-        for k in [k for k, v in _CACHE.items() if v[0]() is None]:
-            del _CACHE[k]
-        if len(_CACHE) > 64:
-            _CACHE.clear()
-    _CACHE[key] = (weakref.ref(edge_index), edge_index._version, n_nodes, plan)
+    _remember(edge_index, n_nodes, plan)
     return plan
 
 
@@ -110,8 +127,55 @@ def adopt_plan(edge_index: Tensor, n_nodes: int, plan: GraphPlan) -> None:
     offline writer) for this ``edge_index`` tensor: ``get_plan`` returns it without sorting."""
     if plan.n_edges != edge_index.size(1) or plan.n_nodes != n_nodes:
         raise ValueError("plan does not match the graph")
-    _CACHE[id(edge_index)] = (weakref.ref(edge_index), edge_index._version, n_nodes, plan)
+    _remember(edge_index, n_nodes, plan)
 
 
 def clear_plan_cache() -> None:
     _CACHE.clear()
+
+
+# ---- deferred range check.  ``gtb_plan_build`` clamps node ids into [0, N) (the kernels that walk the
+# plan can never leave their tables) and raises ``status``; the flag travels to a pinned host slot
+# behind the build and is looked at -- without synchronising -- by the next plan calls, which raise
+# the IndexError the reference's index_select would have raised (at the latest ``GraphPlan.validate``).
+_STATUS_SLOTS = 32
+_status_host: Tensor | None = None
+_status_pending: list[tuple[torch.cuda.Event, int, int]] = []  # (copy done, host slot, id of the status tensor)
+_status_next = 0
+
+
+def _defer_status_check(status: Tensor) -> None:
+    global _status_host, _status_next
+    if _status_host is None:
+        _status_host = torch.zeros(_STATUS_SLOTS, dtype=torch.int32).pin_memory()
+    if len(_status_pending) >= _STATUS_SLOTS:  # ring full: settle the oldest check now
+        ev, slot, _ = _status_pending.pop(0)
+        ev.synchronize()
+        _raise_if_set(slot)
+    slot = _status_next
+    _status_next = (_status_next + 1) % _STATUS_SLOTS
+    _status_host[slot:slot + 1].copy_(status, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(status.device))
+    _status_pending.append((ev, slot, id(status)))
+
+
+def _raise_if_set(slot: int) -> None:
+    if int(_status_host[slot]) != 0:
+        _status_host[slot] = 0
+        raise IndexError("edge_index contains node indices outside [0, num_nodes)")
+
+
+def _forget_status(status: Tensor) -> None:
+    for i, (ev, slot, key) in enumerate(_status_pending):
+        if key == id(status):
+            ev.synchronize()
+            _status_host[slot] = 0
+            del _status_pending[i]
+            return
+
+
+def _poll_status() -> None:
+    while _status_pending and _status_pending[0][0].query():
+        _, slot, _ = _status_pending.pop(0)
+        _raise_if_set(slot)

@@ -35,6 +35,10 @@ CASES = [
     ("big: 1M rows, projected, aggr", 1000000, [64], 100000, [64, 64, 64], {"aggr": True, "scatter": True}),
     ("big W head: 1M rows, 4x64 -> 64 -> 64 -> 1 sigmoid", 1000000, [64, 64, 64, 64], 0, [64, 64, 1], {"sigmoid": True}),
     ("big encoder: 1M rows, 4 -> 64 -> 64 relu", 1000000, [4], 0, [64, 64], {"final_relu": True}),
+    ("edge ws: tile in / tile out", 20000, [64], 700, [64, 64, 64], {"aggr": True}),
+    ("edge ws: gather in / scatter out, relu", 20077, [64], 700, [64, 64, 64], {"aggr": True, "scatter": True, "gather": True, "relu_in": True}),
+    ("edge ws: 100 rows", 100, [64], 30, [64, 64, 64], {"aggr": True, "scatter": True}),
+    ("big edge ws: 1M rows, tile in / tile out", 1000000, [64], 100000, [64, 64, 64], {"aggr": True}),
 ]
 
 
@@ -133,6 +137,22 @@ def run_case(i: int) -> None:
                 ev1.record()
                 torch.cuda.synchronize()
                 msg += f" {ev0.elapsed_time(ev1) / 5 * 1e3:.0f}us"
+                if os.environ.get("EW_PROF"):
+                    L = _lib.lib()
+                    L.gtb_debug_tc_profile(2, None)
+                    ops.fused_mlp(blocks, n, packed, **kw)
+                    torch.cuda.synchronize()
+                    buf = (_lib.C.c_longlong * 32)()
+                    L.gtb_debug_tc_profile(2, buf)
+                    L.gtb_debug_tc_profile(0, None)
+                    tiles = max(1, buf[15])
+                    names = {0: "own:loop", 1: "own:wait e", 2: "own:conv0", 3: "own:Pi loads", 4: "own:wait Pj", 5: "own:wait d0",
+                             6: "own:epi0", 7: "own:wait d1", 8: "own:epi1", 9: "own:seg ids", 10: "own:wait d2", 11: "own:epi2",
+                             12: "own:wait out", 13: "own:aggr", 16: "prod:loop", 17: "prod:wait empty e", 18: "prod:issue e",
+                             19: "prod:wait out", 20: "prod:issue store", 21: "prod:wait empty out", 22: "prod:wait read",
+                             23: "prod:issue Pj", 24: "mma:loop", 25: "mma:wait a", 26: "mma:issue"}
+                    msg += "\n    ew prof (cycles per tile, ctx 0 / CTA 0, %d tiles): " % tiles + ", ".join(
+                        f"{nm} {buf[i] / tiles:.0f}" for i, nm in names.items())
                 if os.environ.get("TC_PROF"):
                     L = _lib.lib()
                     L.gtb_debug_tc_profile(1, None)

@@ -113,6 +113,34 @@ def test_radius_losses_vs_oracle_seeded(cap):
         _close(got[k], ref[k], f"rg.{k}")
 
 
+def test_rg_condensation_points_per_hit_mask():
+    """``eta`` is a per-HIT quantity in the reference's graphs (graph_builder.py:428,451 take it from the
+    point cloud), so a particle can straddle |eta| = max_eta: the RG loss then picks its condensation
+    points among the masked hits only (oc.py:33-43), attracts only those and normalises with
+    ``mask.sum()``.  Every particle here has hits on both sides of the cut, and the most-charged hit of
+    most particles is OUTSIDE the mask."""
+    from gnn_tracking_b200.metrics.losses.oc import CondensationLossRG
+    from oracle import losses_oracle as L
+    gen = torch.Generator().manual_seed(31)
+    n, n_p = 2400, 240
+    x = torch.randn(n, 3, generator=gen) * 1.4
+    pid = torch.randint(0, n_p, (n,), generator=gen)
+    pt = (0.5 + torch.rand(n_p, generator=gen) * 2)[pid]
+    reco = (torch.rand(n_p, generator=gen) < 0.95).long()[pid]
+    eta = (torch.rand(n, generator=gen) - 0.5) * 10          # per hit: about 20 % of every particle's hits fail the cut
+    beta = torch.rand(n, generator=gen).clamp(1e-3, 1 - 1e-3)
+    beta = torch.where(eta.abs() > 4.0, 0.97 + 0.029 * beta, 0.9 * beta)  # the best hits are the cut ones; no ties
+    mask = L.good_node_mask(pt=pt, particle_id=pid, reconstructable=reco, eta=eta)
+    per_particle = torch.zeros(n_p).index_add_(0, pid, mask.float()) / torch.bincount(pid, minlength=n_p).clamp_min(1)
+    assert ((per_particle > 0) & (per_particle < 1)).sum() > n_p // 2  # the mask really splits particles
+    ref = L.condensation_rg(beta=beta.double(), x=x.double(), particle_id=pid, mask=mask)
+    with torch.no_grad():
+        r = CondensationLossRG()(beta=beta.cuda(), x=x.cuda(), particle_id=pid.cuda(), reconstructable=reco.cuda(),
+                                 pt=pt.cuda(), eta=eta.cuda())
+    for k in ref:
+        _close(r.loss_dct[k], ref[k], f"rg_per_hit.{k}")
+
+
 @pytest.mark.parametrize("cap,p_attr,p_rep", [(256, 1.0, 1.0), (5, 2.0, 2.0)])
 def test_radius_loss_gradients(cap, p_attr, p_rep):
     """Gradients of the hinge loss w.r.t. x and of the radius-graph condensation loss w.r.t. x and
