@@ -246,10 +246,12 @@ def relabel_by_phi(g: dict) -> dict:
     return out
 
 
-def edge_kernel_time(model, x_dim, plan, n, e, dev, flush, reps):
+def edge_kernel_time(model, x_dim, plan, n, e, dev, flush, reps, sorted_edges=True):
     """The dominant kernel alone: one launch of the fused IN edge kernel of a middle layer (ReLU on
-    load; gathered pre-projected node tables, relational MLP, scattered store, segmented sum),
-    timed with CUDA events on the launching stream, L2 flushed before every launch."""
+    load; gathered pre-projected node tables, relational MLP, store, segmented sum), timed with CUDA
+    events on the launching stream, L2 flushed before every launch.  ``sorted_edges``: the edge features
+    come and go in the plan's destination-sorted order, as they do between the layers of the stack
+    (contiguous tiles); False: in the caller's order through ``perm`` (first / last layer of a stack)."""
     from gnn_tracking_b200 import ops
     from gnn_tracking_b200.ops import Block
     layer = model.ec_resin.network.layers[1]
@@ -259,7 +261,7 @@ def edge_kernel_time(model, x_dim, plan, n, e, dev, flush, reps):
     xx = torch.randn(n, dn, generator=gen).to(dev)
     ee = torch.randn(e, de, generator=gen).to(dev)
     blocks = [Block(xx, plan.dst_sorted, True, sorted_index=True), Block(xx, plan.src_sorted, True),
-              Block(ee, plan.perm, True)]
+              Block(ee, None, True) if sorted_edges else Block(ee, plan.perm, True)]
     widths = [dn, dn, de]
     n0 = rel.linears[0].out_features
     projected = [len(rel.linears) >= 2 and n0 % 4 == 0 and 2 * n <= e] * 2 + [False]
@@ -279,8 +281,8 @@ def edge_kernel_time(model, x_dim, plan, n, e, dev, flush, reps):
         aggr.zero_()
         s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        ops.fused_mlp(cur, e, packed[0], out=out, out_index=plan.perm, aggr=aggr, seg_id=plan.dst_sorted,
-                      rowptr=plan.rowptr)
+        ops.fused_mlp(cur, e, packed[0], out=out, out_index=None if sorted_edges else plan.perm, aggr=aggr,
+                      seg_id=plan.dst_sorted, rowptr=plan.rowptr)
         t.record()
         torch.cuda.synchronize()
         if i >= 3:
@@ -432,7 +434,8 @@ def run_ours(args) -> None:
     # ---- dominant kernel alone (rank 0's graph)
     dn, de = (HIDDEN, HIDDEN) if args.dims == "wide" else (5, 4)
     plan = build_plan(ei, n)
-    k_ms, k_impl = edge_kernel_time(model, (dn, de), plan, n, e, dev, flush, args.steps)
+    k_ms, k_impl = edge_kernel_time(model, (dn, de), plan, n, e, dev, flush, args.steps, sorted_edges=True)
+    k_ms_perm, _ = edge_kernel_time(model, (dn, de), plan, n, e, dev, flush, args.steps, sorted_edges=False)
     if world > 1:
         hf = torch.tensor([halo_frac], device=dev, dtype=torch.float64)
         dist.all_reduce(hf, op=dist.ReduceOp.MAX)
@@ -484,10 +487,13 @@ def run_ours(args) -> None:
                 "serial_value": e2e_serial_val, "serial_ms_per_step": ms_e2e_serial / args.steps},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm",
-                     "kernel": f"fused IN edge kernel ({k_impl}): gathered pre-projected node rows + relational MLP + scattered store + "
-                               "segmented sum, one layer, one launch",
+                     "kernel": f"fused IN edge kernel ({k_impl}): gathered pre-projected node rows + relational MLP + store + "
+                               "segmented sum, one layer, one launch, edge features in destination-sorted order as between "
+                               "the layers of the stack (kernel_ms_perm: the same launch reading / writing the caller's "
+                               "edge order through perm, as the last layer does)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "algorithmic_bytes_per_launch": alg, "kernel_ms": k_ms, "peak_source": peak_src},
+                     "algorithmic_bytes_per_launch": alg, "kernel_ms": k_ms, "kernel_ms_perm": k_ms_perm,
+                     "frac_perm": alg / (k_ms_perm * 1e-3) / 1e9 / peak, "peak_source": peak_src},
         "clocks": clocks.summary(),
     }
     if multi_parity is not None:

@@ -29,8 +29,10 @@ class _BwdPacks:
         self._key = None
         self._d: dict = {}
 
-    def get(self, linears, name, make):
-        key = tuple((p.data_ptr(), p._version) for lin in linears for p in lin.parameters())
+    def get(self, linears, name, make, sig=()):
+        """``sig``: the calling pattern the packs depend on besides the weights (block widths, which blocks
+        are gathered / activated on load): the same MLP called with another block layout re-packs."""
+        key = (sig,) + tuple((p.data_ptr(), p._version) for lin in linears for p in lin.parameters())
         if key != self._key:
             self._key, self._d = key, {}
         if name not in self._d:
@@ -97,13 +99,14 @@ class FusedMLPFunction(torch.autograd.Function):
         # ---- recompute the hidden activations (post-ReLU) in launch-row order
         fwd_blocks = [Block(t, m[0], m[1]) for t, m in zip(blocks_t, metas)]
         widths = [t.size(1) if t.dim() > 1 else 1 for t in blocks_t]
+        sig = (tuple(widths), tuple((m[0] is not None, bool(m[1])) for m in metas))
         hidden = []
         if nl >= 2:
             p0 = packs.get(linears, "prefix0", lambda: ops.pack_linears([weights[0]], [linears[0].bias], ops.default_impl(),
-                                                                        block_widths=widths))
+                                                                        block_widths=widths), sig)
             hidden.append(ops.fused_mlp(fwd_blocks, n_rows, p0, final_act=ACT_RELU))
             for l in range(1, nl - 1):
-                pl = packs.get(linears, f"layer{l}", lambda l=l: ops.pack_linears([weights[l]], [linears[l].bias], ops.default_impl()))
+                pl = packs.get(linears, f"layer{l}", lambda l=l: ops.pack_linears([weights[l]], [linears[l].bias], ops.default_impl()), sig)
                 hidden.append(ops.fused_mlp([Block(hidden[-1])], n_rows, pl, final_act=ACT_RELU))
 
         # ---- layers L-1 .. 1: weight / bias gradients, then dX = dY W gated by the ReLU mask
@@ -116,7 +119,7 @@ class FusedMLPFunction(torch.autograd.Function):
             grads[nb + l] = gw.t()
             if gb is not None:
                 grads[nb + nl + l] = gb
-            pt = packs.get(linears, f"layerT{l}", lambda l=l: ops.pack_linears([weights[l].t().contiguous()], [None], ops.default_impl()))
+            pt = packs.get(linears, f"layerT{l}", lambda l=l: ops.pack_linears([weights[l].t().contiguous()], [None], ops.default_impl()), sig)
             dz = ops.fused_mlp([Block(dz)], n_rows, pt, gate=a_in)
 
         # ---- first Linear: per source block
@@ -130,7 +133,7 @@ class FusedMLPFunction(torch.autograd.Function):
             small_table = index is not None and 2 * t2.size(0) <= n_rows
             need_t = ctx.needs_input_grad[1 + i]
             wslice_t = packs.get(linears, f"block{i}T", lambda off=off, w=w: ops.pack_linears(
-                [weights[0][:, off:off + w].t().contiguous()], [None], ops.default_impl())) if need_t else None
+                [weights[0][:, off:off + w].t().contiguous()], [None], ops.default_impl()), sig) if need_t else None
             if small_table:
                 # gather of a small table: fold the row gradients onto the table first
                 dp = torch.zeros((t2.size(0), dims[1]), dtype=torch.float32, device=dev)

@@ -35,6 +35,17 @@ inline int check_cuda(cudaError_t e, const char* what) {
 
 constexpr int kNumSMs = 148;  // B200
 
+// cudaFuncSetAttribute is a per-device setting: one flag per device and kernel family (the host side makes
+// the tensors' device current before it calls in, see ops.on_device)
+struct PerDeviceOnce {
+  bool done[64] = {false};
+  bool* slot() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    return &done[dev];
+  }
+};
+
 inline int64_t imin64(int64_t a, int64_t b) { return a < b ? a : b; }
 inline int64_t imax64(int64_t a, int64_t b) { return a > b ? a : b; }
 

@@ -1,32 +1,39 @@
 // Warp-specialised fused Interaction-Network edge kernel (sm_100a), the 64 / 64 / 64 "wide" shape:
 //
-//   e_out[o(r)] = W2 relu(W1 relu(W0e e_in[i(r)] + P_i[dst(r)] + P_j[src(r)] + b0) + b1) + b2
+//   e_out[o(r)] = W2 relu(W1 relu(W0e act(e_in[i(r)]) + P_i[dst(r)] + P_j[src(r)] + b0) + b1) + b2
 //   aggr[dst(r)] += e_out row          (rows r walk the plan's destination-sorted edge list)
 //
 // i.e. reference models/interaction_network.py:75-89 (message) + the SumAggregation of :22,36 with the
-// node-side products P_i = relu(x) W0[:, :Dn]^T, P_j = relu(x) W0[:, Dn:2Dn]^T taken per node (see
+// node-side products P_i = act(x) W0[:, :Dn]^T, P_j = act(x) W0[:, Dn:2Dn]^T taken per node (see
 // GTB_SRC_PROJECTED in include/gtb200.h).  Same arithmetic as the generic tiles of mlp_tc.cu (3xTF32,
 // A operand in TMEM, fp32 accumulation), different machine mapping:
 //
-//   * one persistent CTA per SM, 20 warps with fixed roles, two tile contexts (ctx = alternate tiles):
-//       warp 0 / 1  : TMA producer of ctx 0 / 1 -- edge-feature tile (2-D tile load when the features are
-//                     kept in destination order, tile::gather4 through `perm` otherwise), P_j rows
-//                     (tile::gather4 through src_sorted), and the store of the finished tile
-//                     (tile store / tile::scatter4); completion through mbarrier transaction counts
-//       warp 2 / 3  : tcgen05.mma issue of ctx 0 / 1 (one elected lane, 24 MMAs per Linear)
-//       warps 4-11 / 12-19 : 256 row-owner threads of ctx 0 / 1 (thread = row x 32-column half):
-//                     tf32 hi / lo split into TMEM, accumulator read-back, bias / gathered adds / ReLU,
-//                     output staging and the in-tile segmented sum
+//   * one persistent CTA per SM, two tiles ("contexts" A / B) in flight, 20 warps with fixed roles:
+//       warps 0-15  : 512 row owners (thread = row x 16-column quarter).  ALL of them work on one
+//                     stage of one context at a time and ping-pong between the contexts: while the
+//                     tensor core runs a Linear of context A they run a stage of context B --
+//                        E0(A) E0(B) E1(A) E1(B) E2(A) C0(A') E2(B) AG(A) C0(B') AG(B)
+//                     C0: tf32 hi / lo split of the edge-feature tile into TMEM; E0 / E1: accumulator
+//                     + bias (+ P_i[dst] + P_j[src]) -> ReLU -> next A operand; E2: output tile into
+//                     shared memory; AG: store of the tile, in-tile segmented sum by destination, and
+//                     the gather of the NEXT tile's P_j rows into the rows just vacated
+//       warp 16 / 17: TMA producer of context A / B: edge-feature tile (2-D tile load when the features
+//                     are kept in destination order, tile::gather4 through `perm` otherwise) and the
+//                     tile's dst / src ids (bulk copies)
+//       warp 18 / 19: tcgen05.mma issue of context A / B (one elected lane, 24 MMAs per Linear)
 //   * every hand-over is an mbarrier (no CTA or named barrier inside the tile loop):
-//       full[slot]  producer -> owners   (TMA bytes landed)
-//       empty[slot] owners   -> producer (slot may be overwritten)
-//       a_ready     owners   -> MMA warp (A operand of the next Linear is in TMEM)
-//       d_ready     MMA warp -> owners   (tcgen05.commit: accumulator complete, A operand free)
-//       out_ready   owners   -> producer + owners (output tile staged in shared memory)
-//   * shared memory: packed weights (3 x hi / lo x 16 KB, the image gtb_mlp_pack writes) + a ring of two
-//     32 KB slots per context; per tile the ring carries e_in, P_j, out in that order, so e_in(t + 1)
-//     lands while tile t is still in its second Linear.
-//   * TMEM: 192 columns per context (A hi | A lo | D).
+//       full_e   producer -> owners  (edge-feature tile + ids landed: transaction bytes)
+//       full_p   owners   -> owners  (P_j rows landed: 16 warps x their own 8 rows, transaction bytes)
+//       pj_free  owners   -> producer (P_j consumed: its slot takes the next edge-feature tile)
+//       a_ready  owners   -> MMA warp (A operand of the next Linear is in TMEM)
+//       d_ready  MMA warp -> owners   (tcgen05.commit: accumulator complete, A operand free)
+//       out_ready owners  -> owners   (output tile staged: rows regroup from row owners to 8-row bands)
+//   * TMA: gathers are tile::gather4 (four row coordinates per instruction) issued from single-lane
+//     branches with broadcast coordinates; stores are 8-row tile stores / tile::scatter4, issued by the
+//     warp that sums the same 8 rows, so a band of a slot is refilled by the warp that drained it and the
+//     slot ring needs no producer round trip: per context two 32 KB slots carry e_in(t), P_j(t), out(t).
+//   * shared memory: weights 96 KB (3 x hi / lo x 16 KB, the image gtb_mlp_pack writes) | 4 slots |
+//     biases, ids, barriers = 227 KB.  TMEM: 192 columns per context (A hi | A lo | D).
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "tma_common.cuh"
@@ -36,10 +43,15 @@ namespace gtb {
 using namespace tc;
 
 constexpr int EW_TM = 128;
-constexpr int EW_SLOT = 32768;                // [2 K tiles][128 rows][32 fp32], 128-byte swizzle (TMA == UMMA image)
-constexpr int EW_HEAD = 2048;                 // mbarriers + TMEM slot
-constexpr int EW_WBYTES = 99328;              // packed weights (99072 bytes) rounded up to 1024
-constexpr int EW_SMEM = EW_HEAD + EW_WBYTES + 4 * EW_SLOT;  // 232448 = the 227 KB opt-in maximum
+constexpr int EW_SLOT = 32768;        // [2 K tiles][128 rows][32 fp32], 128-byte swizzle (TMA image == UMMA image)
+constexpr int EW_W = 98304;           // packed weights without the bias rows
+constexpr int EW_SLOTS = EW_W;        // 4 slots: context c, slot s at EW_SLOTS + (2 c + s) * EW_SLOT
+constexpr int EW_BIAS = EW_SLOTS + 4 * EW_SLOT;  // 3 x 64 floats
+constexpr int EW_IDS = EW_BIAS + 768;  // per context: dst ids [128] | src ids [128]
+constexpr int EW_BARS = EW_IDS + 2048;  // per context 64 bytes: full_e | full_p | pj_free | a_ready | d_ready | out_ready
+constexpr int EW_TMEM_SLOT = EW_BARS + 128;
+constexpr int EW_SMEM = 232448;       // the 227 KB opt-in maximum
+static_assert(EW_TMEM_SLOT + 4 <= EW_SMEM, "shared-memory layout");
 constexpr int EW_THREADS = 640;
 constexpr uint32_t EW_A_HI = 0, EW_A_LO = 64, EW_D = 128, EW_CTX = 192;
 
@@ -47,7 +59,7 @@ __device__ int g_ew_fault = 0;  // 1: barrier timeout, 2: TMEM base != 0, 3: sha
 __device__ long long g_ew_prof[32];
 static int g_ew_prof_enabled = 0;
 
-// per-stage clock accumulation by lane 0 of one warp per role of context 0 in CTA 0 (tests/cuda/tc_diag.py)
+// per-stage clock accumulation by lane 0 of one warp per role in CTA 0 (tests/cuda/tc_diag.py)
 #define EW_PROF(id)                                   \
   do {                                                \
     if (PROF && prof_on) {                            \
@@ -58,23 +70,26 @@ static int g_ew_prof_enabled = 0;
   } while (0)
 
 struct EwParams {
-  CUtensorMap e_map;    // e_in  [E, 64] fp32: box 32 x 128 (tile mode) or 32 x 1 (gather mode)
-  CUtensorMap pj_map;   // P_j   [N, 64] fp32: box 32 x 1
-  CUtensorMap out_map;  // e_out [E, 64] fp32: box 32 x 128 (tile mode) or 32 x 1 (scatter mode)
-  const float* pi;      // P_i [N, pi_ld]
-  const int32_t* dst;   // dst_sorted [E]: segment ids of the per-destination sum
-  const int32_t* pi_index;  // row of P_i per edge (the same array in an IN layer)
-  const int32_t* src;   // src_sorted [E]
+  CUtensorMap e_map;     // e_in  [E, 64] fp32: box 32 x 128 (tile mode) or 32 x 1 (gather mode)
+  CUtensorMap pj_map;    // P_j   [N, 64] fp32: box 32 x 1
+  CUtensorMap out_map;   // e_out [E, 64] fp32: box 32 x 8 (tile mode) or 32 x 1 (scatter mode)
+  const float* pi;       // P_i [N, pi_ld], rows addressed by dst
+  const int32_t* dst;    // dst_sorted [E]: P_i row and segment id of every edge
+  const int32_t* src;    // src_sorted [E]
   const int32_t* e_index;    // perm or nullptr (tile mode)
   const int32_t* out_index;  // perm or nullptr (tile mode)
   float* aggr;
-  float* out;           // e_out base (scatter mode: the rows of a partial last tile are stored by their owners)
+  float* out;            // e_out base (scatter mode: a partial last tile is stored with plain stores)
   const unsigned char* packed;
   int64_t n_rows;
-  int32_t n_tiles, pi_ld, aggr_ld, out_ld, w_bytes;
+  int32_t n_tiles, pi_ld, aggr_ld, out_ld;
 };
 
+__device__ __noinline__ void ew_timeout();
 __device__ __forceinline__ void ew_wait(uint32_t bar, uint32_t parity) {
+  // NOT unrolled: ptxas otherwise replicates the try_wait 64 times per wait site (100 KB of SASS: every
+  // stage change then misses the instruction cache)
+#pragma unroll 1
   for (uint32_t i = 0; i < 20000000u; ++i) {
     uint32_t ok;
     asm volatile(
@@ -86,11 +101,12 @@ __device__ __forceinline__ void ew_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     if (ok) return;
   }
-  atomicExch(&g_ew_fault, 1);
-  __trap();  // a protocol error must fail loudly, never hang the GPU
+  ew_timeout();
 }
 
-// row indices 4 lane .. 4 lane + 3 of a tile (clamped / replaced by `fill` past the end of the list)
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// row indices 4 lane .. 4 lane + 3 of a tile (`fill` past the end of the list)
 __device__ __forceinline__ int4 ew_idx4(const int32_t* idx, uint32_t row0, int rows_here, int lane, int fill) {
   if (rows_here == EW_TM) return __ldg(reinterpret_cast<const int4*>(idx + row0) + lane);
   int4 v;
@@ -101,63 +117,310 @@ __device__ __forceinline__ int4 ew_idx4(const int32_t* idx, uint32_t row0, int r
   return v;
 }
 
-// 64 gather4 copies of one 128-row tile: lane j's four row indices are broadcast, ONE elected lane issues
-// (uniform-datapath instruction: coordinates travel through uniform registers, no per-lane waterfall)
-__device__ __forceinline__ void ew_gather_tile(uint32_t slot, const CUtensorMap* map, uint32_t bar, const int4& r4) {
-#pragma unroll 4
-  for (int j = 0; j < 32; ++j) {
-    const int a = __shfl_sync(0xffffffffu, r4.x, j), b = __shfl_sync(0xffffffffu, r4.y, j);
-    const int c = __shfl_sync(0xffffffffu, r4.z, j), d = __shfl_sync(0xffffffffu, r4.w, j);
-    if (elect_one()) {
-      tma::gather4(slot + j * 512, map, bar, 0, a, b, c, d);
-      tma::gather4(slot + 16384 + j * 512, map, bar, 32, a, b, c, d);
-    }
-    __syncwarp();
-  }
+// Barrier timeouts leave through one out-of-line exit (the wait loop itself stays three instructions).
+__device__ __noinline__ void ew_timeout() {
+  atomicExch(&g_ew_fault, 1);
+  __trap();  // a protocol error must fail loudly, never hang the GPU
 }
-__device__ __forceinline__ void ew_scatter_tile(uint32_t slot, const CUtensorMap* map, const int4& r4) {
-#pragma unroll 4
-  for (int j = 0; j < 32; ++j) {
-    const int a = __shfl_sync(0xffffffffu, r4.x, j), b = __shfl_sync(0xffffffffu, r4.y, j);
-    const int c = __shfl_sync(0xffffffffu, r4.z, j), d = __shfl_sync(0xffffffffu, r4.w, j);
-    if (elect_one()) {
-      tma::scatter4(map, slot + j * 512, 0, a, b, c, d);
-      tma::scatter4(map, slot + 16384 + j * 512, 32, a, b, c, d);
-    }
+
+// state of the 512 row owners.  The context c is a RUN-TIME value: one copy of every stage serves both
+// contexts (the loop body stays inside the instruction cache); the only per-context registers are the
+// four segment ids a lane sums in AG, selected with c.
+template <bool RELU_E, bool PROF>
+struct EwOwner {
+  const EwParams& p;
+  uint32_t sm0;
+  int w, lane, r, qd;       // warp 0..15, row 32 (w & 3) + lane, column quarter w >> 2
+  uint32_t rx, own;         // swizzle term of the own row, own row inside the own K tile of a slot
+  int tile00, nA, nB;       // first tile of context 0, number of tiles of each context (stride 2 * gridDim.x)
+  int32_t sgA[4], sgB[4];   // segment ids of the 4 rows this lane sums
+  bool prof_on;
+  long long prof_t;
+
+  __device__ __forceinline__ int n_of(int c) const { return c ? nB : nA; }
+  __device__ __forceinline__ int tile_of(int c, int t) const { return tile00 + (2 * t + c) * (int)gridDim.x; }
+  __device__ __forceinline__ uint32_t bar(int c, int which) const { return sm0 + EW_BARS + 64 * c + 8 * which; }
+  __device__ __forceinline__ uint32_t slot(int c, uint32_t s) const { return sm0 + EW_SLOTS + (2 * c + s) * EW_SLOT; }
+  __device__ __forceinline__ uint32_t tm_lane(int c) const { return (uint32_t)c * EW_CTX + ((uint32_t)((w & 3) * 32) << 16); }
+  __device__ __forceinline__ uint32_t chunk(int q) const { return (((uint32_t)(4 * (qd & 1) + q)) << 4) ^ rx; }
+  __device__ __forceinline__ uint32_t ids(int c) const { return sm0 + EW_IDS + 1024 * c; }
+  __device__ __forceinline__ void arrive(uint32_t b) {
     __syncwarp();
+    if (lane == 0) tma::mbar_arrive(b);
   }
-}
+  __device__ __forceinline__ void a_done(int c) {  // the A operand written by this warp is complete
+    tmem_st_wait();
+    tc_fence_before_sync();
+    arrive(bar(c, 3));
+  }
+  __device__ __forceinline__ void bias_add(float (&v)[16], int layer) {
+    const uint32_t ba = sm0 + EW_BIAS + 256 * layer + 64 * qd;
+    add16(v, lds128(ba), lds128(ba + 16), lds128(ba + 32), lds128(ba + 48));
+  }
+  // accumulator of the own 16 columns, once the l-th Linear of tile iteration t has completed
+  __device__ __forceinline__ void acc_load(int c, int t, int l, float (&v)[16]) {
+    ew_wait(bar(c, 4), (uint32_t)(t + l) & 1u);  // completion number 3 t + l
+    tc_fence_after_sync();
+    uint32_t acc[16];
+    tmem_ld16(tm_lane(c) + EW_D + 16 * qd, acc);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
+  }
+
+  // ---- C0: own 16 columns of the edge-feature row -> tf32 hi / lo -> TMEM
+  __device__ __forceinline__ void c0(int c, int t) {
+    const int tile = tile_of(c, t);
+    const uint32_t row0 = (uint32_t)tile * EW_TM;
+    const int rows_here = (int)min((int64_t)EW_TM, p.n_rows - (int64_t)row0);
+    const uint32_t sl = slot(c, (uint32_t)t & 1u);
+    EW_PROF(0);
+    ew_wait(bar(c, 0), (uint32_t)t & 1u);
+    EW_PROF(1);
+    {  // the target row of P_i is read in E0, a Linear from now: start it towards L1
+      int32_t d = 0;
+      if (rows_here == EW_TM) d = lds_i32(ids(c) + 4 * r);
+      else if (r < rows_here) d = __ldg(p.dst + row0 + r);
+      prefetch_l1(row_ptr(p.pi + 16 * qd, (uint32_t)d, (uint32_t)p.pi_ld * 4u));
+    }
+    float v[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 a = lds128(sl + own + chunk(q));
+      v[4 * q + 0] = a.x; v[4 * q + 1] = a.y; v[4 * q + 2] = a.z; v[4 * q + 3] = a.w;
+    }
+    if (RELU_E) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    split_store16(tm_lane(c) + EW_A_HI + 16 * qd, tm_lane(c) + EW_A_LO + 16 * qd, v);
+    a_done(c);
+    EW_PROF(2);
+  }
+
+  // ---- E0: D + b0 + P_i[dst] + P_j[src] -> ReLU -> A operand of the second Linear
+  __device__ __forceinline__ void e0(int c, int t) {
+    const int tile = tile_of(c, t);
+    const uint32_t row0 = (uint32_t)tile * EW_TM;
+    const int rows_here = (int)min((int64_t)EW_TM, p.n_rows - (int64_t)row0);
+    const uint32_t sl = slot(c, ((uint32_t)t & 1u) ^ 1u);
+    float4 pre[4];
+    {
+      int32_t d = 0;
+      if (rows_here == EW_TM) d = lds_i32(ids(c) + 4 * r);
+      else if (r < rows_here) d = __ldg(p.dst + row0 + r);
+      const float4* rowp = reinterpret_cast<const float4*>(row_ptr(p.pi + 16 * qd, (uint32_t)d, (uint32_t)p.pi_ld * 4u));
+#pragma unroll
+      for (int q = 0; q < 4; ++q) pre[q] = __ldg(rowp + q);
+    }
+    {  // segment ids of the rows this lane sums in AG: rows 8 w + 4 (lane >> 4) + i (the ids leave with P_j)
+      const int rr0 = 8 * w + 4 * (lane >> 4);
+      int4 s;
+      if (rows_here == EW_TM) {
+        asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(s.x), "=r"(s.y), "=r"(s.z), "=r"(s.w) : "r"(ids(c) + 4 * rr0) : "memory");
+      } else {
+        s.x = rr0 + 0 < rows_here ? __ldg(p.dst + row0 + rr0 + 0) : -1;
+        s.y = rr0 + 1 < rows_here ? __ldg(p.dst + row0 + rr0 + 1) : -1;
+        s.z = rr0 + 2 < rows_here ? __ldg(p.dst + row0 + rr0 + 2) : -1;
+        s.w = rr0 + 3 < rows_here ? __ldg(p.dst + row0 + rr0 + 3) : -1;
+      }
+      if (c) { sgB[0] = s.x; sgB[1] = s.y; sgB[2] = s.z; sgB[3] = s.w; }
+      else   { sgA[0] = s.x; sgA[1] = s.y; sgA[2] = s.z; sgA[3] = s.w; }
+    }
+    EW_PROF(3);
+    ew_wait(bar(c, 1), (uint32_t)t & 1u);
+    EW_PROF(4);
+    float v[16];
+    acc_load(c, t, 0, v);
+    EW_PROF(5);
+    float4 x[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) x[q] = lds128(sl + own + chunk(q));
+    bias_add(v, 0);
+    add16(v, pre[0], pre[1], pre[2], pre[3]);
+    add16(v, x[0], x[1], x[2], x[3]);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+    split_store16(tm_lane(c) + EW_A_HI + 16 * qd, tm_lane(c) + EW_A_LO + 16 * qd, v);
+    tmem_st_wait();
+    tc_fence_before_sync();
+    __syncwarp();
+    if (lane == 0) {
+      tma::mbar_arrive(bar(c, 3));
+      tma::mbar_arrive(bar(c, 2));  // P_j(t) consumed: the producer may load e_in(t + 1) over it
+    }
+    EW_PROF(6);
+  }
+
+  // ---- E1: D + b1 -> ReLU -> A operand of the third Linear
+  __device__ __forceinline__ void e1(int c, int t) {
+    EW_PROF(7);
+    float v[16];
+    acc_load(c, t, 1, v);
+    EW_PROF(8);
+    bias_add(v, 1);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+    split_store16(tm_lane(c) + EW_A_HI + 16 * qd, tm_lane(c) + EW_A_LO + 16 * qd, v);
+    a_done(c);
+    EW_PROF(9);
+  }
+
+  // ---- E2: D + b2 -> output tile in shared memory (the slot of e_in(t): the own piece is dead)
+  __device__ __forceinline__ void e2(int c, int t) {
+    const uint32_t sl = slot(c, (uint32_t)t & 1u);
+    EW_PROF(10);
+    float v[16];
+    acc_load(c, t, 2, v);
+    EW_PROF(11);
+    bias_add(v, 2);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) sts128(sl + own + chunk(q), make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+    tc_fence_before_sync();
+    fence_proxy_async_smem();  // the TMA store reads the tile through the async proxy
+    arrive(bar(c, 5));
+    EW_PROF(12);
+  }
+
+  // gather of the P_j rows 8 w .. 8 w + 7 of tile iteration `t` into `sl` (this warp's band of the slot)
+  __device__ __forceinline__ void load_pj(int c, int t, uint32_t sl) {
+    const int tile = tile_of(c, t);
+    const uint32_t row0 = (uint32_t)tile * EW_TM;
+    const int rows_here = (int)min((int64_t)EW_TM, p.n_rows - (int64_t)row0);
+    ew_wait(bar(c, 0), (uint32_t)t & 1u);  // the ids of tile t travel with its edge-feature tile
+    int32_t s = 0;
+    if (lane < 8) {
+      if (rows_here == EW_TM) s = lds_i32(ids(c) + 512 + 4 * (8 * w + lane));
+      else if (8 * w + lane < rows_here) s = __ldg(p.src + row0 + 8 * w + lane);
+    }
+    const uint32_t fb = bar(c, 1);
+    if (lane == 0) tma::mbar_expect_tx(fb, 8 * 256);
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int a = __shfl_sync(0xffffffffu, s, 4 * j + 0), b = __shfl_sync(0xffffffffu, s, 4 * j + 1);
+      const int cc = __shfl_sync(0xffffffffu, s, 4 * j + 2), d = __shfl_sync(0xffffffffu, s, 4 * j + 3);
+      if (elect_one()) {
+        tma::gather4(sl + (uint32_t)(8 * w + 4 * j) * 128u, &p.pj_map, fb, 0, a, b, cc, d);
+        tma::gather4(sl + 16384u + (uint32_t)(8 * w + 4 * j) * 128u, &p.pj_map, fb, 32, a, b, cc, d);
+      }
+      __syncwarp();
+    }
+  }
+
+  // ---- AG: rows regroup into 8-row bands (warp w: rows 8 w .. 8 w + 7, all 64 columns): store of the band,
+  // segmented sum by destination, then the band takes the next tile's P_j rows
+  __device__ __forceinline__ void ag(int c, int t) {
+    const int tile = tile_of(c, t);
+    const uint32_t row0 = (uint32_t)tile * EW_TM;
+    const int rows_here = (int)min((int64_t)EW_TM, p.n_rows - (int64_t)row0);
+    const uint32_t sl = slot(c, (uint32_t)t & 1u);
+    EW_PROF(13);
+    ew_wait(bar(c, 5), (uint32_t)t & 1u);
+    EW_PROF(14);
+    if (8 * w < rows_here) {
+      if (p.out_index == nullptr) {
+        if (elect_one()) {  // rows past the end of the table are clipped
+          tma::store_2d(&p.out_map, sl + (uint32_t)(8 * w) * 128u, 0, (int)row0 + 8 * w);
+          tma::store_2d(&p.out_map, sl + 16384u + (uint32_t)(8 * w) * 128u, 32, (int)row0 + 8 * w);
+        }
+        __syncwarp();
+      } else if (rows_here == EW_TM) {
+        const int32_t o = lane < 8 ? __ldg(p.out_index + row0 + 8 * w + lane) : 0;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int a = __shfl_sync(0xffffffffu, o, 4 * j + 0), b = __shfl_sync(0xffffffffu, o, 4 * j + 1);
+          const int cc = __shfl_sync(0xffffffffu, o, 4 * j + 2), d = __shfl_sync(0xffffffffu, o, 4 * j + 3);
+          if (elect_one()) {
+            tma::scatter4(&p.out_map, sl + (uint32_t)(8 * w + 4 * j) * 128u, 0, a, b, cc, d);
+            tma::scatter4(&p.out_map, sl + 16384u + (uint32_t)(8 * w + 4 * j) * 128u, 32, a, b, cc, d);
+          }
+          __syncwarp();
+        }
+      } else {  // partial last tile, scattered rows: plain stores
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = 8 * w + 2 * i + (lane >> 4), cc = lane & 15;
+          if (row < rows_here) {
+            const float4 v = lds128(sl + (uint32_t)(cc >> 3) * 16384u + (uint32_t)row * 128u + ((((uint32_t)cc & 7u) ^ ((uint32_t)row & 7u)) << 4));
+            float* orow = const_cast<float*>(row_ptr(p.out, (uint32_t)__ldg(p.out_index + row0 + row), (uint32_t)p.out_ld * 4u));
+            reinterpret_cast<float4*>(orow)[cc] = v;
+          }
+        }
+      }
+      tma::bulk_commit();
+      // one vector reduction (red.global.add.v4.f32) per run of equal destinations inside 4 rows
+      const int c4 = lane & 15, rr0 = 8 * w + 4 * (lane >> 4);
+      float4 v[4];
+      const uint32_t colb = sl + (uint32_t)(c4 >> 3) * 16384u + (uint32_t)rr0 * 128u;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)  // (rr0 + i) & 7 == 4 (lane >> 4) + i
+        v[i] = lds128(colb + (uint32_t)i * 128u + ((((uint32_t)c4 & 7u) ^ (uint32_t)(4 * (lane >> 4) + i)) << 4));
+      int32_t sg[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sg[i] = c ? sgB[i] : sgA[i];
+      if (sg[0] >= 0) {
+        const uint32_t ald4 = (uint32_t)p.aggr_ld * 4u;
+        int cur = sg[0];
+        f32x2 s01 = pack2(0.f, 0.f), s23 = s01;
+        auto flush = [&](int seg) {
+          float4 sum;
+          unpack2(s01, sum.x, sum.y);
+          unpack2(s23, sum.z, sum.w);
+          red_add_v4(row_ptr(p.aggr + 4 * c4, (uint32_t)seg, ald4), sum);
+        };
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (sg[i] < 0) break;
+          if (sg[i] != cur) {
+            flush(cur);
+            cur = sg[i];
+            s01 = pack2(0.f, 0.f);
+            s23 = s01;
+          }
+          s01 = add2(s01, pack2(v[i].x, v[i].y));
+          s23 = add2(s23, pack2(v[i].z, v[i].w));
+        }
+        flush(cur);
+      }
+    }
+    EW_PROF(15);
+    if (t + 1 < n_of(c)) {
+      tma::bulk_wait_read0();  // this warp's store has read its band: the band is free
+      __syncwarp();
+      load_pj(c, t + 1, sl);
+    }
+    EW_PROF(16);
+  }
+};
 
 template <bool RELU_E, bool PROF>
 __global__ void __launch_bounds__(EW_THREADS, 1) in_edge_ws_kernel(const __grid_constant__ EwParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t sm0 = smem_u32(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // head: per context c (64 bytes each): full[2] | empty[2] | a_ready | d_ready | out_ready ; TMEM slot at 256
-  const uint32_t wbase = sm0 + EW_HEAD;
-  const uint32_t slots0 = wbase + EW_WBYTES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + 256);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + EW_TMEM_SLOT);
 
-  if (sm0 & 1023u) {  // swizzle atoms need the 1024-byte alignment the layout above assumes
+  if (sm0 & 1023u) {  // swizzle atoms need the 1024-byte alignment the layout assumes
     if (tid == 0) atomicExch(&g_ew_fault, 3);
     __trap();
   }
-  {  // packed weights -> shared memory (generic proxy), visible to the tensor core after the proxy fence
+  {  // packed weights and biases -> shared memory (generic proxy), visible to the tensor core after the proxy fence
     const float4* g4 = reinterpret_cast<const float4*>(p.packed);
-    float4* s4 = reinterpret_cast<float4*>(smem_raw + EW_HEAD);
-    for (int i = tid; i < (p.w_bytes >> 4); i += EW_THREADS) s4[i] = __ldg(g4 + i);
+    float4* s4 = reinterpret_cast<float4*>(smem_raw);
+    for (int i = tid; i < EW_W / 16; i += EW_THREADS) s4[i] = __ldg(g4 + i);
+    float4* b4 = reinterpret_cast<float4*>(smem_raw + EW_BIAS);
+    for (int i = tid; i < 768 / 16; i += EW_THREADS) b4[i] = __ldg(g4 + EW_W / 16 + i);
   }
   if (tid == 0) {
     for (int c = 0; c < 2; ++c) {
-      const uint32_t b = sm0 + 64 * c;
-      mbar_init(reinterpret_cast<uint64_t*>(smem_raw + 64 * c + 0), 1);   // full[0]
-      mbar_init(reinterpret_cast<uint64_t*>(smem_raw + 64 * c + 8), 1);   // full[1]
-      mbar_init(reinterpret_cast<uint64_t*>(smem_raw + 64 * c + 16), 8);  // empty[0]: 8 owner warps
-      mbar_init(reinterpret_cast<uint64_t*>(smem_raw + 64 * c + 24), 8);  // empty[1]
-      mbar_init(reinterpret_cast<uint64_t*>(smem_raw + 64 * c + 32), 8);  // a_ready
-      mbar_init(reinterpret_cast<uint64_t*>(smem_raw + 64 * c + 40), 1);  // d_ready
-      mbar_init(reinterpret_cast<uint64_t*>(smem_raw + 64 * c + 48), 8);  // out_ready
-      (void)b;
+      unsigned char* b = smem_raw + EW_BARS + 64 * c;
+      mbar_init(reinterpret_cast<uint64_t*>(b + 0), 1);    // full_e: the producer's expect_tx
+      mbar_init(reinterpret_cast<uint64_t*>(b + 8), 16);   // full_p: one expect_tx per owner warp
+      mbar_init(reinterpret_cast<uint64_t*>(b + 16), 16);  // pj_free
+      mbar_init(reinterpret_cast<uint64_t*>(b + 24), 16);  // a_ready
+      mbar_init(reinterpret_cast<uint64_t*>(b + 32), 1);   // d_ready
+      mbar_init(reinterpret_cast<uint64_t*>(b + 40), 16);  // out_ready
     }
     fence_barrier_init();
   }
@@ -171,110 +434,118 @@ __global__ void __launch_bounds__(EW_THREADS, 1) in_edge_ws_kernel(const __grid_
     __trap();
   }
 
-  const int ctx = warp < 4 ? (warp & 1) : ((warp - 4) >> 3);
-  const uint32_t bars = sm0 + 64 * ctx;
-  const uint32_t full0 = bars, empty0 = bars + 16, a_ready = bars + 32, d_ready = bars + 40, out_ready = bars + 48;
-  const uint32_t slots = slots0 + (uint32_t)ctx * 2u * EW_SLOT;
-  const uint32_t tmc = (uint32_t)ctx * EW_CTX;
-  // tiles of this context: blockIdx.x + gridDim.x * (2 t + ctx)
-  const int tile0 = (int)blockIdx.x + (int)gridDim.x * ctx, tstep = 2 * (int)gridDim.x;
-  const bool prof_on = PROF && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 2 || warp == 4);
+  // tiles of context c: blockIdx.x + gridDim.x * (2 t + c)
+  const int g = (int)gridDim.x;
+  int tile0[2], n_t[2];
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    tile0[c] = (int)blockIdx.x + g * c;
+    n_t[c] = tile0[c] < p.n_tiles ? (p.n_tiles - tile0[c] + 2 * g - 1) / (2 * g) : 0;
+  }
+  const bool prof_on = PROF && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 16 || warp == 18);
   long long prof_t = prof_on ? clock64() : 0;
 
-  if (warp < 2) {
+  if (warp < 16) {
+    // ================================================================= row owners
+    EwOwner<RELU_E, PROF> o{p, sm0};
+    o.w = warp; o.lane = lane; o.r = 32 * (warp & 3) + lane; o.qd = warp >> 2;
+    o.rx = (uint32_t)(o.r & 7) << 4;
+    o.own = (uint32_t)(o.qd >> 1) * 16384u + (uint32_t)o.r * 128u;
+    o.tile00 = tile0[0]; o.nA = n_t[0]; o.nB = n_t[1];  // nB <= nA <= nB + 1
+    o.prof_on = prof_on; o.prof_t = prof_t;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c)
+      if (o.n_of(c) > 0) o.load_pj(c, 0, o.slot(c, 1));
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c)
+      if (o.n_of(c) > 0) o.c0(c, 0);
+    // stage order of one round (two tiles): E0 E0' E1 E1' E2 E2' AG C0+ AG' C0'+  -- a stage of one context runs
+    // under the Linear of the other; AG sits two stages in front of the E0 that needs the rows it gathers
+#pragma unroll 1
+    for (int t = 0; t < o.nA; ++t) {
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c)
+        if (t < o.n_of(c)) o.e0(c, t);
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c)
+        if (t < o.n_of(c)) o.e1(c, t);
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c)
+        if (t < o.n_of(c)) o.e2(c, t);
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        if (t < o.n_of(c)) o.ag(c, t);
+        if (t + 1 < o.n_of(c)) o.c0(c, t + 1);
+      }
+      if (PROF && prof_on) g_ew_prof[31] += 1;
+    }
+    tma::bulk_wait_all0();
+  } else if (warp < 18) {
     // ================================================================= TMA producer of context `ctx`
+    const int ctx = warp - 16;
+    const uint32_t bars = sm0 + EW_BARS + 64 * ctx;
+    const uint32_t full_e = bars, pj_free = bars + 16;
+    const uint32_t ids = sm0 + EW_IDS + 1024 * ctx;
     if (lane == 0) {
       tma::prefetch_map(&p.e_map);
       tma::prefetch_map(&p.pj_map);
       tma::prefetch_map(&p.out_map);
     }
-    const bool e_gather = p.e_index != nullptr, o_scatter = p.out_index != nullptr;
-    // `keep`: the tile's out_index rows (scatter mode), held until the tile is stored
-    auto load_e = [&](int tile, uint32_t slot_i, int4& keep) {
+    const bool e_gather = p.e_index != nullptr;
+    for (int t = 0; t < n_t[ctx]; ++t) {
+      const int tile = tile0[ctx] + t * 2 * g;
       const uint32_t row0 = (uint32_t)tile * EW_TM;
       const int rows_here = (int)min((int64_t)EW_TM, p.n_rows - (int64_t)row0);
-      const uint32_t sl = slots + slot_i * EW_SLOT, fb = full0 + 8 * slot_i;
-      int4 e4 = make_int4(0, 0, 0, 0);
-      if (e_gather) e4 = ew_idx4(p.e_index, row0, rows_here, lane, 0);
-      if (o_scatter) keep = (e_gather && p.e_index == p.out_index) ? e4 : ew_idx4(p.out_index, row0, rows_here, lane, 0);
-      if (lane == 0) tma::mbar_expect_tx(fb, EW_SLOT);
+      const uint32_t sl = sm0 + EW_SLOTS + (2 * ctx + (t & 1)) * EW_SLOT;
+      EW_PROF(17);
+      if (t > 0) ew_wait(pj_free, (uint32_t)(t - 1) & 1u);  // slot t & 1 held P_j(t - 1)
+      EW_PROF(18);
+      const bool full = rows_here == EW_TM;
+      if (lane == 0) tma::mbar_expect_tx(full_e, EW_SLOT + (full ? 1024 : 0));
       __syncwarp();
       if (e_gather) {
-        ew_gather_tile(sl, &p.e_map, fb, e4);
-      } else if (elect_one()) {
-        tma::load_2d(sl, &p.e_map, fb, 0, (int)row0);
-        tma::load_2d(sl + 16384, &p.e_map, fb, 32, (int)row0);
-      }
-      __syncwarp();
-    };
-    auto load_pj = [&](int tile, uint32_t slot_i) {
-      const uint32_t row0 = (uint32_t)tile * EW_TM;
-      const int rows_here = (int)min((int64_t)EW_TM, p.n_rows - (int64_t)row0);
-      const uint32_t sl = slots + slot_i * EW_SLOT, fb = full0 + 8 * slot_i;
-      const int4 s4 = ew_idx4(p.src, row0, rows_here, lane, 0);
-      if (lane == 0) tma::mbar_expect_tx(fb, EW_SLOT);
-      __syncwarp();
-      ew_gather_tile(sl, &p.pj_map, fb, s4);
-    };
-    int4 keep_cur = make_int4(0, 0, 0, 0), keep_next = keep_cur;
-    if (tile0 < p.n_tiles) {
-      load_e(tile0, 0, keep_cur);
-      load_pj(tile0, 1);
-    }
-    int t = 0;
-    for (int tile = tile0; tile < p.n_tiles; tile += tstep, ++t) {
-      const uint32_t se = (uint32_t)t & 1u, sp = se ^ 1u;
-      const int k = 3 * t;  // item numbers of this tile: k (e_in), k + 1 (P_j), k + 2 (out); slot = item & 1
-      const bool more = tile + tstep < p.n_tiles;
-      if (more) {  // e_in(t + 1) = item k + 3 -> the slot P_j(t) = item k + 1 leaves after the first epilogue
-        EW_PROF(16);
-        ew_wait(empty0 + 8 * sp, (uint32_t)((k + 1) >> 1) & 1u);
-        EW_PROF(17);
-        load_e(tile + tstep, sp, keep_next);
-        EW_PROF(18);
-      }
-      // out(t) = item k + 2, staged by the row owners in slot se
-      ew_wait(out_ready, (uint32_t)t & 1u);
-      EW_PROF(19);
-      {
-        const uint32_t row0 = (uint32_t)tile * EW_TM;
-        const uint32_t sl = slots + se * EW_SLOT;
-        const int rows_here = (int)min((int64_t)EW_TM, p.n_rows - (int64_t)row0);
-        if (o_scatter) {
-          if (rows_here == EW_TM) ew_scatter_tile(sl, &p.out_map, keep_cur);  // a partial tile is stored by its owners
-        } else if (elect_one()) {
-          tma::store_2d(&p.out_map, sl, 0, (int)row0);  // rows past the end of the table are clipped
-          tma::store_2d(&p.out_map, sl + 16384, 32, (int)row0);
+        const int4 r4 = ew_idx4(p.e_index, row0, rows_here, lane, 0);
+#pragma unroll 4
+        for (int j = 0; j < 32; ++j) {
+          const int a = __shfl_sync(0xffffffffu, r4.x, j), b = __shfl_sync(0xffffffffu, r4.y, j);
+          const int c = __shfl_sync(0xffffffffu, r4.z, j), d = __shfl_sync(0xffffffffu, r4.w, j);
+          if (elect_one()) {
+            tma::gather4(sl + j * 512, &p.e_map, full_e, 0, a, b, c, d);
+            tma::gather4(sl + 16384 + j * 512, &p.e_map, full_e, 32, a, b, c, d);
+          }
+          __syncwarp();
         }
-        __syncwarp();
-        tma::bulk_commit();
       }
-      EW_PROF(20);
-      if (more) {  // P_j(t + 1) = item k + 4 -> the slot out(t) leaves once summed and stored
-        ew_wait(empty0 + 8 * se, (uint32_t)((k + 2) >> 1) & 1u);
-        EW_PROF(21);
-        tma::bulk_wait_read0();
-        __syncwarp();
-        EW_PROF(22);
-        load_pj(tile + tstep, se);
-        EW_PROF(23);
+      if (elect_one()) {
+        if (!e_gather) {
+          tma::load_2d(sl, &p.e_map, full_e, 0, (int)row0);  // rows past the end of the table arrive as zeros
+          tma::load_2d(sl + 16384, &p.e_map, full_e, 32, (int)row0);
+        }
+        if (full) {  // ids of the tile (a partial tile reads them with guarded loads instead)
+          tma::bulk_g2s(ids, p.dst + row0, 512, full_e);
+          tma::bulk_g2s(ids + 512, p.src + row0, 512, full_e);
+        }
       }
-      keep_cur = keep_next;
+      __syncwarp();
+      EW_PROF(19);
     }
-    tma::bulk_wait_all0();
-  } else if (warp < 4) {
+  } else {
     // ================================================================= MMA issue of context `ctx`
+    const int ctx = warp - 18;
+    const uint32_t bars = sm0 + EW_BARS + 64 * ctx;
+    const uint32_t a_ready = bars + 24, d_ready = bars + 32;
+    const uint32_t tmc = (uint32_t)ctx * EW_CTX;
     const uint32_t idesc = make_idesc_tf32(EW_TM, 64);
     int n = 0;  // commits so far
-    for (int tile = tile0; tile < p.n_tiles; tile += tstep) {
+    for (int t = 0; t < n_t[ctx]; ++t) {
 #pragma unroll 1
       for (int l = 0; l < 3; ++l, ++n) {
         EW_PROF(24);
         ew_wait(a_ready, (uint32_t)n & 1u);
         EW_PROF(25);
         tc_fence_after_sync();
-        const uint64_t bd_hi = make_smem_desc_sw128(wbase + (uint32_t)l * 32768u);
-        const uint64_t bd_lo = make_smem_desc_sw128(wbase + (uint32_t)l * 32768u + 16384u);
+        const uint64_t bd_hi = make_smem_desc_sw128(sm0 + (uint32_t)l * 32768u);
+        const uint64_t bd_lo = make_smem_desc_sw128(sm0 + (uint32_t)l * 32768u + 16384u);
         if (elect_one()) {
           bool acc = false;
 #pragma unroll
@@ -292,216 +563,6 @@ __global__ void __launch_bounds__(EW_THREADS, 1) in_edge_ws_kernel(const __grid_
         __syncwarp();
         EW_PROF(26);
       }
-    }
-  } else {
-    // ================================================================= row owners of context `ctx`
-    const int cw = (warp - 4) & 7;                 // warp inside the context
-    const int r = 32 * (warp & 3) + lane, h = cw >> 2;  // TMEM lane quarter = warp % 4
-    const int tt = 32 * cw + lane;
-    const uint32_t tm_lane = tmc + ((uint32_t)((warp & 3) * 32) << 16);
-    const uint32_t rx = (uint32_t)(r & 7) << 4;
-    const uint32_t own = (uint32_t)h * 16384u + (uint32_t)r * 128u;  // own row inside the own K tile of a slot
-    const float* bias = reinterpret_cast<const float*>(smem_raw + EW_HEAD + 98304);
-    const uint32_t pld4 = (uint32_t)p.pi_ld * 4u, ald4 = (uint32_t)p.aggr_ld * 4u;
-    const int c4 = tt & 15, rg0 = (tt >> 4) * 8;   // segmented sum: 16-byte piece c4 of rows rg0 .. rg0 + 7
-    int nd = 0;  // accumulator completions consumed so far
-    int32_t dcur = 0;
-    if (tile0 < p.n_tiles) {
-      const uint32_t row = (uint32_t)tile0 * EW_TM + r;
-      dcur = (int64_t)row < p.n_rows ? __ldg(p.pi_index + row) : 0;
-    }
-    int t = 0;
-    for (int tile = tile0; tile < p.n_tiles; tile += tstep, ++t) {
-      const uint32_t se = (uint32_t)t & 1u, sp = se ^ 1u;
-      const uint32_t row0 = (uint32_t)tile * EW_TM;
-      const int rows_here = (int)min((int64_t)EW_TM, p.n_rows - (int64_t)row0);
-      const uint32_t sl_e = slots + se * EW_SLOT, sl_p = slots + sp * EW_SLOT;
-
-      // ---------------- first Linear's A operand: own 32 columns of the edge-feature row
-      EW_PROF(0);
-      ew_wait(full0 + 8 * se, (uint32_t)t & 1u);
-      EW_PROF(1);
-      {
-        float4 a[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) a[q] = lds128(sl_e + own + (((uint32_t)q << 4) ^ rx));
-#pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          float v[16];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            v[4 * q + 0] = a[4 * b + q].x; v[4 * q + 1] = a[4 * b + q].y;
-            v[4 * q + 2] = a[4 * b + q].z; v[4 * q + 3] = a[4 * b + q].w;
-          }
-          if (RELU_E) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-          }
-          split_store16(tm_lane + EW_A_HI + 32 * h + 16 * b, tm_lane + EW_A_LO + 32 * h + 16 * b, v);
-        }
-      }
-      tmem_st_wait();
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) {
-        tma::mbar_arrive(a_ready);
-        tma::mbar_arrive(empty0 + 8 * se);  // item e_in(t) consumed
-      }
-      EW_PROF(2);
-      // gathered target rows (destination-sorted: neighbouring lanes repeat rows) and next tile's ids,
-      // in flight under the first MMA chain
-      float4 pre[8];
-      {
-        const float* rowp = row_ptr(p.pi + 32 * h, (uint32_t)dcur, pld4);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) pre[q] = __ldg(reinterpret_cast<const float4*>(rowp) + q);
-      }
-      int32_t dnext = 0;
-      if (tile + tstep < p.n_tiles) {
-        const uint32_t row = (uint32_t)(tile + tstep) * EW_TM + r;
-        dnext = (int64_t)row < p.n_rows ? __ldg(p.pi_index + row) : 0;
-      }
-
-      // ---------------- hidden layer 0: D + b0 + P_i[dst] + P_j[src] -> ReLU -> A operand
-      EW_PROF(3);
-      ew_wait(full0 + 8 * sp, (uint32_t)t & 1u);
-      EW_PROF(4);
-      ew_wait(d_ready, (uint32_t)nd & 1u);
-      EW_PROF(5);
-      ++nd;
-      tc_fence_after_sync();
-#pragma unroll
-      for (int b = 0; b < 2; ++b) {
-        const int cb = 32 * h + 16 * b;
-        uint32_t acc[16];
-        tmem_ld16(tm_lane + EW_D + cb, acc);
-        float4 x[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) x[q] = lds128(sl_p + own + (((uint32_t)(4 * b + q) << 4) ^ rx));
-        tmem_ld_wait();
-        float v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
-        const float4* b4 = reinterpret_cast<const float4*>(bias + cb);
-        add16(v, b4[0], b4[1], b4[2], b4[3]);
-        add16(v, pre[4 * b + 0], pre[4 * b + 1], pre[4 * b + 2], pre[4 * b + 3]);
-        add16(v, x[0], x[1], x[2], x[3]);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-        split_store16(tm_lane + EW_A_HI + cb, tm_lane + EW_A_LO + cb, v);
-      }
-      tmem_st_wait();
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) {
-        tma::mbar_arrive(a_ready);
-        tma::mbar_arrive(empty0 + 8 * sp);  // item P_j(t) consumed
-      }
-      EW_PROF(6);
-
-      // ---------------- hidden layer 1
-      ew_wait(d_ready, (uint32_t)nd & 1u);
-      EW_PROF(7);
-      ++nd;
-      tc_fence_after_sync();
-#pragma unroll
-      for (int b = 0; b < 2; ++b) {
-        const int cb = 32 * h + 16 * b;
-        uint32_t acc[16];
-        tmem_ld16(tm_lane + EW_D + cb, acc);
-        tmem_ld_wait();
-        float v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
-        const float4* b4 = reinterpret_cast<const float4*>(bias + 64 + cb);
-        add16(v, b4[0], b4[1], b4[2], b4[3]);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-        split_store16(tm_lane + EW_A_HI + cb, tm_lane + EW_A_LO + cb, v);
-      }
-      tmem_st_wait();
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) tma::mbar_arrive(a_ready);
-      EW_PROF(8);
-
-      // segment ids of the rows this thread will sum (rg0 is a multiple of 8: 32-byte aligned loads)
-      int sg[8];
-      if (rows_here == EW_TM) {
-        const int4 s0 = __ldg(reinterpret_cast<const int4*>(p.dst + row0 + rg0));
-        const int4 s1 = __ldg(reinterpret_cast<const int4*>(p.dst + row0 + rg0) + 1);
-        sg[0] = s0.x; sg[1] = s0.y; sg[2] = s0.z; sg[3] = s0.w; sg[4] = s1.x; sg[5] = s1.y; sg[6] = s1.z; sg[7] = s1.w;
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) sg[i] = rg0 + i < rows_here ? __ldg(p.dst + row0 + rg0 + i) : -1;
-      }
-
-      // ---------------- output Linear: D + b2 -> staged tile (slot se: the thread's own e_in piece is dead)
-      EW_PROF(9);
-      ew_wait(d_ready, (uint32_t)nd & 1u);
-      EW_PROF(10);
-      ++nd;
-      tc_fence_after_sync();
-#pragma unroll
-      for (int b = 0; b < 2; ++b) {
-        const int cb = 32 * h + 16 * b;
-        uint32_t acc[16];
-        tmem_ld16(tm_lane + EW_D + cb, acc);
-        tmem_ld_wait();
-        float v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
-        const float4* b4 = reinterpret_cast<const float4*>(bias + 128 + cb);
-        add16(v, b4[0], b4[1], b4[2], b4[3]);
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          sts128(sl_e + own + (((uint32_t)(4 * b + q) << 4) ^ rx), make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
-      }
-      if (p.out_index != nullptr && rows_here < EW_TM && r < rows_here) {  // partial last tile, scattered rows
-        float* orow = const_cast<float*>(row_ptr(p.out + 32 * h, (uint32_t)__ldg(p.out_index + row0 + r), (uint32_t)p.out_ld * 4u));
-#pragma unroll
-        for (int q = 0; q < 8; ++q) reinterpret_cast<float4*>(orow)[q] = lds128(sl_e + own + (((uint32_t)q << 4) ^ rx));
-      }
-      fence_proxy_async_smem();  // the TMA store reads the tile through the async proxy
-      __syncwarp();
-      if (lane == 0) tma::mbar_arrive(out_ready);
-      EW_PROF(11);
-
-      // ---------------- in-tile segmented sum by destination: one vector reduction per run inside 8 rows
-      ew_wait(out_ready, (uint32_t)t & 1u);
-      EW_PROF(12);
-      if (rg0 < rows_here) {
-        float4 v[8];
-        const uint32_t colb = sl_e + (uint32_t)(c4 >> 3) * 16384u + (uint32_t)rg0 * 128u;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = lds128(colb + (uint32_t)i * 128u + ((((uint32_t)c4 & 7u) ^ (uint32_t)i) << 4));
-        int cur = sg[0];
-        f32x2 s01 = pack2(0.f, 0.f), s23 = s01;
-        auto flush = [&](int seg) {
-          float4 sum;
-          unpack2(s01, sum.x, sum.y);
-          unpack2(s23, sum.z, sum.w);
-          red_add_v4(row_ptr(p.aggr + 4 * c4, (uint32_t)seg, ald4), sum);
-        };
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (sg[i] < 0) break;
-          if (sg[i] != cur) {
-            flush(cur);
-            cur = sg[i];
-            s01 = pack2(0.f, 0.f);
-            s23 = s01;
-          }
-          s01 = add2(s01, pack2(v[i].x, v[i].y));
-          s23 = add2(s23, pack2(v[i].z, v[i].w));
-        }
-        flush(cur);
-      }
-      __syncwarp();
-      if (lane == 0) tma::mbar_arrive(empty0 + 8 * se);  // item out(t) consumed by the owners
-      EW_PROF(13);
-      if (PROF && prof_on) g_ew_prof[15] += 1;
-      dcur = dnext;
     }
   }
 
@@ -543,8 +604,9 @@ static bool ew_match(const gtb_mlp_desc_t& d, int* s_e, int* s_pi, int* s_pj) {
   return true;
 }
 
-// n_table_rows: rows of the gathered tables are not part of the C descriptor; the TMA map only needs an
-// upper bound for its bounds check, the indices are the plan's (validated when the plan is built).
+// The rows of the gathered tables are not part of the C descriptor; a TMA map only needs an upper bound for
+// its bounds check, the indices are the plan's (clamped into their tables when the plan is built).  The
+// projected block flagged SORTED (P_i) must be indexed by seg_id itself: one id array serves both.
 int in_edge_ws(const gtb_mlp_desc_t& d, cudaStream_t st, bool* handled) {
   *handled = false;
   static const bool disabled = getenv("GTB_NO_EDGE_WS") != nullptr;
@@ -559,35 +621,32 @@ int in_edge_ws(const gtb_mlp_desc_t& d, cudaStream_t st, bool* handled) {
   const uint64_t e_rows = e_gather ? big : (uint64_t)d.n_rows, o_rows = o_scatter ? big : (uint64_t)d.n_rows;
   if (!tma::make_map_2d(&p.e_map, se.ptr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, e_rows, 64, (uint64_t)se.ld, 32, e_gather ? 1 : 128) ||
       !tma::make_map_2d(&p.pj_map, spj.ptr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, big, 64, (uint64_t)spj.ld, 32, 1) ||
-      !tma::make_map_2d(&p.out_map, d.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, o_rows, 64, (uint64_t)d.out_ld, 32, o_scatter ? 1 : 128))
+      !tma::make_map_2d(&p.out_map, d.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, o_rows, 64, (uint64_t)d.out_ld, 32, o_scatter ? 1 : 8))
     return GTB_OK;  // the driver refused a map: the generic tiles take the launch
   p.pi = spi.ptr;
   p.pi_ld = spi.ld;
   p.dst = d.seg_id;
-  p.pi_index = spi.index;
   p.src = spj.index;
   p.e_index = se.index;
   p.out_index = d.out_index;
   p.aggr = d.aggr;
   p.aggr_ld = d.aggr_ld;
   p.packed = static_cast<const unsigned char*>(d.packed);
-  p.w_bytes = 99072;
   p.n_rows = d.n_rows;
   p.n_tiles = (int32_t)((d.n_rows + EW_TM - 1) / EW_TM);
   p.out = d.out;
   p.out_ld = d.out_ld;
   *handled = true;
   if (d.n_rows == 0) return GTB_OK;
-  static bool configured[64] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev >= 0 && dev < 64 && !configured[dev]) {
+  static PerDeviceOnce once;
+  bool& configured = *once.slot();
+  if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(in_edge_ws_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EW_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(in_edge_ws_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EW_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(in_edge_ws_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EW_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(in_edge_ws_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EW_SMEM);
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(in_edge_ws)");
-    configured[dev] = true;
+    configured = true;
   }
   const int pairs = (p.n_tiles + 1) / 2;
   const int grid = pairs < kNumSMs ? pairs : kNumSMs;

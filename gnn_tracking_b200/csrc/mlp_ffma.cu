@@ -301,7 +301,8 @@ int pack_ffma(int n_layers, const int32_t* dims, const float* const* weights, co
 template <int NC>
 static int launch_ffma(const gtb_mlp_desc_t& d, const FfmaLayout& L, cudaStream_t st) {
   const size_t smem = Smem<NC>::bytes(d.n_srcs);
-  static bool configured = false;  // one process drives one GPU (one rank per device)
+  static PerDeviceOnce once;
+  bool& configured = *once.slot();
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(fused_mlp_ffma_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)Smem<NC>::bytes(GTB_MAX_SRCS));

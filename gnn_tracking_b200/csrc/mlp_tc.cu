@@ -258,6 +258,9 @@ __device__ __forceinline__ uint32_t slot_off(int r, int c4) {  // 16-byte chunk 
 }
 
 __device__ __forceinline__ void wait_or_trap(uint32_t bar_addr, uint32_t parity) {
+  // NOT unrolled: ptxas otherwise replicates the try_wait 64 times per wait site (100 KB of SASS: every
+  // stage change then misses the instruction cache)
+#pragma unroll 1
   for (uint32_t i = 0; i < 20000000u; ++i) {
     uint32_t ok;
     asm volatile(
@@ -1193,7 +1196,8 @@ int fused_mlp_tc(const gtb_mlp_desc_t& d, cudaStream_t st) {
   }
   if (d.n_rows == 0) return GTB_OK;
   const size_t smem = fixed + (size_t)p.ring * p.n_teams * TC_SLOT;
-  static bool configured = false;  // one process drives one GPU (one rank per device)
+  static PerDeviceOnce once;
+  bool& configured = *once.slot();
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(fused_mlp_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_MAX);
     if (e == cudaSuccess)

@@ -27,6 +27,16 @@ class PackedCache:
         self._packed: list[PackedMLP] = []
         self._proj: dict[int, PackedMLP] = {}
 
+    def invalidate(self) -> None:
+        """Forget the packed copies (and the backward's, ``autograd._BwdPacks``).  The cache key is
+        (storage pointer, ``_version``) per parameter, which sees optimizer steps, ``load_state_dict``
+        and ``.to()``; writes through ``param.data`` (``p.data.clamp_()``, EMA / SWA copies, legacy
+        optimizers) do NOT bump ``_version`` -- call ``invalidate_packed_weights(model)`` after them."""
+        self._key = None
+        self._packed, self._proj = [], {}
+        if hasattr(self, "bwd"):
+            del self.bwd
+
     @staticmethod
     def _groups(linears, widths, projected, impl):
         """<= 3 Linear layers per launch.  With the tcgen05 tiles a 3-layer chain whose weights
@@ -72,6 +82,29 @@ class PackedCache:
                 self._packed.append(ops.pack_linears(ws, bs, impl, block_widths=bw))
             self._key = key
         return self._packed, self._proj
+
+
+def invalidate_packed_weights(module: nn.Module) -> None:
+    """Drops every packed-weight cache below ``module``: the next forward re-packs from the live
+    parameters.  Needed after in-place writes through ``param.data`` (see ``PackedCache.invalidate``);
+    ``.to()`` / ``.cuda()`` / ``load_state_dict`` call it themselves."""
+    for m in module.modules():
+        for v in vars(m).values():
+            for c in (v if isinstance(v, (list, tuple)) else (v,)):
+                if isinstance(c, PackedCache):
+                    c.invalidate()
+
+
+class _PackedWeightsMixin:
+    """``_apply`` (``.to`` / ``.cuda`` / ``.float``) and ``load_state_dict`` invalidate the packed copies."""
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        invalidate_packed_weights(self)
+        return out
+
+    def _hook_state_dict(self) -> None:
+        self.register_load_state_dict_post_hook(lambda module, incompatible_keys: invalidate_packed_weights(module))
 
 
 def _run_nograd(cache: PackedCache, linears: Sequence[nn.Linear], blocks: Sequence[Block], n_rows: int,
@@ -154,7 +187,7 @@ def run_linears(cache: PackedCache, linears: Sequence[nn.Linear], blocks: Sequen
                               seg_id=epilogue.get("seg_id"), rowptr=epilogue.get("rowptr"))
 
 
-class MLP(nn.Module):
+class MLP(_PackedWeightsMixin, nn.Module):
     def __init__(self, input_size: int, output_size: int, hidden_dim: int | None, L: int = 3, *,
                  bias: bool = True, include_last_activation: bool = False):
         """Linear/ReLU chain: 1 input layer, ``L - 2`` hidden layers, 1 output layer.
@@ -174,6 +207,7 @@ class MLP(nn.Module):
         self.layers = nn.ModuleList(mods)
         self._last_act = include_last_activation
         self._cache = PackedCache()
+        self._hook_state_dict()
 
     @property
     def linears(self) -> list[nn.Linear]:
@@ -202,7 +236,7 @@ class MLP(nn.Module):
         return self.forward_blocks([Block(x)], x.size(0))
 
 
-class ResFCNN(nn.Module):
+class ResFCNN(_PackedWeightsMixin, nn.Module):
     def __init__(self, *, in_dim: int, hidden_dim: int, out_dim: int, depth: int, alpha: float = 0.6,
                  bias: bool = True):
         """L2-normalise rows -> encoder -> (depth-1) residual hidden layers
@@ -222,6 +256,7 @@ class ResFCNN(nn.Module):
         self._alpha = alpha
         self._cache = PackedCache()
         self._layer_caches = [PackedCache() for _ in range(depth)]
+        self._hook_state_dict()
 
     @staticmethod
     def _init(layer: nn.Linear, var: float) -> None:

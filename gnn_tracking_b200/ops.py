@@ -54,6 +54,26 @@ def stream_ptr(dev: torch.device) -> int:
     return torch.cuda.current_stream(dev).cuda_stream
 
 
+class on_device:
+    """Makes ``dev`` the current CUDA device around a library call when it is not already (tensors on
+    cuda:1 while cuda:0 is current): kernel attributes and launches are per device.  A no-op -- one
+    integer compare -- in the usual one-process-per-GPU set-up."""
+
+    __slots__ = ("_guard",)
+
+    def __init__(self, dev: torch.device):
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        self._guard = torch.cuda.device(idx) if idx != torch.cuda.current_device() else None
+
+    def __enter__(self):
+        if self._guard is not None:
+            self._guard.__enter__()
+
+    def __exit__(self, *exc):
+        if self._guard is not None:
+            self._guard.__exit__(*exc)
+
+
 def default_impl() -> int:
     """GTB_IMPL_AUTO unless ``GTB_IMPL`` = ffma | tcgen05 forces one."""
     v = os.environ.get("GTB_IMPL", "auto").lower()
@@ -151,7 +171,8 @@ def pack_linears(weights: Sequence[Tensor], biases: Sequence[Tensor | None], imp
     bs = [None if b is None else b.detach().to(torch.float32).contiguous() for b in biases]
     wp = (C.c_void_p * n)(*[w.data_ptr() for w in ws])
     bp = (C.c_void_p * n)(*[(b.data_ptr() if b is not None else None) for b in bs])
-    check(lib().gtb_mlp_pack(n, dims_c, len(bw), bw_c, wp, bp, impl, buf.data_ptr(), stream_ptr(dev)))
+    with on_device(dev):
+        check(lib().gtb_mlp_pack(n, dims_c, len(bw), bw_c, wp, bp, impl, buf.data_ptr(), stream_ptr(dev)))
     _count(n if impl == IMPL_FFMA else 1)
     return PackedMLP(buf, tuple(dims), impl, tuple(bw))
 
@@ -212,7 +233,8 @@ def fused_mlp(blocks: Sequence[Block], n_rows: int, packed: PackedMLP, *, final_
         d.aggr, d.aggr_ld = aggr.data_ptr(), aggr.stride(0)
         d.seg_id, d.rowptr = _idx(seg_id), _idx(rowptr)
     if n_rows > 0:  # an empty edge set (E = 0) launches nothing; `out` is empty, `aggr` stays zero
-        check(lib().gtb_fused_mlp_f32(C.byref(d), stream_ptr(dev)))
+        with on_device(dev):
+            check(lib().gtb_fused_mlp_f32(C.byref(d), stream_ptr(dev)))
         _count(1)
     del keep
     return out if want_out else None

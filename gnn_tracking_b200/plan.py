@@ -77,8 +77,9 @@ def build_plan(edge_index: Tensor, n_nodes: int) -> GraphPlan:
     status = torch.empty(1, **i32)
     ws_bytes = lib().gtb_plan_workspace_bytes(n_nodes, e)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    check(lib().gtb_plan_build(ei.data_ptr(), n_nodes, e, perm.data_ptr(), rowptr.data_ptr(), src.data_ptr(),
-                               dst.data_ptr(), status.data_ptr(), ws.data_ptr(), ws_bytes, ops.stream_ptr(dev)))
+    with ops.on_device(dev):
+        check(lib().gtb_plan_build(ei.data_ptr(), n_nodes, e, perm.data_ptr(), rowptr.data_ptr(), src.data_ptr(),
+                                   dst.data_ptr(), status.data_ptr(), ws.data_ptr(), ws_bytes, ops.stream_ptr(dev)))
     ops._count(6)  # keys, radix-sort passes, rowptr
     _defer_status_check(status)
     return GraphPlan(n_nodes, e, perm, rowptr, src, dst, status)

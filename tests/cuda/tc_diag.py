@@ -145,13 +145,12 @@ def run_case(i: int) -> None:
                     buf = (_lib.C.c_longlong * 32)()
                     L.gtb_debug_tc_profile(2, buf)
                     L.gtb_debug_tc_profile(0, None)
-                    tiles = max(1, buf[15])
-                    names = {0: "own:loop", 1: "own:wait e", 2: "own:conv0", 3: "own:Pi loads", 4: "own:wait Pj", 5: "own:wait d0",
-                             6: "own:epi0", 7: "own:wait d1", 8: "own:epi1", 9: "own:seg ids", 10: "own:wait d2", 11: "own:epi2",
-                             12: "own:wait out", 13: "own:aggr", 16: "prod:loop", 17: "prod:wait empty e", 18: "prod:issue e",
-                             19: "prod:wait out", 20: "prod:issue store", 21: "prod:wait empty out", 22: "prod:wait read",
-                             23: "prod:issue Pj", 24: "mma:loop", 25: "mma:wait a", 26: "mma:issue"}
-                    msg += "\n    ew prof (cycles per tile, ctx 0 / CTA 0, %d tiles): " % tiles + ", ".join(
+                    tiles = max(1, buf[31])
+                    names = {0: "c0:pre", 1: "c0:wait e", 2: "c0:body", 3: "e0:pre", 4: "e0:wait Pj", 5: "e0:wait d", 6: "e0:body",
+                             7: "e1:pre", 8: "e1:wait d", 9: "e1:body", 10: "e2:pre", 11: "e2:wait d", 12: "e2:body",
+                             13: "ag:pre", 14: "ag:wait out", 15: "ag:body", 16: "ag:refill Pj", 17: "prod:loop",
+                             18: "prod:wait free", 19: "prod:issue", 24: "mma:loop", 25: "mma:wait a", 26: "mma:issue"}
+                    msg += "\n    ew prof (cycles per PAIR of tiles, warp 0 / CTA 0, both contexts; prod / mma: context A; %d pairs): " % tiles + ", ".join(
                         f"{nm} {buf[i] / tiles:.0f}" for i, nm in names.items())
                 if os.environ.get("TC_PROF"):
                     L = _lib.lib()
