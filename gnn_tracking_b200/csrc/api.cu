@@ -31,6 +31,9 @@ int fused_mlp_tc(const gtb_mlp_desc_t&, cudaStream_t);
 int in_edge_ws(const gtb_mlp_desc_t&, cudaStream_t, bool*);
 int ew_fault_flag(int*);
 int ew_profile(int, long long*);
+int ew_pack_bf16(const float* const*, const float* const*, void*, cudaStream_t);
+int in_edge_ws_bf16(const void*, int32_t, const int32_t*, int32_t, const void*, int32_t, const void*, int32_t, int64_t,
+                    const int32_t*, const int32_t*, const void*, void*, int32_t, const int32_t*, float*, int32_t, cudaStream_t);
 int tc_timeout_flag(int*);
 int oc_potentials_grad(const float*, const float*, int32_t, const int64_t*, const int32_t*, int64_t, const int32_t*, int32_t,
                        float, int64_t, const float*, float*, float*, float*, cudaStream_t);
@@ -115,6 +118,20 @@ int gtb_debug_tc_profile(int enable, long long* out32) {
     return rc != GTB_OK ? rc : ew_profile((enable >> 1) & 1, nullptr);
   }
   return enable == 2 ? ew_profile(0, out32) : tc_profile(enable, out32);
+}
+
+size_t gtb_in_edge_bf16_packed_bytes(void) { return 99072; }
+
+int gtb_in_edge_bf16_pack(const float* const* weights, const float* const* biases, void* packed, void* stream) {
+  return ew_pack_bf16(weights, biases, packed, static_cast<cudaStream_t>(stream));
+}
+
+int gtb_in_edge_forward_bf16(const void* e_in, int32_t e_ld, const int32_t* e_index, int32_t relu_e, const void* p_i,
+                             int32_t pi_ld, const void* p_j, int32_t pj_ld, int64_t n_edges, const int32_t* src_sorted,
+                             const int32_t* dst_sorted, const void* packed, void* e_out, int32_t eo_ld,
+                             const int32_t* out_index, float* aggr, int32_t aggr_ld, void* stream) {
+  return in_edge_ws_bf16(e_in, e_ld, e_index, relu_e, p_i, pi_ld, p_j, pj_ld, n_edges, src_sorted, dst_sorted, packed, e_out,
+                         eo_ld, out_index, aggr, aggr_ld, static_cast<cudaStream_t>(stream));
 }
 
 int gtb_arch_ok(int device) {

@@ -34,6 +34,8 @@
 //     slot ring needs no producer round trip: per context two 32 KB slots carry e_in(t), P_j(t), out(t).
 //   * shared memory: weights 96 KB (3 x hi / lo x 16 KB, the image gtb_mlp_pack writes) | 4 slots |
 //     biases, ids, barriers = 227 KB.  TMEM: 192 columns per context (A hi | A lo | D).
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "tma_common.cuh"
@@ -73,13 +75,13 @@ struct EwParams {
   CUtensorMap e_map;     // e_in  [E, 64] fp32: box 32 x 128 (tile mode) or 32 x 1 (gather mode)
   CUtensorMap pj_map;    // P_j   [N, 64] fp32: box 32 x 1
   CUtensorMap out_map;   // e_out [E, 64] fp32: box 32 x 8 (tile mode) or 32 x 1 (scatter mode)
-  const float* pi;       // P_i [N, pi_ld], rows addressed by dst
+  const void* pi;        // P_i [N, pi_ld], rows addressed by dst (fp32, or bf16 in the bf16 variant)
   const int32_t* dst;    // dst_sorted [E]: P_i row and segment id of every edge
   const int32_t* src;    // src_sorted [E]
   const int32_t* e_index;    // perm or nullptr (tile mode)
   const int32_t* out_index;  // perm or nullptr (tile mode)
   float* aggr;
-  float* out;            // e_out base (scatter mode: a partial last tile is stored with plain stores)
+  void* out;             // e_out base (scatter mode: a partial last tile is stored with plain stores)
   const unsigned char* packed;
   int64_t n_rows;
   int32_t n_tiles, pi_ld, aggr_ld, out_ld;
@@ -126,8 +128,12 @@ __device__ __noinline__ void ew_timeout() {
 // state of the 512 row owners.  The context c is a RUN-TIME value: one copy of every stage serves both
 // contexts (the loop body stays inside the instruction cache); the only per-context registers are the
 // four segment ids a lane sums in AG, selected with c.
-template <bool RELU_E, bool PROF>
+template <bool BF, bool RELU_E, bool PROF>
 struct EwOwner {
+  static constexpr uint32_t ES = BF ? 2u : 4u;            // bytes per element of the tables
+  static constexpr int KT = BF ? 64 : 32;                 // columns of one 128-byte K tile
+  static constexpr uint32_t TA = 0, TD = BF ? 64u : 128u;  // TMEM columns: A operand (bf16: 64 columns; fp32: hi | lo), accumulator
+
   const EwParams& p;
   uint32_t sm0;
   int w, lane, r, qd;       // warp 0..15, row 32 (w & 3) + lane, column quarter w >> 2
@@ -153,6 +159,39 @@ struct EwOwner {
     tc_fence_before_sync();
     arrive(bar(c, 3));
   }
+  __device__ __forceinline__ static float4 u2f(const uint4& u) {
+    return make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+  }
+  // own quarter (64 bytes) of row d of P_i
+  __device__ __forceinline__ const void* pi_row(int32_t d) const {
+    return reinterpret_cast<const char*>(p.pi) + (uint64_t)(uint32_t)d * ((uint32_t)p.pi_ld * ES) + 64u * (uint32_t)qd;
+  }
+  // ---- bf16 variant: own 32 columns
+  __device__ __forceinline__ void acc_load32(int c, int t, int l, float (&v)[32]) {
+    ew_wait(bar(c, 4), (uint32_t)(t + l) & 1u);
+    tc_fence_after_sync();
+    uint32_t a0[16], a1[16];
+    tmem_ld16(tm_lane(c) + TD + 32 * qd, a0);
+    tmem_ld16(tm_lane(c) + TD + 32 * qd + 16, a1);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      v[j] = __uint_as_float(a0[j]);
+      v[16 + j] = __uint_as_float(a1[j]);
+    }
+  }
+  __device__ __forceinline__ void bias_add32(float (&v)[32], int layer) {
+    const uint32_t ba = sm0 + EW_BIAS + 256 * layer + 64 * qd;
+    bf2_add16(v, 0, lds128u(ba), lds128u(ba + 16));
+    bf2_add16(v, 16, lds128u(ba + 32), lds128u(ba + 48));
+  }
+  // Linear output rounded to bf16 (what autocast's Linear returns), ReLU, into the next A operand
+  __device__ __forceinline__ void act_store32(int c, const float (&v)[32]) {
+    uint32_t a[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[j] = bf2_relu(bf2_pack_rn(v[2 * j], v[2 * j + 1]));
+    tmem_st16(tm_lane(c) + TA + 16 * qd, a);
+  }
   __device__ __forceinline__ void bias_add(float (&v)[16], int layer) {
     const uint32_t ba = sm0 + EW_BIAS + 256 * layer + 64 * qd;
     add16(v, lds128(ba), lds128(ba + 16), lds128(ba + 32), lds128(ba + 48));
@@ -177,24 +216,40 @@ struct EwOwner {
     EW_PROF(0);
     ew_wait(bar(c, 0), (uint32_t)t & 1u);
     EW_PROF(1);
-    {  // the target row of P_i is read in E0, a Linear from now: start it towards L1
+    const void* pi_line;
+    {  // the target row of P_i is read in E0, a Linear from now: start it towards L1 at the end of this stage
       int32_t d = 0;
       if (rows_here == EW_TM) d = lds_i32(ids(c) + 4 * r);
       else if (r < rows_here) d = __ldg(p.dst + row0 + r);
-      prefetch_l1(row_ptr(p.pi + 16 * qd, (uint32_t)d, (uint32_t)p.pi_ld * 4u));
+      pi_line = pi_row(d);
     }
-    float v[16];
+    if constexpr (BF) {  // 32 bf16 columns = 16 words, straight into the A operand
+      uint32_t a[16];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float4 a = lds128(sl + own + chunk(q));
-      v[4 * q + 0] = a.x; v[4 * q + 1] = a.y; v[4 * q + 2] = a.z; v[4 * q + 3] = a.w;
-    }
-    if (RELU_E) {
+      for (int q = 0; q < 4; ++q) {
+        const uint4 x = lds128u(sl + own + chunk(q));
+        a[4 * q + 0] = x.x; a[4 * q + 1] = x.y; a[4 * q + 2] = x.z; a[4 * q + 3] = x.w;
+      }
+      if (RELU_E) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+        for (int j = 0; j < 16; ++j) a[j] = bf2_relu(a[j]);
+      }
+      tmem_st16(tm_lane(c) + TA + 16 * qd, a);
+    } else {
+      float v[16];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 a = lds128(sl + own + chunk(q));
+        v[4 * q + 0] = a.x; v[4 * q + 1] = a.y; v[4 * q + 2] = a.z; v[4 * q + 3] = a.w;
+      }
+      if (RELU_E) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      split_store16(tm_lane(c) + EW_A_HI + 16 * qd, tm_lane(c) + EW_A_LO + 16 * qd, v);
     }
-    split_store16(tm_lane(c) + EW_A_HI + 16 * qd, tm_lane(c) + EW_A_LO + 16 * qd, v);
     a_done(c);
+    prefetch_l1(pi_line);
     EW_PROF(2);
   }
 
@@ -204,12 +259,12 @@ struct EwOwner {
     const uint32_t row0 = (uint32_t)tile * EW_TM;
     const int rows_here = (int)min((int64_t)EW_TM, p.n_rows - (int64_t)row0);
     const uint32_t sl = slot(c, ((uint32_t)t & 1u) ^ 1u);
-    float4 pre[4];
+    uint4 pre[4];
     {
       int32_t d = 0;
       if (rows_here == EW_TM) d = lds_i32(ids(c) + 4 * r);
       else if (r < rows_here) d = __ldg(p.dst + row0 + r);
-      const float4* rowp = reinterpret_cast<const float4*>(row_ptr(p.pi + 16 * qd, (uint32_t)d, (uint32_t)p.pi_ld * 4u));
+      const uint4* rowp = reinterpret_cast<const uint4*>(pi_row(d));
 #pragma unroll
       for (int q = 0; q < 4; ++q) pre[q] = __ldg(rowp + q);
     }
@@ -230,18 +285,33 @@ struct EwOwner {
     EW_PROF(3);
     ew_wait(bar(c, 1), (uint32_t)t & 1u);
     EW_PROF(4);
-    float v[16];
-    acc_load(c, t, 0, v);
-    EW_PROF(5);
-    float4 x[4];
+    if constexpr (BF) {
+      float v[32];
+      acc_load32(c, t, 0, v);
+      EW_PROF(5);
+      uint4 x[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) x[q] = lds128(sl + own + chunk(q));
-    bias_add(v, 0);
-    add16(v, pre[0], pre[1], pre[2], pre[3]);
-    add16(v, x[0], x[1], x[2], x[3]);
+      for (int q = 0; q < 4; ++q) x[q] = lds128u(sl + own + chunk(q));
+      bias_add32(v, 0);
+      bf2_add16(v, 0, pre[0], pre[1]);
+      bf2_add16(v, 16, pre[2], pre[3]);
+      bf2_add16(v, 0, x[0], x[1]);
+      bf2_add16(v, 16, x[2], x[3]);
+      act_store32(c, v);
+    } else {
+      float v[16];
+      acc_load(c, t, 0, v);
+      EW_PROF(5);
+      float4 x[4];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-    split_store16(tm_lane(c) + EW_A_HI + 16 * qd, tm_lane(c) + EW_A_LO + 16 * qd, v);
+      for (int q = 0; q < 4; ++q) x[q] = lds128(sl + own + chunk(q));
+      bias_add(v, 0);
+      add16(v, u2f(pre[0]), u2f(pre[1]), u2f(pre[2]), u2f(pre[3]));
+      add16(v, x[0], x[1], x[2], x[3]);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+      split_store16(tm_lane(c) + EW_A_HI + 16 * qd, tm_lane(c) + EW_A_LO + 16 * qd, v);
+    }
     tmem_st_wait();
     tc_fence_before_sync();
     __syncwarp();
@@ -255,13 +325,21 @@ struct EwOwner {
   // ---- E1: D + b1 -> ReLU -> A operand of the third Linear
   __device__ __forceinline__ void e1(int c, int t) {
     EW_PROF(7);
-    float v[16];
-    acc_load(c, t, 1, v);
-    EW_PROF(8);
-    bias_add(v, 1);
+    if constexpr (BF) {
+      float v[32];
+      acc_load32(c, t, 1, v);
+      EW_PROF(8);
+      bias_add32(v, 1);
+      act_store32(c, v);
+    } else {
+      float v[16];
+      acc_load(c, t, 1, v);
+      EW_PROF(8);
+      bias_add(v, 1);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
-    split_store16(tm_lane(c) + EW_A_HI + 16 * qd, tm_lane(c) + EW_A_LO + 16 * qd, v);
+      for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+      split_store16(tm_lane(c) + EW_A_HI + 16 * qd, tm_lane(c) + EW_A_LO + 16 * qd, v);
+    }
     a_done(c);
     EW_PROF(9);
   }
@@ -270,12 +348,23 @@ struct EwOwner {
   __device__ __forceinline__ void e2(int c, int t) {
     const uint32_t sl = slot(c, (uint32_t)t & 1u);
     EW_PROF(10);
-    float v[16];
-    acc_load(c, t, 2, v);
-    EW_PROF(11);
-    bias_add(v, 2);
+    if constexpr (BF) {
+      float v[32];
+      acc_load32(c, t, 2, v);
+      EW_PROF(11);
+      bias_add32(v, 2);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) sts128(sl + own + chunk(q), make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+      for (int q = 0; q < 4; ++q)
+        sts128u(sl + own + chunk(q), make_uint4(bf2_pack_rn(v[8 * q + 0], v[8 * q + 1]), bf2_pack_rn(v[8 * q + 2], v[8 * q + 3]),
+                                                bf2_pack_rn(v[8 * q + 4], v[8 * q + 5]), bf2_pack_rn(v[8 * q + 6], v[8 * q + 7])));
+    } else {
+      float v[16];
+      acc_load(c, t, 2, v);
+      EW_PROF(11);
+      bias_add(v, 2);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) sts128(sl + own + chunk(q), make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+    }
     tc_fence_before_sync();
     fence_proxy_async_smem();  // the TMA store reads the tile through the async proxy
     arrive(bar(c, 5));
@@ -288,12 +377,26 @@ struct EwOwner {
     const uint32_t row0 = (uint32_t)tile * EW_TM;
     const int rows_here = (int)min((int64_t)EW_TM, p.n_rows - (int64_t)row0);
     ew_wait(bar(c, 0), (uint32_t)t & 1u);  // the ids of tile t travel with its edge-feature tile
-    int32_t s = 0;
-    if (lane < 8) {
-      if (rows_here == EW_TM) s = lds_i32(ids(c) + 512 + 4 * (8 * w + lane));
-      else if (8 * w + lane < rows_here) s = __ldg(p.src + row0 + 8 * w + lane);
-    }
     const uint32_t fb = bar(c, 1);
+    const uint32_t d0 = sl + (uint32_t)(8 * w) * 128u;
+    if (rows_here == EW_TM) {
+      // one lane: eight ids from shared memory -> uniform registers -> four gather4 (no shuffles, no re-convergence)
+      if (elect_one()) {
+        int4 s0, s1;
+        const uint32_t ia = ids(c) + 512 + 32 * w;
+        asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(s0.x), "=r"(s0.y), "=r"(s0.z), "=r"(s0.w) : "r"(ia) : "memory");
+        asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(s1.x), "=r"(s1.y), "=r"(s1.z), "=r"(s1.w) : "r"(ia + 16) : "memory");
+        tma::mbar_expect_tx(fb, 8 * 256);
+        tma::gather4(d0, &p.pj_map, fb, 0, s0.x, s0.y, s0.z, s0.w);
+        tma::gather4(d0 + 16384u, &p.pj_map, fb, KT, s0.x, s0.y, s0.z, s0.w);
+        tma::gather4(d0 + 512u, &p.pj_map, fb, 0, s1.x, s1.y, s1.z, s1.w);
+        tma::gather4(d0 + 16384u + 512u, &p.pj_map, fb, KT, s1.x, s1.y, s1.z, s1.w);
+      }
+      __syncwarp();
+      return;
+    }
+    int32_t s = 0;  // partial last tile: guarded loads, rows past the end gather row 0
+    if (lane < 8 && 8 * w + lane < rows_here) s = __ldg(p.src + row0 + 8 * w + lane);
     if (lane == 0) tma::mbar_expect_tx(fb, 8 * 256);
     __syncwarp();
 #pragma unroll
@@ -301,8 +404,8 @@ struct EwOwner {
       const int a = __shfl_sync(0xffffffffu, s, 4 * j + 0), b = __shfl_sync(0xffffffffu, s, 4 * j + 1);
       const int cc = __shfl_sync(0xffffffffu, s, 4 * j + 2), d = __shfl_sync(0xffffffffu, s, 4 * j + 3);
       if (elect_one()) {
-        tma::gather4(sl + (uint32_t)(8 * w + 4 * j) * 128u, &p.pj_map, fb, 0, a, b, cc, d);
-        tma::gather4(sl + 16384u + (uint32_t)(8 * w + 4 * j) * 128u, &p.pj_map, fb, 32, a, b, cc, d);
+        tma::gather4(d0 + (uint32_t)(4 * j) * 128u, &p.pj_map, fb, 0, a, b, cc, d);
+        tma::gather4(d0 + 16384u + (uint32_t)(4 * j) * 128u, &p.pj_map, fb, KT, a, b, cc, d);
       }
       __syncwarp();
     }
@@ -322,7 +425,7 @@ struct EwOwner {
       if (p.out_index == nullptr) {
         if (elect_one()) {  // rows past the end of the table are clipped
           tma::store_2d(&p.out_map, sl + (uint32_t)(8 * w) * 128u, 0, (int)row0 + 8 * w);
-          tma::store_2d(&p.out_map, sl + 16384u + (uint32_t)(8 * w) * 128u, 32, (int)row0 + 8 * w);
+          tma::store_2d(&p.out_map, sl + 16384u + (uint32_t)(8 * w) * 128u, KT, (int)row0 + 8 * w);
         }
         __syncwarp();
       } else if (rows_here == EW_TM) {
@@ -333,7 +436,7 @@ struct EwOwner {
           const int cc = __shfl_sync(0xffffffffu, o, 4 * j + 2), d = __shfl_sync(0xffffffffu, o, 4 * j + 3);
           if (elect_one()) {
             tma::scatter4(&p.out_map, sl + (uint32_t)(8 * w + 4 * j) * 128u, 0, a, b, cc, d);
-            tma::scatter4(&p.out_map, sl + 16384u + (uint32_t)(8 * w + 4 * j) * 128u, 32, a, b, cc, d);
+            tma::scatter4(&p.out_map, sl + 16384u + (uint32_t)(8 * w + 4 * j) * 128u, KT, a, b, cc, d);
           }
           __syncwarp();
         }
@@ -342,46 +445,76 @@ struct EwOwner {
         for (int i = 0; i < 4; ++i) {
           const int row = 8 * w + 2 * i + (lane >> 4), cc = lane & 15;
           if (row < rows_here) {
-            const float4 v = lds128(sl + (uint32_t)(cc >> 3) * 16384u + (uint32_t)row * 128u + ((((uint32_t)cc & 7u) ^ ((uint32_t)row & 7u)) << 4));
-            float* orow = const_cast<float*>(row_ptr(p.out, (uint32_t)__ldg(p.out_index + row0 + row), (uint32_t)p.out_ld * 4u));
-            reinterpret_cast<float4*>(orow)[cc] = v;
+            const uint4 v = lds128u(sl + (uint32_t)(cc >> 3) * 16384u + (uint32_t)row * 128u + ((((uint32_t)cc & 7u) ^ ((uint32_t)row & 7u)) << 4));
+            char* orow = reinterpret_cast<char*>(p.out) + (uint64_t)(uint32_t)__ldg(p.out_index + row0 + row) * ((uint32_t)p.out_ld * ES);
+            reinterpret_cast<uint4*>(orow)[cc] = v;
           }
         }
       }
       tma::bulk_commit();
       // one vector reduction (red.global.add.v4.f32) per run of equal destinations inside 4 rows
       const int c4 = lane & 15, rr0 = 8 * w + 4 * (lane >> 4);
-      float4 v[4];
+      uint4 v[4];
       const uint32_t colb = sl + (uint32_t)(c4 >> 3) * 16384u + (uint32_t)rr0 * 128u;
 #pragma unroll
       for (int i = 0; i < 4; ++i)  // (rr0 + i) & 7 == 4 (lane >> 4) + i
-        v[i] = lds128(colb + (uint32_t)i * 128u + ((((uint32_t)c4 & 7u) ^ (uint32_t)(4 * (lane >> 4) + i)) << 4));
+        v[i] = lds128u(colb + (uint32_t)i * 128u + ((((uint32_t)c4 & 7u) ^ (uint32_t)(4 * (lane >> 4) + i)) << 4));
       int32_t sg[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) sg[i] = c ? sgB[i] : sgA[i];
       if (sg[0] >= 0) {
         const uint32_t ald4 = (uint32_t)p.aggr_ld * 4u;
         int cur = sg[0];
-        f32x2 s01 = pack2(0.f, 0.f), s23 = s01;
-        auto flush = [&](int seg) {
-          float4 sum;
-          unpack2(s01, sum.x, sum.y);
-          unpack2(s23, sum.z, sum.w);
-          red_add_v4(row_ptr(p.aggr + 4 * c4, (uint32_t)seg, ald4), sum);
-        };
+        if constexpr (BF) {  // the 16-byte piece holds 8 bf16 columns: fp32 sums, two vector reductions per run
+          float s8[8];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (sg[i] < 0) break;
-          if (sg[i] != cur) {
-            flush(cur);
-            cur = sg[i];
-            s01 = pack2(0.f, 0.f);
-            s23 = s01;
+          for (int j = 0; j < 8; ++j) s8[j] = 0.f;
+          auto flush = [&](int seg) {
+            const float* a = row_ptr(p.aggr + 8 * c4, (uint32_t)seg, ald4);
+            red_add_v4(a, make_float4(s8[0], s8[1], s8[2], s8[3]));
+            red_add_v4(a + 4, make_float4(s8[4], s8[5], s8[6], s8[7]));
+          };
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (sg[i] < 0) break;
+            if (sg[i] != cur) {
+              flush(cur);
+              cur = sg[i];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) s8[j] = 0.f;
+            }
+            const uint32_t wv[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float lo, hi;
+              bf2_unpack(wv[j], lo, hi);
+              s8[2 * j] += lo;
+              s8[2 * j + 1] += hi;
+            }
           }
-          s01 = add2(s01, pack2(v[i].x, v[i].y));
-          s23 = add2(s23, pack2(v[i].z, v[i].w));
+          flush(cur);
+        } else {
+          f32x2 s01 = pack2(0.f, 0.f), s23 = s01;
+          auto flush = [&](int seg) {
+            float4 sum;
+            unpack2(s01, sum.x, sum.y);
+            unpack2(s23, sum.z, sum.w);
+            red_add_v4(row_ptr(p.aggr + 4 * c4, (uint32_t)seg, ald4), sum);
+          };
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (sg[i] < 0) break;
+            if (sg[i] != cur) {
+              flush(cur);
+              cur = sg[i];
+              s01 = pack2(0.f, 0.f);
+              s23 = s01;
+            }
+            s01 = add2(s01, pack2(__uint_as_float(v[i].x), __uint_as_float(v[i].y)));
+            s23 = add2(s23, pack2(__uint_as_float(v[i].z), __uint_as_float(v[i].w)));
+          }
+          flush(cur);
         }
-        flush(cur);
       }
     }
     EW_PROF(15);
@@ -394,7 +527,7 @@ struct EwOwner {
   }
 };
 
-template <bool RELU_E, bool PROF>
+template <bool BF, bool RELU_E, bool PROF>
 __global__ void __launch_bounds__(EW_THREADS, 1) in_edge_ws_kernel(const __grid_constant__ EwParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t sm0 = smem_u32(smem_raw);
@@ -447,7 +580,7 @@ __global__ void __launch_bounds__(EW_THREADS, 1) in_edge_ws_kernel(const __grid_
 
   if (warp < 16) {
     // ================================================================= row owners
-    EwOwner<RELU_E, PROF> o{p, sm0};
+    EwOwner<BF, RELU_E, PROF> o{p, sm0};
     o.w = warp; o.lane = lane; o.r = 32 * (warp & 3) + lane; o.qd = warp >> 2;
     o.rx = (uint32_t)(o.r & 7) << 4;
     o.own = (uint32_t)(o.qd >> 1) * 16384u + (uint32_t)o.r * 128u;
@@ -511,7 +644,7 @@ __global__ void __launch_bounds__(EW_THREADS, 1) in_edge_ws_kernel(const __grid_
           const int c = __shfl_sync(0xffffffffu, r4.z, j), d = __shfl_sync(0xffffffffu, r4.w, j);
           if (elect_one()) {
             tma::gather4(sl + j * 512, &p.e_map, full_e, 0, a, b, c, d);
-            tma::gather4(sl + 16384 + j * 512, &p.e_map, full_e, 32, a, b, c, d);
+            tma::gather4(sl + 16384 + j * 512, &p.e_map, full_e, BF ? 64 : 32, a, b, c, d);
           }
           __syncwarp();
         }
@@ -519,7 +652,7 @@ __global__ void __launch_bounds__(EW_THREADS, 1) in_edge_ws_kernel(const __grid_
       if (elect_one()) {
         if (!e_gather) {
           tma::load_2d(sl, &p.e_map, full_e, 0, (int)row0);  // rows past the end of the table arrive as zeros
-          tma::load_2d(sl + 16384, &p.e_map, full_e, 32, (int)row0);
+          tma::load_2d(sl + 16384, &p.e_map, full_e, BF ? 64 : 32, (int)row0);
         }
         if (full) {  // ids of the tile (a partial tile reads them with guarded loads instead)
           tma::bulk_g2s(ids, p.dst + row0, 512, full_e);
@@ -535,7 +668,7 @@ __global__ void __launch_bounds__(EW_THREADS, 1) in_edge_ws_kernel(const __grid_
     const uint32_t bars = sm0 + EW_BARS + 64 * ctx;
     const uint32_t a_ready = bars + 24, d_ready = bars + 32;
     const uint32_t tmc = (uint32_t)ctx * EW_CTX;
-    const uint32_t idesc = make_idesc_tf32(EW_TM, 64);
+    const uint32_t idesc = BF ? make_idesc_bf16(EW_TM, 128) : make_idesc_tf32(EW_TM, 64);
     int n = 0;  // commits so far
     for (int t = 0; t < n_t[ctx]; ++t) {
 #pragma unroll 1
@@ -547,15 +680,22 @@ __global__ void __launch_bounds__(EW_THREADS, 1) in_edge_ws_kernel(const __grid_
         const uint64_t bd_hi = make_smem_desc_sw128(sm0 + (uint32_t)l * 32768u);
         const uint64_t bd_lo = make_smem_desc_sw128(sm0 + (uint32_t)l * 32768u + 16384u);
         if (elect_one()) {
-          bool acc = false;
+          if constexpr (BF) {
+            // 128 x 128 x 128 in bf16: eight K = 16 steps; the weights of a layer are two K tiles [128][64 bf16]
 #pragma unroll
-          for (int pass = 0; pass < 3; ++pass) {  // small terms first: lo*hi, hi*lo, hi*hi
-            const uint32_t a = tmc + ((pass == 0) ? EW_A_LO : EW_A_HI);
-            const uint64_t bd = (pass == 1) ? bd_lo : bd_hi;
+            for (int ks = 0; ks < 8; ++ks)
+              mma_bf16_ts(tmc + 64u, tmc + 8 * ks, (ks < 4 ? bd_hi : bd_lo) + (uint64_t)((ks & 3) * 2), idesc, ks > 0);
+          } else {
+            bool acc = false;
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
-              mma_tf32_ts(tmc + EW_D, a + 8 * ks, bd + (uint64_t)((ks >> 2) * 512 + (ks & 3) * 2), idesc, acc);
-              acc = true;
+            for (int pass = 0; pass < 3; ++pass) {  // small terms first: lo*hi, hi*lo, hi*hi
+              const uint32_t a = tmc + ((pass == 0) ? EW_A_LO : EW_A_HI);
+              const uint64_t bd = (pass == 1) ? bd_lo : bd_hi;
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks) {
+                mma_tf32_ts(tmc + EW_D, a + 8 * ks, bd + (uint64_t)((ks >> 2) * 512 + (ks & 3) * 2), idesc, acc);
+                acc = true;
+              }
             }
           }
           mma_commit_addr(d_ready);
@@ -572,6 +712,40 @@ __global__ void __launch_bounds__(EW_THREADS, 1) in_edge_ws_kernel(const __grid_
 }
 
 // ------------------------------------------------------------------------------ host side
+template <bool BF, bool RELU_E, bool PROF>
+static cudaError_t ew_configure() {
+  return cudaFuncSetAttribute(in_edge_ws_kernel<BF, RELU_E, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, EW_SMEM);
+}
+
+static int ew_launch(const EwParams& p, bool bf, bool relu, cudaStream_t st) {
+  static PerDeviceOnce once;
+  bool& configured = *once.slot();
+  if (!configured) {
+    cudaError_t e = ew_configure<false, false, false>();
+    if (e == cudaSuccess) e = ew_configure<false, true, false>();
+    if (e == cudaSuccess) e = ew_configure<false, false, true>();
+    if (e == cudaSuccess) e = ew_configure<false, true, true>();
+    if (e == cudaSuccess) e = ew_configure<true, false, false>();
+    if (e == cudaSuccess) e = ew_configure<true, true, false>();
+    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(in_edge_ws)");
+    configured = true;
+  }
+  const int pairs = (p.n_tiles + 1) / 2;
+  const int grid = pairs < kNumSMs ? pairs : kNumSMs;
+  if (bf) {
+    if (relu) in_edge_ws_kernel<true, true, false><<<grid, EW_THREADS, EW_SMEM, st>>>(p);
+    else      in_edge_ws_kernel<true, false, false><<<grid, EW_THREADS, EW_SMEM, st>>>(p);
+  } else if (g_ew_prof_enabled) {
+    if (relu) in_edge_ws_kernel<false, true, true><<<grid, EW_THREADS, EW_SMEM, st>>>(p);
+    else      in_edge_ws_kernel<false, false, true><<<grid, EW_THREADS, EW_SMEM, st>>>(p);
+  } else {
+    if (relu) in_edge_ws_kernel<false, true, false><<<grid, EW_THREADS, EW_SMEM, st>>>(p);
+    else      in_edge_ws_kernel<false, false, false><<<grid, EW_THREADS, EW_SMEM, st>>>(p);
+  }
+  GTB_CHECK_LAUNCH("in_edge_ws_kernel");
+  return GTB_OK;
+}
+
 // Does this descriptor have the shape of the wide IN edge kernel?  (Checked by fused_mlp_tc before the
 // generic tiles.)  Returns the positions of the three source blocks through the out arguments.
 static bool ew_match(const gtb_mlp_desc_t& d, int* s_e, int* s_pi, int* s_pj) {
@@ -638,27 +812,80 @@ int in_edge_ws(const gtb_mlp_desc_t& d, cudaStream_t st, bool* handled) {
   p.out_ld = d.out_ld;
   *handled = true;
   if (d.n_rows == 0) return GTB_OK;
-  static PerDeviceOnce once;
-  bool& configured = *once.slot();
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(in_edge_ws_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EW_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(in_edge_ws_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EW_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(in_edge_ws_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EW_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(in_edge_ws_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EW_SMEM);
-    if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(in_edge_ws)");
-    configured = true;
+  return ew_launch(p, false, se.relu != 0, st);
+}
+
+// ------------------------------------------------------------------------------ bf16 variant (128 / 128 / 128)
+// Packed image: per layer two K tiles [128 n][64 bf16] in the 128-byte-swizzle UMMA layout (16 KB each), then the
+// three bias rows as bf16 (autocast casts the bias with the weight): 3 * 32 KB + 768 B, the fp32 image's size.
+__global__ void pack_ew_bf16_kernel(const float* __restrict__ w0, const float* __restrict__ w1, const float* __restrict__ w2,
+                                    const float* __restrict__ b0, const float* __restrict__ b1, const float* __restrict__ b2,
+                                    unsigned char* __restrict__ packed) {
+  const float* ws[3] = {w0, w1, w2};
+  const float* bs[3] = {b0, b1, b2};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 3 * 128 * 128 + 3 * 128; i += gridDim.x * blockDim.x) {
+    if (i < 3 * 128 * 128) {
+      const int l = i / 16384, n = (i >> 7) & 127, k = i & 127;
+      const uint32_t kb = (uint32_t)(k & 63) * 2u;
+      const uint32_t off = (uint32_t)l * 32768u + (uint32_t)(k >> 6) * 16384u + (uint32_t)(n >> 3) * 1024u + (uint32_t)(n & 7) * 128u +
+                           ((((kb >> 4) ^ (uint32_t)(n & 7)) & 7u) << 4) + (kb & 15u);
+      *reinterpret_cast<__nv_bfloat16*>(packed + off) = __float2bfloat16_rn(ws[l][n * 128 + k]);
+    } else {
+      const int j = i - 3 * 128 * 128, l = j >> 7, n = j & 127;
+      reinterpret_cast<__nv_bfloat16*>(packed + EW_W)[j] = __float2bfloat16_rn(bs[l] ? bs[l][n] : 0.f);
+    }
   }
-  const int pairs = (p.n_tiles + 1) / 2;
-  const int grid = pairs < kNumSMs ? pairs : kNumSMs;
-  if (g_ew_prof_enabled) {
-    if (se.relu) in_edge_ws_kernel<true, true><<<grid, EW_THREADS, EW_SMEM, st>>>(p);
-    else         in_edge_ws_kernel<false, true><<<grid, EW_THREADS, EW_SMEM, st>>>(p);
-  } else {
-    if (se.relu) in_edge_ws_kernel<true, false><<<grid, EW_THREADS, EW_SMEM, st>>>(p);
-    else         in_edge_ws_kernel<false, false><<<grid, EW_THREADS, EW_SMEM, st>>>(p);
-  }
-  GTB_CHECK_LAUNCH("in_edge_ws_kernel");
+}
+
+int ew_pack_bf16(const float* const* weights, const float* const* biases, void* packed, cudaStream_t st) {
+  GTB_REQUIRE(weights && weights[0] && weights[1] && weights[2] && packed, GTB_ERR_BAD_ARG, "gtb_in_edge_bf16_pack: null argument");
+  pack_ew_bf16_kernel<<<96, 256, 0, st>>>(weights[0], weights[1], weights[2], biases ? biases[0] : nullptr,
+                                          biases ? biases[1] : nullptr, biases ? biases[2] : nullptr,
+                                          static_cast<unsigned char*>(packed));
+  GTB_CHECK_LAUNCH("pack_ew_bf16_kernel");
   return GTB_OK;
+}
+
+int in_edge_ws_bf16(const void* e_in, int32_t e_ld, const int32_t* e_index, int32_t relu_e, const void* p_i, int32_t pi_ld,
+                    const void* p_j, int32_t pj_ld, int64_t n_edges, const int32_t* src_sorted, const int32_t* dst_sorted,
+                    const void* packed, void* e_out, int32_t eo_ld, const int32_t* out_index, float* aggr, int32_t aggr_ld,
+                    cudaStream_t st) {
+  GTB_REQUIRE(e_in && p_i && p_j && src_sorted && dst_sorted && packed && e_out && aggr, GTB_ERR_BAD_ARG,
+              "gtb_in_edge_forward_bf16: null argument");
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  GTB_REQUIRE(al16(e_in) && al16(p_i) && al16(p_j) && al16(e_out) && al16(aggr) && al16(src_sorted) && al16(dst_sorted) &&
+                  al16(packed) && (e_index == nullptr || al16(e_index)) && (out_index == nullptr || al16(out_index)),
+              GTB_ERR_BAD_ARG, "gtb_in_edge_forward_bf16: pointers must be 16-byte aligned");
+  GTB_REQUIRE(e_ld >= 128 && pi_ld >= 128 && pj_ld >= 128 && eo_ld >= 128 && aggr_ld >= 128 && !(e_ld & 7) && !(pi_ld & 7) &&
+                  !(pj_ld & 7) && !(eo_ld & 7) && !(aggr_ld & 3),
+              GTB_ERR_BAD_ARG, "gtb_in_edge_forward_bf16: row strides must cover 128 columns in 16-byte steps");
+  GTB_REQUIRE(n_edges >= 0 && n_edges < (1ll << 31) - 256, GTB_ERR_BAD_ARG, "gtb_in_edge_forward_bf16: bad n_edges");
+  GTB_REQUIRE(tma::encode_fn() != nullptr, GTB_ERR_CUDA, "gtb_in_edge_forward_bf16: cuTensorMapEncodeTiled is not available");
+  if (n_edges == 0) return GTB_OK;
+  EwParams p;
+  memset(&p, 0, sizeof(p));
+  const uint64_t big = 1ull << 31;
+  const bool e_gather = e_index != nullptr, o_scatter = out_index != nullptr;
+  const uint64_t e_rows = e_gather ? big : (uint64_t)n_edges, o_rows = o_scatter ? big : (uint64_t)n_edges;
+  const CUtensorMapDataType bf = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  GTB_REQUIRE(tma::make_map_2d(&p.e_map, e_in, bf, 2, e_rows, 128, (uint64_t)e_ld, 64, e_gather ? 1 : 128) &&
+                  tma::make_map_2d(&p.pj_map, p_j, bf, 2, big, 128, (uint64_t)pj_ld, 64, 1) &&
+                  tma::make_map_2d(&p.out_map, e_out, bf, 2, o_rows, 128, (uint64_t)eo_ld, 64, o_scatter ? 1 : 8),
+              GTB_ERR_CUDA, "gtb_in_edge_forward_bf16: the driver refused a tensor map");
+  p.pi = p_i;
+  p.pi_ld = pi_ld;
+  p.dst = dst_sorted;
+  p.src = src_sorted;
+  p.e_index = e_index;
+  p.out_index = out_index;
+  p.aggr = aggr;
+  p.aggr_ld = aggr_ld;
+  p.packed = static_cast<const unsigned char*>(packed);
+  p.n_rows = n_edges;
+  p.n_tiles = (int32_t)((n_edges + EW_TM - 1) / EW_TM);
+  p.out = e_out;
+  p.out_ld = eo_ld;
+  return ew_launch(p, true, relu_e != 0, st);
 }
 
 int ew_profile(int enable, long long* out32) {

@@ -343,5 +343,57 @@ __device__ __forceinline__ void add16(float (&v)[16], const float4& x0, const fl
 }
 
 
+
+// ---- bf16 pairs (kind::f16 tiles: two bf16 per 32-bit word, the even element in the low half)
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
+  return (1u << 4)                    // D format: F32
+         | (1u << 7)                  // A format: BF16
+         | (1u << 10)                 // B format: BF16
+         | ((uint32_t)(n >> 3) << 17) // N >> 3
+         | ((uint32_t)(m >> 4) << 24);  // M >> 4
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T, bf16 operands, fp32 accumulation (one K = 16 step); issued by ONE thread
+__device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void bf2_unpack(uint32_t w, float& lo, float& hi) {
+  lo = __uint_as_float(w << 16);
+  hi = __uint_as_float(w & 0xffff0000u);
+}
+__device__ __forceinline__ uint32_t bf2_pack_rn(float lo, float hi) {  // round to nearest even, as torch's .to(bfloat16)
+  uint32_t w;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(hi), "f"(lo));
+  return w;
+}
+__device__ __forceinline__ uint32_t bf2_relu(uint32_t w) {
+  uint32_t r;
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(w), "r"(0u));
+  return r;
+}
+// v[2 j], v[2 j + 1] += the two halves of word j
+__device__ __forceinline__ void bf2_add16(float (&v)[32], int base, const uint4& a, const uint4& b) {
+  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float lo, hi;
+    bf2_unpack(w[j], lo, hi);
+    v[base + 2 * j] += lo;
+    v[base + 2 * j + 1] += hi;
+  }
+}
+__device__ __forceinline__ uint4 lds128u(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128u(uint32_t a, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 }  // namespace tc
 }  // namespace gtb

@@ -16,7 +16,7 @@ from ._lib import (ACT_NONE, ACT_RELU, ACT_SIGMOID_AFFINE, IMPL_AUTO, IMPL_FFMA,
 
 __all__ = ["ACT_NONE", "ACT_RELU", "ACT_SIGMOID_AFFINE", "IMPL_AUTO", "IMPL_FFMA", "IMPL_TCGEN05", "Block",
            "PackedMLP", "fused_mlp", "pack_linears", "require_cuda", "default_impl", "launch_count", "rows_gather",
-           "tc_slots"]
+           "tc_slots", "in_edge_bf16", "pack_in_edge_bf16"]
 
 _LAUNCHES = 0  # kernels launched through the C ABI by this process (bench.py reports it)
 
@@ -238,6 +238,46 @@ def fused_mlp(blocks: Sequence[Block], n_rows: int, packed: PackedMLP, *, final_
         _count(1)
     del keep
     return out if want_out else None
+
+
+def pack_in_edge_bf16(weights: Sequence[Tensor], biases: Sequence[Tensor | None]) -> Tensor:
+    """Packs the relational model of a 128 / 128 / 128 Interaction-Network layer for
+    ``in_edge_bf16``: three ``[128, 128]`` weights (the first one = the EDGE columns of the first
+    Linear) and their biases, rounded to bf16 as ``torch.autocast`` casts them."""
+    dev = require_cuda(*weights)
+    if len(weights) != 3 or any(tuple(w.shape) != (128, 128) for w in weights):
+        raise ValueError("in_edge_bf16 takes three [128, 128] weights")
+    ws = [w.detach().to(torch.float32).contiguous() for w in weights]
+    bs = [None if b is None else b.detach().to(torch.float32).contiguous() for b in biases]
+    buf = torch.empty(lib().gtb_in_edge_bf16_packed_bytes(), dtype=torch.uint8, device=dev)
+    wp = (C.c_void_p * 3)(*[w.data_ptr() for w in ws])
+    bp = (C.c_void_p * 3)(*[(b.data_ptr() if b is not None else None) for b in bs])
+    with on_device(dev):
+        check(lib().gtb_in_edge_bf16_pack(wp, bp, buf.data_ptr(), stream_ptr(dev)))
+    _count(1)
+    return buf
+
+
+def in_edge_bf16(e_in: Tensor, p_i: Tensor, p_j: Tensor, src_sorted: Tensor, dst_sorted: Tensor, packed: Tensor,
+                 n_nodes: int, *, e_index: Tensor | None = None, out_index: Tensor | None = None,
+                 relu_e: bool = False) -> tuple[Tensor, Tensor]:
+    """bf16 Interaction-Network edge kernel (``gtb_in_edge_forward_bf16`` in include/gtb200.h):
+    returns ``(e_out bf16 [E, 128], aggr fp32 [n_nodes, 128])``."""
+    dev = require_cuda(e_in, p_i, p_j, src_sorted, dst_sorted, packed)
+    for t in (e_in, p_i, p_j):
+        if t.dtype != torch.bfloat16 or t.dim() != 2 or t.size(1) != 128 or t.stride(1) != 1:
+            raise TypeError("in_edge_bf16 takes bf16 [*, 128] tables")
+    n_edges = src_sorted.numel()
+    e_out = torch.empty((n_edges, 128), dtype=torch.bfloat16, device=dev)
+    aggr = torch.zeros((n_nodes, 128), dtype=torch.float32, device=dev)
+    if n_edges:
+        with on_device(dev):
+            check(lib().gtb_in_edge_forward_bf16(
+                e_in.data_ptr(), e_in.stride(0), _idx(e_index), int(relu_e), p_i.data_ptr(), p_i.stride(0),
+                p_j.data_ptr(), p_j.stride(0), n_edges, _idx(src_sorted), _idx(dst_sorted), packed.data_ptr(),
+                e_out.data_ptr(), e_out.stride(0), _idx(out_index), aggr.data_ptr(), aggr.stride(0), stream_ptr(dev)))
+        _count(1)
+    return e_out, aggr
 
 
 def rows_atb(a: Tensor, b: Tensor, out: Tensor, *, a_index: Tensor | None = None, a_relu: bool = False,

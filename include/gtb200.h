@@ -207,6 +207,25 @@ int gtb_in_node_forward_f32(const float* x, int32_t x_ld, int32_t relu_x,
                             float res_a, float res_b, const float* res, int32_t res_ld,
                             float* x_out, int32_t xo_ld, void* stream);
 
+/* bf16 variant of the edge kernel for the reference's mixed-precision runs (torch.autocast(bfloat16) around
+ * models/interaction_network.py:75-89; BASELINE config 3: GraphTCN with node = edge = hidden width 128).
+ * All feature tables are bf16 [*, ld] (ld in elements, 16-byte multiples), fp32 accumulation on the tensor
+ * cores (tcgen05 kind::f16), every Linear output rounded to bf16 as autocast's Linear does, the
+ * per-destination sum accumulated in fp32:
+ *   e_out[o(r)] = bf16(W2 relu(bf16(W1 relu(bf16(W0e act(e_in[i(r)]) + P_i[dst(r)] + P_j[src(r)] + b0)) + b1)) + b2)
+ *   aggr[dst(r), 0:128] += e_out row      (aggr fp32 [N, aggr_ld], zero-filled by the caller)
+ * rows r walk the plan's destination-sorted edge list; e_index / out_index: `perm`, or NULL when the edge
+ * features are already / stay in that order.  P_i / P_j: act(x) times the two node column blocks of the first
+ * Linear, per node (the caller's GEMM).  gtb_in_edge_bf16_pack: weights fp32 [128, 128] x 3 (nn.Linear
+ * layout; W0 = the EDGE columns of the first Linear), biases fp32 [128] x 3 (entries may be NULL). */
+size_t gtb_in_edge_bf16_packed_bytes(void);
+int gtb_in_edge_bf16_pack(const float* const* weights, const float* const* biases, void* packed, void* stream);
+int gtb_in_edge_forward_bf16(const void* e_in, int32_t e_ld, const int32_t* e_index, int32_t relu_e,
+                             const void* p_i, int32_t pi_ld, const void* p_j, int32_t pj_ld, int64_t n_edges,
+                             const int32_t* src_sorted, const int32_t* dst_sorted, const void* packed,
+                             void* e_out, int32_t eo_ld, const int32_t* out_index,
+                             float* aggr, int32_t aggr_ld, void* stream);
+
 /* ------------------------------------------------------------------- EC losses
  * metrics/losses/ec.py.  y_true may be NULL-free uint8 or float labels:
  *   label_kind 0: float [E], 1: uint8/bool [E].
