@@ -29,6 +29,7 @@ if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
 
 N_NODES, N_EDGES = 100_000, 1_000_000
+GRAPH_KIND = "trackml"  # --graph
 NODE_IN, EDGE_IN, HIDDEN, L_EC = 14, 4, 64, 3
 
 
@@ -74,6 +75,8 @@ def make_graph(n_nodes: int, n_edges: int, seed: int = 0) -> dict:
     bwd = torch.stack([-dr, -dphi, -dz, dR], 1)
     edge_index = torch.cat([torch.stack([src, dst]), torch.stack([dst, src])], 1).contiguous()
     edge_attr = torch.cat([fwd, bwd], 0).contiguous()
+    if GRAPH_KIND == "uniform":  # the worst-locality control: same sizes and features, random endpoints
+        edge_index = torch.randint(0, n_nodes, (2, edge_index.size(1)), generator=gen)
     eta = torch.asinh(z / r)
     x = torch.cat([torch.stack([r, phi / math.pi, z, eta, r * torch.cos(phi), r * torch.sin(phi)], 1),
                    torch.randn(n_nodes, 8, generator=gen)], 1).contiguous()
@@ -92,7 +95,8 @@ def model_kwargs(dims: str) -> dict:
 
 def workload_name(dims: str, n: int, e: int) -> str:
     d = "Dn=De=H=64 (wide)" if dims == "wide" else "Dn=5,De=4,H=64 (reference-default widths)"
-    return f"ECForGraphTCN forward, L_ec=3, {d}, fp32, TrackML-shaped synthetic graph {n} nodes / {e} edges, plan build per step"
+    kind = "TrackML-shaped synthetic graph" if GRAPH_KIND == "trackml" else "UNIFORM-RANDOM-edge control graph"
+    return f"ECForGraphTCN forward, L_ec=3, {d}, fp32, {kind} {n} nodes / {e} edges, plan build per step"
 
 
 def layer_algorithmic_bytes(n: int, e: int, dn: int, de: int) -> float:
@@ -311,7 +315,8 @@ def run_ours(args) -> None:
         # weak scaling on ONE graph: world x (100k nodes / 1M edges), nodes relabelled by phi and
         # partitioned into contiguous ranges; every rank owns the edges that END in its range and
         # receives its halo rows by one all-to-all-v per layer (+ one for the W head)
-        gg = relabel_by_phi(make_graph(N_NODES * world, N_EDGES * world, seed=0))
+        scale = args.total_scale if args.total_scale > 0 else world
+        gg = relabel_by_phi(make_graph(int(N_NODES * scale), int(N_EDGES * scale), seed=0))
         shard = partition_graph(gg["edge_index"], gg["n_nodes"], world, rank)
         g = {"x": gg["x"][shard.node_lo:shard.node_hi].contiguous(), "edge_index": shard.edge_index.contiguous(),
              "edge_attr": gg["edge_attr"][shard.edge_ids].contiguous(), "n_nodes": shard.n_local,
@@ -466,14 +471,18 @@ def run_ours(args) -> None:
     e2e_pipelined_val = n_total_edges * args.steps / (ms_e2e * 1e-3) if ms_e2e is not None else None
     e2e_val = max(e2e_pipelined_val or 0.0, e2e_serial_val)
     e2e_ms = min(ms_e2e if ms_e2e is not None else ms_e2e_serial, ms_e2e_serial) / args.steps
-    multi = ("one graph of %d x (100k nodes / 1M edges), node-partitioned by phi wedge, edges owned by their destination's rank, "
-             "one NCCL all-to-all-v of halo rows per IN layer + one for the W head; max halo/owned = %.3f" % (world, halo_frac)
+    multi = ("one graph of %g x (100k nodes / 1M edges), node-partitioned by phi wedge, edges owned by their destination's rank, "
+             "one NCCL all-to-all-v of halo rows per IN layer + one for the W head; max halo/owned = %.3f"
+             % (args.total_scale if args.total_scale > 0 else world, halo_frac)
              if partitioned else "one independent graph per rank per step, no data-path collective")
     line = {
         "metric": "edges/sec", "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak" if not (partitioned and args.total_scale > 0) else "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.dims, N_NODES, N_EDGES) + (f" x {world} ranks" if world > 1 else ""),
+        "config": {"workload": (workload_name(args.dims, N_NODES, N_EDGES) + (f" x {world} ranks" if world > 1 else "")
+                                if not (partitioned and args.total_scale > 0) else
+                                workload_name(args.dims, int(N_NODES * args.total_scale), int(N_EDGES * args.total_scale))
+                                + f" partitioned over {world} ranks"),
                    "l2": "flushed between timed iterations (256 MB write)", "multi_gpu": multi,
                    "impl": os.environ.get("GTB_IMPL", "auto")},
         "e2e": {"value": e2e_val, "unit": "edges/s", "ms_per_step": e2e_ms,
@@ -538,11 +547,33 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dims", default="wide", choices=["wide", "default"])
+    ap.add_argument("--config", default="ec", choices=["ec", "tcn_bf16", "pipeline"],
+                    help="ec: BASELINE config 2 (headline); tcn_bf16: config 3; pipeline: config 5 (see bench_extra.py)")
+    ap.add_argument("--mode", default="forward", choices=["forward", "train"], help="train: one EC training step (fwd + bwd + Adam)")
+    ap.add_argument("--graph", default="trackml", choices=["trackml", "uniform"],
+                    help="uniform: edge_index = randint(0, N, (2, E)), the worst-locality control of SURVEY 8d / 8e")
+    ap.add_argument("--trials", type=int, default=20, help="DBSCAN trials per step of --config pipeline")
+    ap.add_argument("--total-scale", type=float, default=0.0,
+                    help="N > 1, partitioned: the ONE graph has total-scale x (100k nodes / 1M edges); default = N (weak scaling). "
+                         "BASELINE config 4 (500k nodes / 5M edges on 8 GPUs) is --gpus 8 --total-scale 5")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--multi", default="partitioned", choices=["partitioned", "independent"],
                     help="N > 1: one node-partitioned graph with halo exchange (default) or one graph per rank")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    global GRAPH_KIND
+    GRAPH_KIND = args.graph
+    if args.config != "ec" or args.mode != "forward":
+        import bench_extra
+        if int(os.environ.get("RANK", "0")) != 0:
+            return  # the other configurations are single-GPU lines
+        if args.config == "tcn_bf16":
+            (bench_extra.run_tcn_bf16_reference if args.impl == "reference" else bench_extra.run_tcn_bf16)(args)
+        elif args.config == "pipeline":
+            bench_extra.run_pipeline(args)
+        else:
+            bench_extra.run_train(args)
+        return
     if args.impl == "reference":
         run_reference(args)
     else:

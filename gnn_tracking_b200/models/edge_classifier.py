@@ -55,9 +55,13 @@ class ECForGraphTCN(nn.Module, HyperparametersMixin):
         assert_feat_dim(edge_attr, self.hparams.edge_indim)
         ops.require_cuda(x, edge_index, edge_attr)
         if plan is None:
+            torch.cuda.nvtx.range_push("gtb.plan")
             plan = get_plan(edge_index, x.size(0) if halo is None else halo.shard.n_local)
+            torch.cuda.nvtx.range_pop()
         n, e = x.size(0), edge_attr.size(0)
+        nvtx = torch.cuda.nvtx
         # encoders + the ReLU behind them (edge_classifier.py:102-103)
+        nvtx.range_push("gtb.ec.encoders")
         h = self.ec_node_encoder.forward_blocks([Block(x)], n, final_act=ACT_RELU)
         # The edge features live in the plan's destination-sorted order inside the model (the encoder
         # gathers its 4 input columns through ``perm``): every layer then streams contiguous tiles.  Only
@@ -65,7 +69,11 @@ class ECForGraphTCN(nn.Module, HyperparametersMixin):
         sorted_edges = len(self.ec_resin.network.layers) > 0
         ea = self.ec_edge_encoder.forward_blocks(
             [Block(edge_attr, plan.perm, unique_index=True) if sorted_edges else Block(edge_attr)], e, final_act=ACT_RELU)
+        nvtx.range_pop()
+        nvtx.range_push("gtb.ec.resin")
         h, ea, eas = self.ec_resin.forward_planned(h, plan, ea, halo=halo, sorted_edges=sorted_edges)
+        nvtx.range_pop()
+        nvtx.range_push("gtb.ec.w_head")
         # W head over cat[h[src], h[dst], e_0 .. e_L] (edge_classifier.py:108-117), walked in
         # dst-sorted order (h[dst] rows repeat) and written back in the caller's edge order
         blocks = []
@@ -75,6 +83,7 @@ class ECForGraphTCN(nn.Module, HyperparametersMixin):
         blocks += [Block(t, None) if has_sorted_edges(t) else Block(t, plan.perm, unique_index=True)
                    for t in (eas if self.hparams.use_intermediate_edge_embeddings else [ea])]
         w = self.W.forward_blocks(blocks, e, final_act=ACT_SIGMOID_AFFINE, act_eps=0.001, out_index=plan.perm)
+        nvtx.range_pop()
         return {"W": w.squeeze(), "node_embedding": h, "edge_embedding": ea}
 
 

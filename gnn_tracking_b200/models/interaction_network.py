@@ -6,6 +6,7 @@ e_tilde)`` in the caller's edge order -- computed by two fused kernels over a
 destination-sorted plan instead of PyG's gather / cat / addmm / scatter_add chain."""
 from __future__ import annotations
 
+import torch
 from torch import Tensor, nn
 
 from .. import ops
@@ -13,7 +14,7 @@ from .._hparams import HyperparametersMixin
 from ..ops import Block
 from ..plan import GraphPlan, get_plan
 from ..utils.asserts import assert_feat_dim
-from .mlp import MLP
+from .mlp import MLP, autocast_bf16
 
 
 class InteractionNetwork(nn.Module, HyperparametersMixin):
@@ -47,6 +48,9 @@ class InteractionNetwork(nn.Module, HyperparametersMixin):
         (the module-level ``forward`` never exposes that order)."""
         dev = ops.require_cuda(x, edge_attr)
         n, e = x.size(0), edge_attr.size(0)
+        if autocast_bf16() and halo is None and self._bf16_wide():
+            return self._forward_bf16(x, plan, edge_attr, relu_x=relu_x, relu_e=relu_e, res=res, res_a=res_a,
+                                      res_b=res_b, e_sorted=e_sorted, out_sorted=out_sorted)
         e_out = self.hparams.edge_outdim
         # zeroed: isolated nodes keep 0 (SumAggregation), partial runs are added atomically
         ext = None if halo is None else halo.extend
@@ -60,3 +64,46 @@ class InteractionNetwork(nn.Module, HyperparametersMixin):
         x_tilde = self.object_model.forward_blocks([Block(x, None, relu_x), Block(aggr)], n,
                                                    res=res, res_a=res_a, res_b=res_b)
         return x_tilde, e_tilde
+
+    # ------------------------------------------------------------------ bf16 (torch.autocast) path
+    def _bf16_wide(self) -> bool:
+        hp = self.hparams
+        return (hp.node_indim == hp.edge_indim == hp.edge_outdim == hp.edge_hidden_dim == 128)
+
+    def _forward_bf16(self, x, plan, edge_attr, *, relu_x, relu_e, res, res_a, res_b, e_sorted, out_sorted):
+        """The layer under ``torch.autocast(bfloat16)`` at width 128 (BASELINE config 3): the edge side --
+        gather, relational MLP, per-destination sum -- is ONE native bf16 launch (``gtb_in_edge_forward_bf16``:
+        tcgen05 kind::f16, fp32 accumulation, Linear outputs rounded to bf16 as autocast does); the node
+        side (the two N x 128 x 128 pre-projections and the object model) are plain library GEMMs on
+        bf16 operands."""
+        if torch.is_grad_enabled() and (x.requires_grad or edge_attr.requires_grad
+                                        or any(p.requires_grad for p in self.relational_model.parameters())):
+            raise NotImplementedError("the bf16 edge kernel is forward-only: wrap inference in torch.no_grad()")
+        bf = torch.bfloat16
+        rel = self.relational_model.linears
+        w0 = rel[0].weight
+        cache = self.__dict__.setdefault("_bf16_cache", {})
+        key = tuple((p.data_ptr(), p._version) for lin in rel for p in lin.parameters())
+        if cache.get("key") != key:
+            cache["packed"] = ops.pack_in_edge_bf16([w0[:, 256:].contiguous(), rel[1].weight, rel[2].weight],
+                                                    [rel[0].bias, rel[1].bias, rel[2].bias])
+            cache["w_i"] = w0[:, :128].detach().to(bf).contiguous()
+            cache["w_j"] = w0[:, 128:256].detach().to(bf).contiguous()
+            cache["key"] = key
+        xa = (torch.relu(x) if relu_x else x).to(bf)
+        p_i = nn.functional.linear(xa, cache["w_i"])
+        p_j = nn.functional.linear(xa, cache["w_j"])
+        ea = edge_attr.to(bf)
+        if not ea.is_contiguous():
+            ea = ea.contiguous()
+        e_tilde, aggr = ops.in_edge_bf16(ea, p_i, p_j, plan.src_sorted, plan.dst_sorted, cache["packed"], x.size(0),
+                                         e_index=None if e_sorted else plan.perm,
+                                         out_index=None if out_sorted else plan.perm, relu_e=relu_e)
+        # update(): cat[x, aggr] promotes to fp32, the Linear casts back to bf16 (interaction_network.py:92-103)
+        h = torch.cat([xa.float(), aggr], dim=1)
+        for m in self.object_model.layers:
+            h = m(h)
+        if res is not None:
+            h = res_a * res + res_b * h
+        return h, e_tilde
+

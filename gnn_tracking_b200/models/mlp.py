@@ -107,6 +107,56 @@ class _PackedWeightsMixin:
         self.register_load_state_dict_post_hook(lambda module, incompatible_keys: invalidate_packed_weights(module))
 
 
+def autocast_bf16() -> bool:
+    """True inside ``torch.autocast("cuda", dtype=torch.bfloat16)``: the reference's mixed-precision mode
+    (BASELINE config 3).  Linear layers then take bf16 operands and return bf16, as autocast makes
+    ``nn.Linear`` do; see DESIGN.md "bf16 path" for which launches are native in that mode."""
+    return torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.bfloat16
+
+
+def _run_autocast(linears: Sequence[nn.Linear], blocks: Sequence[Block], n_rows: int, *, final_act: int = ACT_NONE,
+                  act_eps: float = 0.0, res: Tensor | None = None, res_a: float = 0.0, res_b: float = 1.0,
+                  out_scale: Tensor | None = None, row_scale: Tensor | None = None, out_index: Tensor | None = None,
+                  aggr_rows: int | None = None, seg_id: Tensor | None = None, **unused):
+    """A Linear / ReLU chain over concatenated column blocks under bf16 autocast, op for op what the
+    reference's modules run there (models/mlp.py:59-62, edge_classifier.py:108-117): library GEMMs on
+    bf16 operands with bf16 results.  Used for everything around the Interaction-Network edge kernel in
+    bf16 mode (encoders, object model, heads); the edge kernel itself is ``ops.in_edge_bf16``."""
+    cols = []
+    for b in blocks:
+        if b.extend is not None or b.projected:
+            raise NotImplementedError("bf16 autocast over halo / pre-projected blocks is not implemented")
+        t = b.tensor if b.tensor.dim() > 1 else b.tensor.unsqueeze(1)
+        if b.index is not None:
+            t = t[b.index.long()]
+        cols.append(torch.relu(t) if b.relu else t)
+    h = cols[0] if len(cols) == 1 else torch.cat(cols, dim=1)
+    if row_scale is not None:
+        h = h * row_scale.unsqueeze(1)
+    for i, lin in enumerate(linears):
+        h = nn.functional.linear(h, lin.weight, lin.bias)  # autocast: bf16 x bf16 -> bf16
+        if i + 1 < len(linears):
+            h = torch.relu(h)
+    if final_act == ACT_RELU:
+        h = torch.relu(h)
+    elif final_act == ops.ACT_SIGMOID_AFFINE:
+        h = act_eps + (1.0 - 2.0 * act_eps) * torch.sigmoid(h)
+    if res is not None:
+        h = res_a * res + res_b * h
+    elif res_b != 1.0:
+        h = res_b * h
+    if out_scale is not None:
+        h = h * out_scale
+    aggr = None
+    if aggr_rows is not None:
+        aggr = torch.zeros((aggr_rows, h.size(1)), dtype=torch.float32, device=h.device).index_add_(0, seg_id.long(), h.float())
+    if out_index is not None:
+        out = torch.empty_like(h)
+        out[out_index.long()] = h
+        h = out
+    return h if aggr_rows is None else (h, aggr)
+
+
 def _run_nograd(cache: PackedCache, linears: Sequence[nn.Linear], blocks: Sequence[Block], n_rows: int,
                 *, final_act: int = ACT_NONE, **epilogue) -> Tensor | None:
     """Linear/ReLU chain over concatenated column blocks; <= 3 Linear layers per
@@ -124,17 +174,31 @@ def _run_nograd(cache: PackedCache, linears: Sequence[nn.Linear], blocks: Sequen
     if all(projected):
         projected[-1] = False
     packed, proj = cache.get(linears, widths, projected)
-    cur = []
-    for i, b in enumerate(blocks):
+    cur: list = [None] * len(blocks)
+    pending = []
+    # blocks that cross the halo exchange of a node-partitioned graph first: their transfer runs under the
+    # launches of the other blocks' projections
+    for i in sorted(range(len(blocks)), key=lambda i: blocks[i].extend is None):
+        b = blocks[i]
+        ext = b.extend
+        start = getattr(ext, "__self__", None).start if hasattr(getattr(ext, "__self__", None), "start") else None
         if projected[i]:
-            table = ops.fused_mlp([Block(b.tensor, None, b.relu)], b.tensor.size(0), proj[i])
-            if b.extend is not None:  # halo rows of the projected table from their owners
-                table = b.extend(table)
-            cur.append(Block(table, b.index, False, projected=True, sorted_index=b.sorted_index))
-        elif b.extend is not None:
-            cur.append(Block(b.extend(b.tensor), b.index, b.relu, sorted_index=b.sorted_index))
+            out = None
+            if start is not None:  # the projection writes the owned rows of the extended table in place
+                out = ext.__self__.buffer(proj[i].dims[-1], b.tensor)
+            table = ops.fused_mlp([Block(b.tensor, None, b.relu)], b.tensor.size(0), proj[i], out=out)
+            if ext is not None:  # halo rows of the projected table from their owners
+                if start is not None:
+                    pending.append((i, start(table), b))
+                    continue
+                table = ext(table)
+            cur[i] = Block(table, b.index, False, projected=True, sorted_index=b.sorted_index)
+        elif ext is not None:
+            cur[i] = Block(ext(b.tensor), b.index, b.relu, sorted_index=b.sorted_index)
         else:
-            cur.append(b)
+            cur[i] = b
+    for i, handle, b in pending:
+        cur[i] = Block(b.extend.__self__.finish(handle), b.index, False, projected=True, sorted_index=b.sorted_index)
     for i, p in enumerate(packed):
         if i + 1 < len(packed):
             h = ops.fused_mlp(cur, n_rows, p, final_act=ACT_RELU)
@@ -149,6 +213,8 @@ def run_linears(cache: PackedCache, linears: Sequence[nn.Linear], blocks: Sequen
     """``_run_nograd`` plus autograd (``autograd.FusedMLPFunction``, recompute-based backward through
     the same kernels) when a block, a weight or the residual requires a gradient.  With
     ``aggr_rows`` the per-destination sum is returned as well: ``(out, aggr)``."""
+    if autocast_bf16():
+        return _run_autocast(linears, blocks, n_rows, final_act=final_act, aggr_rows=aggr_rows, **epilogue)
     res = epilogue.get("res")
     needs_grad = torch.is_grad_enabled() and (
         any(b.tensor.requires_grad for b in blocks) or any(p.requires_grad for lin in linears for p in lin.parameters())
@@ -161,6 +227,13 @@ def run_linears(cache: PackedCache, linears: Sequence[nn.Linear], blocks: Sequen
         out = _run_nograd(cache, linears, blocks, n_rows, final_act=final_act, aggr=aggr, **epilogue)
         return out, aggr
     from ..autograd import _BwdPacks, fused_mlp_autograd
+    if any(b.extend is not None for b in blocks):
+        # node-partitioned graph under autograd: the raw rows cross the halo through a differentiable
+        # exchange (its backward is the reverse all-to-all-v), the rest is the single-GPU backward
+        from ..partition import halo_extend
+        blocks = [b if b.extend is None else
+                  Block(halo_extend(b.tensor, b.extend.__self__), b.index, b.relu, sorted_index=b.sorted_index)
+                  for b in blocks]
     bad = [k for k in ("row_scale", "out_scale", "out", "gate", "aggr") if epilogue.get(k) is not None]
     if bad or epilogue.get("want_out") is False:
         raise NotImplementedError(f"backward with the epilogue options {bad or ['want_out=False']} is not implemented")
@@ -265,6 +338,16 @@ class ResFCNN(_PackedWeightsMixin, nn.Module):
             nn.init.normal_(p.data, mean=0.0, std=math.sqrt(var))
 
     def forward_blocks(self, blocks: Sequence[Block], n_rows: int, *, final_act: int = ACT_NONE) -> Tensor:
+        if autocast_bf16():  # reference mlp.py:115-120 under autocast: library GEMMs, bf16 results
+            cols = [(torch.relu(b.tensor) if b.relu else b.tensor) if b.index is None else
+                    (torch.relu(b.tensor[b.index.long()]) if b.relu else b.tensor[b.index.long()]) for b in blocks]
+            x = nn.functional.normalize(cols[0] if len(cols) == 1 else torch.cat(cols, 1), p=2.0, dim=1, eps=1e-12)
+            x = self._encoder(x)
+            a, b2 = math.sqrt(self._alpha), math.sqrt(1 - self._alpha)
+            for lay in self._layers:
+                x = a * x + b2 * lay(torch.relu(x))
+            x = self._decoder(torch.relu(x))
+            return torch.relu(x) if final_act == ACT_RELU else x
         if torch.is_grad_enabled() and (any(b.tensor.requires_grad for b in blocks)
                                         or any(p.requires_grad for p in self.parameters())):
             return self._forward_grad(blocks, n_rows, final_act)

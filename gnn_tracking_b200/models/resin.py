@@ -9,6 +9,7 @@ import math
 from abc import ABC, abstractmethod
 from itertools import pairwise
 
+import torch
 from torch import Tensor, nn
 
 from .._hparams import HyperparametersMixin
@@ -76,9 +77,16 @@ class ResidualNetwork(ABC, nn.Module):
         kw = {} if co is None else dict(res=residue, res_a=co[0], res_b=co[1])
         self._calls_left -= 1
         out_sorted = self._sorted and self._calls_left > 0  # the stack's final edge tensor: caller's order
-        xo, eo = self.layers[i].forward_planned(x, plan, e, relu_x=not first, relu_e=not first, halo=self._halo,
-                                                e_sorted=has_sorted_edges(e), out_sorted=out_sorted, **kw)
+        torch.cuda.nvtx.range_push(f"gtb.in_layer.{i}")
+        try:
+            xo, eo = self._layer_call(i, x, plan, e, first, out_sorted, kw)
+        finally:
+            torch.cuda.nvtx.range_pop()
         return xo, (mark_sorted_edges(eo) if out_sorted else eo)
+
+    def _layer_call(self, i, x, plan, e, first, out_sorted, kw):
+        return self.layers[i].forward_planned(x, plan, e, relu_x=not first, relu_e=not first, halo=self._halo,
+                                                e_sorted=has_sorted_edges(e), out_sorted=out_sorted, **kw)
 
     @abstractmethod
     def _forward(self, x: Tensor, plan: GraphPlan, edge_attr: Tensor):

@@ -130,6 +130,12 @@ class HaloExchange:
         return torch.empty((self.shard.n_local, width), dtype=like.dtype, device=like.device)
 
     def extend(self, table: Tensor, buf: Tensor | None = None) -> Tensor:
+        return self.finish(self.start(table, buf))
+
+    def start(self, table: Tensor, buf: Tensor | None = None):
+        """Issues the exchange (asynchronously where the backend allows) and returns a handle for
+        ``finish``: the caller launches whatever does not need the halo rows in between -- the other
+        pre-projection of the layer runs under the transfer."""
         sh = self.shard
         if table.dim() != 2 or table.size(0) not in (sh.n_owned, sh.n_local):
             raise ValueError(f"expected a table of {sh.n_owned} owned rows, got {tuple(table.shape)}")
@@ -141,9 +147,15 @@ class HaloExchange:
                 buf = self.buffer(w, table)
             buf[:sh.n_owned].copy_(table)
         if sh.world == 1:
-            return buf
+            return buf, None
         send = self._pack(buf, sh.send_idx, sh.n_owned)
-        ops_, so, ro = [], 0, sh.n_owned
+        self.bytes_sent += send.numel() * send.element_size()
+        if buf.is_cuda:
+            # one all-to-all-v: NCCL runs it on its own stream, the caller's stream goes on
+            work = dist.all_to_all_single(buf[sh.n_owned:], send, output_split_sizes=list(sh.recv_counts),
+                                          input_split_sizes=list(sh.send_counts), group=self.group, async_op=True)
+            return buf, (work, send)
+        ops_, so, ro = [], 0, sh.n_owned  # gloo (CPU tests): the same exchange as point-to-point operations
         for q in range(sh.world):
             if sh.recv_counts[q]:
                 ops_.append(dist.P2POp(dist.irecv, buf[ro:ro + sh.recv_counts[q]], self._peer(q), self.group))
@@ -151,11 +163,50 @@ class HaloExchange:
             if sh.send_counts[q]:
                 ops_.append(dist.P2POp(dist.isend, send[so:so + sh.send_counts[q]], self._peer(q), self.group))
                 so += sh.send_counts[q]
-        if ops_:
-            for req in dist.batch_isend_irecv(ops_):
-                req.wait()
-        self.bytes_sent += send.numel() * send.element_size()
+        return buf, (dist.batch_isend_irecv(ops_) if ops_ else [], send)
+
+    @staticmethod
+    def finish(handle) -> Tensor:
+        buf, pending = handle
+        if pending is not None:
+            work, _send = pending
+            for req in (work if isinstance(work, list) else [work]):
+                req.wait()  # NCCL: the current stream waits for the transfer, the host does not
         return buf
+
+    def reverse(self, grad_ext: Tensor) -> Tensor:
+        """Adjoint of ``extend``: ``grad_ext [n_owned + n_halo, w] -> grad [n_owned, w]``.  The halo rows'
+        gradients travel back to their owners (the reverse all-to-all-v) and are added onto the
+        rows they were copied from; a row sent to several ranks collects all of them."""
+        sh = self.shard
+        g = grad_ext.contiguous()
+        out = g[:sh.n_owned].clone()
+        if sh.world == 1 or (sh.n_halo == 0 and sum(sh.send_counts) == 0):
+            return out
+        back = g[sh.n_owned:]
+        recv = torch.empty((sum(sh.send_counts), g.size(1)), dtype=g.dtype, device=g.device)
+        if g.is_cuda:
+            dist.all_to_all_single(recv, back, output_split_sizes=list(sh.send_counts),
+                                   input_split_sizes=list(sh.recv_counts), group=self.group)
+        else:  # gloo (CPU tests)
+            ops_, so, ro = [], 0, 0
+            for q in range(sh.world):
+                if sh.send_counts[q]:
+                    ops_.append(dist.P2POp(dist.irecv, recv[ro:ro + sh.send_counts[q]], self._peer(q), self.group))
+                    ro += sh.send_counts[q]
+                if sh.recv_counts[q]:
+                    ops_.append(dist.P2POp(dist.isend, back[so:so + sh.recv_counts[q]].contiguous(), self._peer(q), self.group))
+                    so += sh.recv_counts[q]
+            for req in (dist.batch_isend_irecv(ops_) if ops_ else []):
+                req.wait()
+        self.bytes_sent += back.numel() * back.element_size()
+        if recv.numel():
+            if g.is_cuda:
+                from . import ops
+                ops.rows_scatter_add(recv, sh.send_idx, out)
+            else:
+                out.index_add_(0, sh.send_idx.long(), recv)
+        return out
 
     def _peer(self, q: int) -> int:
         return q if self.group is None else dist.get_global_rank(self.group, q)
@@ -166,3 +217,37 @@ class HaloExchange:
             from . import ops
             return ops.rows_gather(buf, idx)
         return buf.index_select(0, idx.long())  # CPU tensors: host-side tests of the plumbing (gloo)
+
+
+class _HaloExtend(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, table: Tensor, halo: "HaloExchange") -> Tensor:
+        ctx.halo = halo
+        return halo.extend(table.detach())
+
+    @staticmethod
+    def backward(ctx, grad_ext: Tensor):
+        return ctx.halo.reverse(grad_ext), None
+
+
+def halo_extend(table: Tensor, halo: HaloExchange) -> Tensor:
+    """Differentiable ``halo.extend(table)``: the backward is the reverse exchange (``HaloExchange.reverse``).
+    Training on a node-partitioned graph exchanges the RAW node rows of a layer through this (the fused
+    kernel's backward then treats the extended table like any gathered table)."""
+    return _HaloExtend.apply(table, halo)
+
+
+def allreduce_gradients(module: torch.nn.Module, group=None) -> None:
+    """Sums the parameter gradients over the ranks of a node-partitioned graph (every rank holds all the
+    weights and the gradient of ITS edges and nodes): call between ``backward()`` and the optimiser
+    step.  Losses must be normalised with GLOBAL counts (e.g. BCE summed locally / the global edge count)."""
+    grads = [p.grad for p in module.parameters() if p.grad is not None]
+    if not grads or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, group=group)
+    off = 0
+    for g in grads:
+        g.copy_(flat[off:off + g.numel()].view_as(g))
+        off += g.numel()
+

@@ -38,9 +38,7 @@ def mlp(x: Tensor, sd: dict, prefix: str) -> Tensor:
     for n, i in enumerate(lins):
         w = sd[f"{prefix}layers.{i}.weight"]
         b = sd.get(f"{prefix}layers.{i}.bias")
-        x = x @ w.t()
-        if b is not None:
-            x = x + b
+        x = torch.nn.functional.linear(x, w, b)  # nn.Linear: under torch.autocast the bias joins the bf16 GEMM
         if n + 1 < len(lins):
             x = torch.relu(x)
     return x
@@ -60,9 +58,7 @@ def res_fcnn(x: Tensor, sd: dict, prefix: str, alpha: float) -> Tensor:
 
 
 def _linear(x, sd, prefix):
-    y = x @ sd[prefix + "weight"].t()
-    b = sd.get(prefix + "bias")
-    return y if b is None else y + b
+    return torch.nn.functional.linear(x, sd[prefix + "weight"], sd.get(prefix + "bias"))
 
 
 # ------------------------------------------------------------ Interaction network

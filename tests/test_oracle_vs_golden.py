@@ -105,3 +105,31 @@ def test_plan_oracle_is_stable_sort(golden_graphs):
     assert rowptr[-1] == ei.size(1) and rowptr[0] == 0
     deg = rowptr[1:] - rowptr[:-1]
     assert torch.equal(deg, torch.bincount(ei[1], minlength=n))
+
+
+def test_oracle_graph_tcn_bf16_autocast_vs_reference_golden():
+    """BASELINE config 3 pin: the restatement under ``torch.autocast("cpu", bfloat16)`` against the
+    reference's own GraphTCN run the same way (tests/golden/make_golden_bf16.py).  Same ops, same dtypes:
+    a bf16 ulp on the TrackML sector graph.  The synthetic fixture has a destination with 700 incoming
+    edges, and autocast leaves the aggregation in bf16 (scatter_add_ on bf16 messages): a 700-term bf16 sum
+    depends on the order of the additions at the per-cent level (the reference's own bf16 and fp32 runs differ
+    by 0.55 % of the scale there), so that graph is held to 2.5e-2."""
+    import torch
+
+    from gnn_tracking_b200.models.track_condensation_networks import GraphTCN
+    from oracle import in_oracle as O
+    from tests.golden.common import load
+    gold = load("bf16_tcn")
+    torch.manual_seed(gold["seed"])
+    sd = {k: v.clone() for k, v in GraphTCN(**gold["kwargs"]).state_dict().items()}
+    chk = float(sum(v.double().abs().sum() for v in sd.values()))
+    assert abs(chk - gold["param_checksum"]) <= 1e-9 * gold["param_checksum"]
+    for gname, case in gold["cases"].items():
+        gd = load("graphs")[gname]
+        with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+            out = O.graph_tcn_forward(gd["x"], gd["edge_index"], gd["edge_attr"], sd, ec_threshold=0.0)
+        for k in ("W", "H", "B"):
+            r = case["outputs"][k]
+            err = float((out[k].float().reshape(r.shape) - r).abs().max())
+            tol = 2 ** -7 if gname == "sector0" else 2.5e-2
+            assert err <= tol * max(1.0, float(r.abs().max())), (gname, k, err)

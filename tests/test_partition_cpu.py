@@ -76,6 +76,17 @@ def _worker(rank, world, port, n, e, width, q):
             ok = ok and torch.equal(ext, exp)
         # a per-edge gather through the local numbering equals the global gather
         ok = ok and torch.equal(ext[sh.edge_index[0]], table[ei[0][sh.edge_ids]])
+        # backward through the halo: reverse() is the adjoint of extend(), i.e. summed over the ranks
+        # <extend(t), g> == <t, reverse(g)>; and autograd goes through halo_extend
+        from gnn_tracking_b200.partition import halo_extend
+        g = torch.randn(sh.n_local, width, generator=torch.Generator().manual_seed(100 + rank), dtype=torch.float64)
+        t = table[sh.node_lo:sh.node_hi].double().clone().requires_grad_(True)
+        lhs = (halo_extend(t, halo) * g).sum()
+        lhs.backward()
+        rhs = (t.detach() * halo.reverse(g)).sum()
+        both = torch.stack([lhs.detach(), rhs])
+        dist.all_reduce(both)
+        ok = ok and bool(torch.allclose(both[0], both[1], rtol=1e-12)) and bool(torch.allclose(t.grad, halo.reverse(g)))
         q.put((rank, ok, sh.n_halo, halo.bytes_sent))
     finally:
         dist.destroy_process_group()
