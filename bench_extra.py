@@ -208,9 +208,15 @@ def run_pipeline(args) -> None:
     x, ei, ea = g["x"].to(dev), g["edge_index"].to(dev), g["edge_attr"].to(dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     n_trials = args.trials
+    # The scan explores radii around the cluster size it is looking for (tracks of ~10 hits): eps runs over the
+    # 3rd .. 30th nearest-neighbour distance of the latent space (median over 2000 sampled hits), whatever the
+    # random-init network makes of it.
     with torch.no_grad():
-        spread = float(model(GraphData(x=x, edge_index=ei, edge_attr=ea))["H"].std())
-    trials = [(spread * (0.01 + 0.04 * i / max(1, n_trials - 1)), 1 + i % 3) for i in range(n_trials)]
+        h0 = model(GraphData(x=x, edge_index=ei, edge_attr=ea))["H"].float()
+        sample = h0[torch.randperm(n, device=dev, generator=torch.Generator(device=dev).manual_seed(0))[:2000]]
+        knn = torch.cdist(sample, h0).topk(31, dim=1, largest=False).values.median(dim=0).values  # [31], entry 0 = self
+    ks = [3 + round(27 * i / max(1, n_trials - 1)) for i in range(n_trials)]
+    trials = [(float(knn[k]) * 1.0001, 1 + i % 3) for i, k in enumerate(ks)]
     hold = {}
 
     def step():
@@ -236,6 +242,7 @@ def run_pipeline(args) -> None:
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"GraphTCN forward (reference-default widths, hidden 64, L_ec=3, L_hc=3, 3 latent dimensions) + {n_trials} DBSCAN "
                                f"trials of the hyper-parameter scan on the latent space of {n} hits / {e} edges (BASELINE config 5)",
+                   "eps": "3rd .. 30th nearest-neighbour distance of the latent space (median over 2000 hits), min_samples 1 .. 3",
                    "split": {"forward_ms": ms_fwd / args.steps, "scan_ms": (ms - ms_fwd) / args.steps,
                              "ms_per_trial": (ms - ms_fwd) / args.steps / n_trials},
                    "l2": "flushed between timed iterations (256 MB write)"},

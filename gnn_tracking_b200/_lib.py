@@ -90,6 +90,8 @@ SIGNATURES = {
     "gtb_edge_dist_pow_sum_f32": (C.c_int, [_vp, _i32, _vp, _i64, _vp, _f32, _vp, _vp]),
     "gtb_oc_potentials_grad": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _i64, _vp, _i32, _f32, _i64, _vp, _vp, _vp, _vp, _vp]),
     "gtb_dbscan_f32": (C.c_int, [_vp, _i32, _i64, C.c_double, _i32, _vp, _vp, _vp, _vp]),
+    "gtb_dbscan_grid_workspace_bytes": (_sz, [_i64]),
+    "gtb_dbscan_grid_f32": (C.c_int, [_vp, _i32, _i64, C.c_double, _i32, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gtb_rows_inv_l2norm_f32": (C.c_int, [C.POINTER(Src), _i32, _i64, _f32, _vp, _vp]),
     "gtb_rows_atb_f32": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _vp, _i32, _i32, _i64, _vp, _i32, _vp, _vp]),
     "gtb_rows_scatter_add_f32": (C.c_int, [_vp, _i32, _vp, _i64, _i32, _vp, _i32, _vp]),

@@ -38,6 +38,8 @@ int tc_timeout_flag(int*);
 int oc_potentials_grad(const float*, const float*, int32_t, const int64_t*, const int32_t*, int64_t, const int32_t*, int32_t,
                        float, int64_t, const float*, float*, float*, float*, cudaStream_t);
 int dbscan(const float*, int, int64_t, double, int, unsigned char*, int*, int*, cudaStream_t);
+size_t dbscan_grid_workspace_bytes(int64_t);
+int dbscan_grid(const float*, int, int64_t, double, int, unsigned char*, int*, int*, void*, size_t, cudaStream_t);
 int radius_pair_sum(const float*, int, int64_t, const int64_t*, const int64_t*, const unsigned char*, const float*, float, float,
                     float, float, int, int, double*, cudaStream_t);
 int edge_dist_pow_sum(const float*, int, const int64_t*, int64_t, const unsigned char*, float, double*, cudaStream_t);
@@ -132,6 +134,13 @@ int gtb_in_edge_forward_bf16(const void* e_in, int32_t e_ld, const int32_t* e_in
                              const int32_t* out_index, float* aggr, int32_t aggr_ld, void* stream) {
   return in_edge_ws_bf16(e_in, e_ld, e_index, relu_e, p_i, pi_ld, p_j, pj_ld, n_edges, src_sorted, dst_sorted, packed, e_out,
                          eo_ld, out_index, aggr, aggr_ld, static_cast<cudaStream_t>(stream));
+}
+
+size_t gtb_dbscan_grid_workspace_bytes(int64_t n) { return dbscan_grid_workspace_bytes(n); }
+
+int gtb_dbscan_grid_f32(const float* x, int32_t d, int64_t n, double eps, int32_t min_pts, uint8_t* core, int32_t* parent,
+                        int32_t* root, void* workspace, size_t workspace_bytes, void* stream) {
+  return dbscan_grid(x, d, n, eps, min_pts, core, parent, root, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int gtb_arch_ok(int device) {

@@ -1,0 +1,305 @@
+// DBSCAN over a uniform cell list (the neighbour search SURVEY 2a K6 / 8f-2 names): same results as
+// dbscan.cu -- labels identical to sklearn's -- without the N^2 candidate walk.
+//
+// The points are binned on their first min(d, 3) coordinates into cells at least eps wide, so every
+// neighbour (dist <= eps) of a point lies in the 3^k cells around its own; the full-dimensional distance
+// test is the one of dbscan.cu (fp32 screen, float64 decision on the rim).  Per call (= one trial of the
+// hyper-parameter scan, postprocessing/dbscanscanner.py:146-187; eps changes from trial to trial, so the
+// grid is rebuilt -- a 21-bit radix sort of the cell ids):
+//   bounding box -> cell ids -> sort (cell id, point) -> cell_begin[] -> coordinates in cell order
+//   pass 0: neighbour counts -> core flags        pass 1: union-find of the core samples
+//   pass 2: roots (core: own component, border: smallest adjacent root, noise: -1)
+// Everything visible to the caller (core, parent, root) is indexed by the ORIGINAL point index, and the
+// outcome does not depend on the order in which neighbours are visited (components are rooted at their
+// lowest index, a border point takes the smallest adjacent root), so the numbering equals dbscan_inner's.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace gtb {
+
+constexpr int DG_T = 128;
+constexpr int DG_MAXD = 16;
+constexpr int DG_CELL_BITS = 21;  // at most 2^21 cells
+
+struct DgGrid {        // written by dg_setup_kernel, read by everything else
+  float lo[3];         // lower corner of the box in the grid dimensions
+  double inv_h[3];     // 1 / cell size
+  int g[3];            // cells per grid dimension (unused dimensions: 1)
+  int dim[3];          // coordinate index of each grid dimension (-1: unused)
+  int n_cells;
+};
+
+__device__ __forceinline__ unsigned dg_f2o(float f) {  // order-preserving float -> unsigned
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float dg_o2f(unsigned o) {
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
+__global__ void dg_bbox_kernel(const float* __restrict__ x, int d, int64_t n, int k, unsigned* __restrict__ mm /* [3 min | 3 max] */) {
+  unsigned lo[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, hi[3] = {0u, 0u, 0u};
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    for (int c = 0; c < k; ++c) {
+      const unsigned o = dg_f2o(__ldg(x + i * d + c));
+      lo[c] = min(lo[c], o);
+      hi[c] = max(hi[c], o);
+    }
+  for (int c = 0; c < k; ++c) {
+    for (int s = 16; s > 0; s >>= 1) {
+      lo[c] = min(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], s));
+      hi[c] = max(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], s));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicMin(mm + c, lo[c]);
+      atomicMax(mm + 3 + c, hi[c]);
+    }
+  }
+}
+
+// grid dimensions: the LAST grid dimension is always used (cells adjacent in it are adjacent in memory)
+__global__ void dg_setup_kernel(const unsigned* __restrict__ mm, int k, double eps, DgGrid* __restrict__ grid) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int cap = k == 1 ? (1 << DG_CELL_BITS) : (k == 2 ? 1448 : 128);  // cap^k <= 2^21
+  DgGrid gr;
+  gr.n_cells = 1;
+  for (int a = 0; a < 3; ++a) {
+    const int c = a - (3 - k);  // coordinate index, or < 0 for an unused leading dimension
+    gr.dim[a] = c;
+    gr.lo[a] = 0.f;
+    gr.inv_h[a] = 0.0;
+    gr.g[a] = 1;
+    if (c < 0) continue;
+    const float lo = dg_o2f(mm[c]), hi = dg_o2f(mm[3 + c]);
+    double range = (double)hi - (double)lo;
+    if (!(range >= 0.0) || !isfinite(range)) range = 0.0;  // NaN / Inf coordinates: one cell (they match nothing anyway)
+    double h = eps * (1.0 + 1e-9);
+    if (!(h > 0.0)) h = 1.0;
+    int g = range / h >= (double)cap ? cap : (int)(range / h) + 1;
+    if (g < 1) g = 1;
+    if (g == cap) h = range / (double)cap * (1.0 + 1e-9);  // wider cells than eps: still a valid cell list
+    gr.lo[a] = lo;
+    gr.inv_h[a] = 1.0 / h;
+    gr.g[a] = g;
+    gr.n_cells *= g;
+  }
+  *grid = gr;
+}
+
+__device__ __forceinline__ int dg_cell_coord(float v, const DgGrid& gr, int a) {
+  int c = (int)floor(((double)v - (double)gr.lo[a]) * gr.inv_h[a]);
+  return c < 0 ? 0 : (c >= gr.g[a] ? gr.g[a] - 1 : c);  // NaNs land in cell 0
+}
+
+__global__ void dg_keys_kernel(const float* __restrict__ x, int d, int64_t n, const DgGrid* __restrict__ grid,
+                               int32_t* __restrict__ keys, int32_t* __restrict__ vals) {
+  const DgGrid gr = *grid;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    int cell = 0;
+    for (int a = 0; a < 3; ++a) {
+      const int c = gr.dim[a] < 0 ? 0 : dg_cell_coord(__ldg(x + i * d + gr.dim[a]), gr, a);
+      cell = cell * gr.g[a] + c;
+    }
+    keys[i] = cell;
+    vals[i] = (int32_t)i;
+  }
+}
+
+// cell_begin[c] = first sorted position whose cell is >= c (c in [0, n_cells]); coordinates in cell order,
+// zero-padded to D floats
+template <int D>
+__global__ void dg_layout_kernel(const float* __restrict__ x, int d, int64_t n, const DgGrid* __restrict__ grid,
+                                 const int32_t* __restrict__ keys_sorted, const int32_t* __restrict__ idx_sorted,
+                                 int32_t* __restrict__ cell_begin, float* __restrict__ xs) {
+  const int n_cells = grid->n_cells;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p <= n; p += stride) {
+    const int prev = p == 0 ? -1 : keys_sorted[p - 1];
+    const int cur = p == n ? n_cells : keys_sorted[p];
+    for (int c = prev + 1; c <= cur; ++c) cell_begin[c] = (int32_t)p;
+    if (p < n) {
+      const int64_t i = idx_sorted[p];
+#pragma unroll
+      for (int c = 0; c < D; ++c) xs[p * D + c] = c < d ? __ldg(x + i * d + c) : 0.f;
+    }
+  }
+}
+
+template <int D>
+__device__ __forceinline__ bool dg_near(const float (&xi)[D], const float* __restrict__ xj, double eps2, float e2_hi, float e2_lo) {
+  float v[D];
+#pragma unroll
+  for (int q = 0; q < D / 4; ++q) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(xj) + q);
+    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < D; ++c) {
+    const float u = xi[c] - v[c];
+    s = fmaf(u, u, s);
+  }
+  if (s > e2_hi) return false;
+  if (s < e2_lo) return true;
+  double d2 = 0.0;  // on the rim of the eps-ball: decide in float64 like sklearn
+#pragma unroll
+  for (int c = 0; c < D; ++c) {
+    const double u = (double)xi[c] - (double)v[c];
+    d2 = fma(u, u, d2);
+  }
+  return d2 <= eps2;
+}
+
+__device__ __forceinline__ int dg_find(int* parent, int v) {
+  while (true) {
+    const int p = __ldcg(parent + v);
+    if (p == v) return v;
+    const int gp = __ldcg(parent + p);
+    if (gp != p) __stcg(parent + v, gp);
+    v = p;
+  }
+}
+__device__ __forceinline__ void dg_unite(int* parent, int a, int b) {
+  while (true) {
+    a = dg_find(parent, a);
+    b = dg_find(parent, b);
+    if (a == b) return;
+    if (a < b) {
+      const int t = a;
+      a = b;
+      b = t;
+    }
+    if (atomicCAS(parent + a, a, b) == a) return;  // the larger root goes under the smaller one
+  }
+}
+
+// one thread per point, walked in cell order (neighbouring threads share their candidate ranges)
+template <int D>
+__global__ void __launch_bounds__(DG_T) dg_pass_kernel(const float* __restrict__ xs, int64_t n, const DgGrid* __restrict__ grid,
+                                                       const int32_t* __restrict__ keys_sorted,
+                                                       const int32_t* __restrict__ idx_sorted,
+                                                       const int32_t* __restrict__ cell_begin, double eps2, int min_pts, int phase,
+                                                       unsigned char* __restrict__ core, int* __restrict__ parent,
+                                                       int* __restrict__ root) {
+  const DgGrid gr = *grid;
+  const float e2_hi = (float)eps2 * 1.0001f, e2_lo = (float)eps2 * 0.9999f;
+  const int64_t p = (int64_t)blockIdx.x * DG_T + threadIdx.x;
+  if (p >= n) return;
+  const int i = idx_sorted[p];
+  const bool core_i = phase > 0 && core[i];
+  if (phase == 1 && !core_i) return;
+  if (phase == 2 && core_i) {
+    root[i] = dg_find(parent, i);
+    return;
+  }
+  float xi[D];
+#pragma unroll
+  for (int c = 0; c < D; ++c) xi[c] = xs[p * D + c];
+  int cell = keys_sorted[p];
+  const int ic = cell % gr.g[2];
+  cell /= gr.g[2];
+  const int ib = cell % gr.g[1], ia = cell / gr.g[1];
+  const int c_lo = max(ic - 1, 0), c_hi = min(ic + 1, gr.g[2] - 1);
+  int count = 0, best = 0x7fffffff, my_root = i;
+  for (int a = max(ia - 1, 0); a <= min(ia + 1, gr.g[0] - 1); ++a)
+    for (int b = max(ib - 1, 0); b <= min(ib + 1, gr.g[1] - 1); ++b) {
+      const int base = (a * gr.g[1] + b) * gr.g[2];
+      const int q_end = cell_begin[base + c_hi + 1];
+      for (int q = cell_begin[base + c_lo]; q < q_end; ++q) {
+        if (phase == 0) {
+          count += dg_near<D>(xi, xs + (int64_t)q * D, eps2, e2_hi, e2_lo) ? 1 : 0;
+        } else {
+          const int j = idx_sorted[q];
+          if (phase == 1 ? (j >= i) : false) continue;  // pass 1: every pair once, from its higher index
+          if (!core[j] || !dg_near<D>(xi, xs + (int64_t)q * D, eps2, e2_hi, e2_lo)) continue;
+          if (phase == 1) {
+            if (__ldcg(parent + j) != my_root) {
+              dg_unite(parent, i, j);
+              my_root = dg_find(parent, i);
+            }
+          } else {
+            best = min(best, dg_find(parent, j));
+          }
+        }
+      }
+    }
+  if (phase == 0) {
+    core[i] = count >= min_pts ? 1 : 0;
+    parent[i] = i;
+  } else if (phase == 2) {
+    root[i] = best == 0x7fffffff ? -1 : best;
+  }
+}
+
+static size_t dg_align(size_t v) { return (v + 255) / 256 * 256; }
+
+static size_t dg_cub_bytes(int64_t n) {
+  size_t b = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, b, (const int32_t*)nullptr, (int32_t*)nullptr, (const int32_t*)nullptr,
+                                  (int32_t*)nullptr, (int)n, 0, DG_CELL_BITS);
+  return b;
+}
+
+size_t dbscan_grid_workspace_bytes(int64_t n) {
+  if (n <= 0) return 256;
+  return 256 + 256 + 4 * dg_align((size_t)n * 4) + dg_align(((size_t)1 << DG_CELL_BITS) * 4 + 8) +
+         dg_align((size_t)n * DG_MAXD * 4) + dg_align(dg_cub_bytes(n));
+}
+
+template <int D>
+static int dg_run(const float* x, int d, int64_t n, double eps, int min_pts, unsigned char* core, int* parent, int* root,
+                  char* ws, cudaStream_t st) {
+  unsigned* mm = reinterpret_cast<unsigned*>(ws);
+  DgGrid* grid = reinterpret_cast<DgGrid*>(ws + 256);
+  char* p = ws + 512;
+  int32_t* keys = reinterpret_cast<int32_t*>(p); p += dg_align((size_t)n * 4);
+  int32_t* vals = reinterpret_cast<int32_t*>(p); p += dg_align((size_t)n * 4);
+  int32_t* keys_s = reinterpret_cast<int32_t*>(p); p += dg_align((size_t)n * 4);
+  int32_t* idx_s = reinterpret_cast<int32_t*>(p); p += dg_align((size_t)n * 4);
+  int32_t* cell_begin = reinterpret_cast<int32_t*>(p); p += dg_align(((size_t)1 << DG_CELL_BITS) * 4 + 8);
+  float* xs = reinterpret_cast<float*>(p); p += dg_align((size_t)n * DG_MAXD * 4);
+  size_t cub_bytes = dg_cub_bytes(n);
+  const int k = d < 3 ? d : 3;
+  const int threads = 256;
+  const int blocks = (int)imin64((n + threads - 1) / threads, (int64_t)kNumSMs * 8);
+  int rc = check_cuda(cudaMemsetAsync(mm, 0xff, 12, st), "dbscan grid: init");  // running minima
+  if (rc == GTB_OK) rc = check_cuda(cudaMemsetAsync(mm + 3, 0, 12, st), "dbscan grid: init");  // running maxima
+  if (rc) return rc;
+  dg_bbox_kernel<<<blocks, threads, 0, st>>>(x, d, n, k, mm);
+  GTB_CHECK_LAUNCH("dg_bbox_kernel");
+  dg_setup_kernel<<<1, 32, 0, st>>>(mm, k, eps, grid);
+  GTB_CHECK_LAUNCH("dg_setup_kernel");
+  dg_keys_kernel<<<blocks, threads, 0, st>>>(x, d, n, grid, keys, vals);
+  GTB_CHECK_LAUNCH("dg_keys_kernel");
+  rc = check_cuda(cub::DeviceRadixSort::SortPairs(p, cub_bytes, keys, keys_s, vals, idx_s, (int)n, 0, DG_CELL_BITS, st),
+                  "dbscan grid: SortPairs");
+  if (rc) return rc;
+  dg_layout_kernel<D><<<blocks, threads, 0, st>>>(x, d, n, grid, keys_s, idx_s, cell_begin, xs);
+  GTB_CHECK_LAUNCH("dg_layout_kernel");
+  const double eps2 = eps * eps;
+  const int pb = (int)((n + DG_T - 1) / DG_T);
+  for (int phase = 0; phase < 3; ++phase) {
+    dg_pass_kernel<D><<<pb, DG_T, 0, st>>>(xs, n, grid, keys_s, idx_s, cell_begin, eps2, min_pts, phase, core, parent, root);
+    GTB_CHECK_LAUNCH("dg_pass_kernel");
+  }
+  return GTB_OK;
+}
+
+int dbscan_grid(const float* x, int d, int64_t n, double eps, int min_pts, unsigned char* core, int* parent, int* root,
+                void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  GTB_REQUIRE(x && core && parent && root && d >= 1 && d <= DG_MAXD && n < (1ll << 31) - 1 && min_pts >= 1, GTB_ERR_BAD_ARG,
+              "gtb_dbscan_grid_f32: bad arguments (dimension must be in [1, %d])", DG_MAXD);
+  GTB_REQUIRE(workspace != nullptr && workspace_bytes >= dbscan_grid_workspace_bytes(n), GTB_ERR_WORKSPACE,
+              "gtb_dbscan_grid_f32: workspace too small");
+  GTB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, GTB_ERR_BAD_ARG, "gtb_dbscan_grid_f32: workspace must be 256-byte aligned");
+  if (n == 0) return GTB_OK;
+  char* ws = static_cast<char*>(workspace);
+  if (d <= 4) return dg_run<4>(x, d, n, eps, min_pts, core, parent, root, ws, st);
+  if (d <= 8) return dg_run<8>(x, d, n, eps, min_pts, core, parent, root, ws, st);
+  return dg_run<16>(x, d, n, eps, min_pts, core, parent, root, ws, st);
+}
+
+}  // namespace gtb

@@ -85,6 +85,8 @@ struct EwParams {
   const unsigned char* packed;
   int64_t n_rows;
   int32_t n_tiles, pi_ld, aggr_ld, out_ld;
+  int32_t debug_bar;     // GTB_EW_DEBUG_BAR=1: a named barrier beside the out_ready mbarrier (compute-sanitizer racecheck
+                         // does not model mbarrier hand-overs; with the barrier in place it must report no hazard)
 };
 
 __device__ __noinline__ void ew_timeout();
@@ -420,6 +422,7 @@ struct EwOwner {
     const uint32_t sl = slot(c, (uint32_t)t & 1u);
     EW_PROF(13);
     ew_wait(bar(c, 5), (uint32_t)t & 1u);
+    if (p.debug_bar) asm volatile("bar.sync 1, 512;" ::: "memory");
     EW_PROF(14);
     if (8 * w < rows_here) {
       if (p.out_index == nullptr) {
@@ -518,6 +521,7 @@ struct EwOwner {
       }
     }
     EW_PROF(15);
+    if (p.debug_bar) asm volatile("bar.sync 1, 512;" ::: "memory");
     if (t + 1 < n_of(c)) {
       tma::bulk_wait_read0();  // this warp's store has read its band: the band is free
       __syncwarp();
@@ -717,7 +721,9 @@ static cudaError_t ew_configure() {
   return cudaFuncSetAttribute(in_edge_ws_kernel<BF, RELU_E, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, EW_SMEM);
 }
 
-static int ew_launch(const EwParams& p, bool bf, bool relu, cudaStream_t st) {
+static int ew_launch(EwParams& p, bool bf, bool relu, cudaStream_t st) {
+  static const bool debug_bar = getenv("GTB_EW_DEBUG_BAR") != nullptr;
+  p.debug_bar = debug_bar ? 1 : 0;
   static PerDeviceOnce once;
   bool& configured = *once.slot();
   if (!configured) {

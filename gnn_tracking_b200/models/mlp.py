@@ -146,7 +146,7 @@ def _run_autocast(linears: Sequence[nn.Linear], blocks: Sequence[Block], n_rows:
     elif res_b != 1.0:
         h = res_b * h
     if out_scale is not None:
-        h = h * out_scale
+        h = h * out_scale.to(h.dtype)  # the reference's product with the latent scale stays bf16 under autocast
     aggr = None
     if aggr_rows is not None:
         aggr = torch.zeros((aggr_rows, h.size(1)), dtype=torch.float32, device=h.device).index_add_(0, seg_id.long(), h.float())

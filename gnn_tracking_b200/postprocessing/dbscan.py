@@ -8,6 +8,8 @@ passes over shared-memory tiles: core flags, union-find of the core samples, lab
 are identical to sklearn's, including their numbering."""
 from __future__ import annotations
 
+import os
+
 import torch
 from torch import Tensor
 
@@ -15,9 +17,10 @@ from .. import ops
 from .._lib import check, lib
 
 
-def dbscan(x: Tensor, eps: float = 1.0, min_samples: int = 1) -> Tensor:
+def dbscan(x: Tensor, eps: float = 1.0, min_samples: int = 1, *, method: str | None = None) -> Tensor:
     """``sklearn.cluster.DBSCAN(eps, min_samples).fit_predict(x)`` as an int64 tensor on ``x``'s
-    device (-1 = noise)."""
+    device (-1 = noise).  ``method``: "grid" (default: uniform cell list, ``gtb_dbscan_grid_f32``) or
+    "brute" (all pairs, ``gtb_dbscan_f32``); both give the same labels (``GTB_DBSCAN`` overrides the default)."""
     dev = ops.require_cuda(x)
     x = x.detach().to(torch.float32).contiguous()
     n, d = x.shape
@@ -26,9 +29,19 @@ def dbscan(x: Tensor, eps: float = 1.0, min_samples: int = 1) -> Tensor:
     core = torch.empty(n, dtype=torch.uint8, device=dev)
     parent = torch.empty(n, dtype=torch.int32, device=dev)
     root = torch.empty(n, dtype=torch.int32, device=dev)
-    check(lib().gtb_dbscan_f32(x.data_ptr(), d, n, float(eps), int(min_samples), core.data_ptr(), parent.data_ptr(),
-                               root.data_ptr(), ops.stream_ptr(dev)))
-    ops._count(3)
+    method = method or os.environ.get("GTB_DBSCAN", "grid")
+    if method == "grid":
+        ws_bytes = lib().gtb_dbscan_grid_workspace_bytes(n)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        check(lib().gtb_dbscan_grid_f32(x.data_ptr(), d, n, float(eps), int(min_samples), core.data_ptr(), parent.data_ptr(),
+                                        root.data_ptr(), ws.data_ptr(), ws_bytes, ops.stream_ptr(dev)))
+        ops._count(10)
+    elif method == "brute":
+        check(lib().gtb_dbscan_f32(x.data_ptr(), d, n, float(eps), int(min_samples), core.data_ptr(), parent.data_ptr(),
+                                   root.data_ptr(), ops.stream_ptr(dev)))
+        ops._count(3)
+    else:
+        raise ValueError(f"unknown DBSCAN method {method!r}")
     # number the clusters in increasing order of their lowest core index (dbscan_inner's order)
     is_root = torch.zeros(n + 1, dtype=torch.int64, device=dev)
     clustered = root >= 0

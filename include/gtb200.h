@@ -337,6 +337,13 @@ int gtb_edge_dist_pow_grad_f32(const float* x, int32_t d, const int64_t* edges, 
  *                     root; noise: -1.  sklearn's label = rank of `root` among the distinct roots. */
 int gtb_dbscan_f32(const float* x, int32_t d, int64_t n, double eps, int32_t min_pts,
                    uint8_t* core, int32_t* parent, int32_t* root, void* stream);
+/* The same clustering over a uniform cell list on the first min(d, 3) coordinates (cells at least eps wide:
+ * the neighbour search SURVEY 2a K6 names) instead of the brute-force candidate walk; identical outputs.
+ * workspace: gtb_dbscan_grid_workspace_bytes(n) bytes, 256-byte aligned. */
+size_t gtb_dbscan_grid_workspace_bytes(int64_t n);
+int gtb_dbscan_grid_f32(const float* x, int32_t d, int64_t n, double eps, int32_t min_pts,
+                        uint8_t* core, int32_t* parent, int32_t* root,
+                        void* workspace, size_t workspace_bytes, void* stream);
 
 /* inv_norm[r] = 1 / max(||cat_s src_s[r]||_2, eps): torch.nn.functional.normalize(x, p=2, dim=1,
  * eps) as used by ResFCNN.forward (mlp.py:115-116); feed the result as row_scale. */

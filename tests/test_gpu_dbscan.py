@@ -114,3 +114,20 @@ def test_graph_tcn_latent_space_clustering():
         got = scanner.cluster(eps=eps, min_pts=min_pts).cpu().numpy()
         want = DBSCAN(eps=eps, min_samples=min_pts).fit_predict(hc)
         assert np.array_equal(got, want), (eps, min_pts)
+
+
+@pytest.mark.parametrize("n,d,eps,min_samples", [(5000, 1, 0.01, 2), (8000, 2, 0.03, 3), (8000, 3, 0.1, 2), (6000, 5, 0.4, 3),
+                                                 (4000, 8, 0.9, 4), (3000, 3, 50.0, 2), (3000, 3, 1e-4, 1), (100000, 3, 0.05, 2)])
+def test_dbscan_grid_equals_brute_force(n, d, eps, min_samples):
+    """The cell-list search (gtb_dbscan_grid_f32) against the all-pairs walk (gtb_dbscan_f32): identical labels,
+    for every grid shape (1 to 3 binned coordinates, one giant cell, cells far smaller than the spacing)."""
+    from gnn_tracking_b200.postprocessing.dbscan import dbscan
+
+    rng = np.random.default_rng(n + 7 * d)
+    centres = rng.uniform(-2, 2, size=(max(n // 12, 1), d))
+    x = (centres[rng.integers(0, len(centres), n)] + 0.1 * rng.standard_normal((n, d))).astype(np.float32)
+    x[: n // 50] = x[n // 50: 2 * (n // 50)]  # duplicates
+    xt = torch.from_numpy(x).cuda()
+    a = dbscan(xt, eps, min_samples, method="grid")
+    b = dbscan(xt, eps, min_samples, method="brute")
+    assert torch.equal(a, b)
