@@ -218,12 +218,12 @@ struct EwOwner {
     EW_PROF(0);
     ew_wait(bar(c, 0), (uint32_t)t & 1u);
     EW_PROF(1);
-    const void* pi_line;
-    {  // the target row of P_i is read in E0, a Linear from now: start it towards L1 at the end of this stage
+    const char* pi_own;  // own 64 bytes of the target row of P_i
+    {
       int32_t d = 0;
       if (rows_here == EW_TM) d = lds_i32(ids(c) + 4 * r);
       else if (r < rows_here) d = __ldg(p.dst + row0 + r);
-      pi_line = pi_row(d);
+      pi_own = reinterpret_cast<const char*>(pi_row(d));
     }
     if constexpr (BF) {  // 32 bf16 columns = 16 words, straight into the A operand
       uint32_t a[16];
@@ -251,7 +251,7 @@ struct EwOwner {
       split_store16(tm_lane(c) + EW_A_HI + 16 * qd, tm_lane(c) + EW_A_LO + 16 * qd, v);
     }
     a_done(c);
-    prefetch_l1(pi_line);
+    prefetch_l1(pi_own);  // read in E0, a Linear from now
     EW_PROF(2);
   }
 
@@ -261,7 +261,7 @@ struct EwOwner {
     const uint32_t row0 = (uint32_t)tile * EW_TM;
     const int rows_here = (int)min((int64_t)EW_TM, p.n_rows - (int64_t)row0);
     const uint32_t sl = slot(c, ((uint32_t)t & 1u) ^ 1u);
-    uint4 pre[4];
+    uint4 pre[4];  // own 64 bytes of P_i[dst]: destination-sorted rows, neighbouring lanes repeat lines
     {
       int32_t d = 0;
       if (rows_here == EW_TM) d = lds_i32(ids(c) + 4 * r);

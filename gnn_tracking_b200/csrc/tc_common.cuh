@@ -110,6 +110,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
+// the same through L1 (rows that neighbouring threads repeat: destination-sorted gathers)
+__device__ __forceinline__ void cp_async16_ca(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 // wait until at most `n` of this thread's most recent groups are pending (n clamped to [0, 3])
 __device__ __forceinline__ void cp_async_wait_pending(int n) {
