@@ -35,6 +35,9 @@ int ew_pack_bf16(const float* const*, const float* const*, void*, cudaStream_t);
 int in_edge_ws_bf16(const void*, int32_t, const int32_t*, int32_t, const void*, int32_t, const void*, int32_t, int64_t,
                     const int32_t*, const int32_t*, const void*, void*, int32_t, const int32_t*, float*, int32_t, cudaStream_t);
 int tc_timeout_flag(int*);
+int in_node_ws(const float*, int32_t, int32_t, float*, int32_t, int32_t, int64_t, const void*, float, float, const float*, int32_t,
+               float*, int32_t, const void*, const void*, int32_t, float*, int32_t, float*, int32_t, cudaStream_t);
+int nw_fault_flag(int*);
 int oc_potentials_grad(const float*, const float*, int32_t, const int64_t*, const int32_t*, int64_t, const int32_t*, int32_t,
                        float, int64_t, const float*, float*, float*, float*, cudaStream_t);
 int dbscan(const float*, int, int64_t, double, int, unsigned char*, int*, int*, cudaStream_t);
@@ -107,10 +110,11 @@ int gtb_version(void) { return 100; }
 const char* gtb_last_error(void) { return g_err; }
 
 int gtb_debug_tc_timeout(int* flag) {
-  int a = 0, b = 0;
+  int a = 0, b = 0, c = 0;
   int rc = tc_timeout_flag(&a);
   if (rc == GTB_OK) rc = ew_fault_flag(&b);
-  *flag = a ? a : (b ? 16 + b : 0);
+  if (rc == GTB_OK) rc = nw_fault_flag(&c);
+  *flag = a ? a : (b ? 16 + b : (c ? 32 + c : 0));
   return rc;
 }
 int gtb_debug_tc_profile(int enable, long long* out32) {
@@ -134,6 +138,14 @@ int gtb_in_edge_forward_bf16(const void* e_in, int32_t e_ld, const int32_t* e_in
                              const int32_t* out_index, float* aggr, int32_t aggr_ld, void* stream) {
   return in_edge_ws_bf16(e_in, e_ld, e_index, relu_e, p_i, pi_ld, p_j, pj_ld, n_edges, src_sorted, dst_sorted, packed, e_out,
                          eo_ld, out_index, aggr, aggr_ld, static_cast<cudaStream_t>(stream));
+}
+
+int gtb_in_node_fused_f32(const float* x, int32_t x_ld, int32_t relu_x, float* aggr, int32_t aggr_ld, int32_t zero_aggr,
+                          int64_t n_nodes, const void* packed_obj, float res_a, float res_b, const float* res, int32_t res_ld,
+                          float* x_out, int32_t xo_ld, const void* packed_pa, const void* packed_pb, int32_t proj_relu,
+                          float* p_a, int32_t pa_ld, float* p_b, int32_t pb_ld, void* stream) {
+  return in_node_ws(x, x_ld, relu_x, aggr, aggr_ld, zero_aggr, n_nodes, packed_obj, res_a, res_b, res, res_ld, x_out, xo_ld,
+                    packed_pa, packed_pb, proj_relu, p_a, pa_ld, p_b, pb_ld, static_cast<cudaStream_t>(stream));
 }
 
 size_t gtb_dbscan_grid_workspace_bytes(int64_t n) { return dbscan_grid_workspace_bytes(n); }

@@ -13,7 +13,7 @@ from .._hparams import HyperparametersMixin
 from ..ops import ACT_RELU, ACT_SIGMOID_AFFINE, Block
 from ..plan import GraphPlan, get_plan
 from ..utils.asserts import assert_feat_dim
-from .mlp import MLP
+from .mlp import MLP, projection_packs
 from .resin import ResIN, has_sorted_edges
 
 
@@ -71,7 +71,17 @@ class ECForGraphTCN(nn.Module, HyperparametersMixin):
             [Block(edge_attr, plan.perm, unique_index=True) if sorted_edges else Block(edge_attr)], e, final_act=ACT_RELU)
         nvtx.range_pop()
         nvtx.range_push("gtb.ec.resin")
-        h, ea, eas = self.ec_resin.forward_planned(h, plan, ea, halo=halo, sorted_edges=sorted_edges)
+        # the last node launch of the stack also multiplies the final node embedding by the head's two node
+        # column blocks (the products the head gathers): no separate projection launches
+        hp = self.hparams
+        n_eb = (self.ec_resin.concat_edge_embeddings_length // hp.interaction_edge_dim
+                if hp.use_intermediate_edge_embeddings else 1)
+        final_proj = None
+        if hp.use_node_embedding and self.ec_resin.network.fused_ok(h, ea, halo):
+            final_proj = projection_packs(self.W, [hp.interaction_node_dim] * 2 + [hp.interaction_edge_dim] * n_eb)
+        h, ea, eas = self.ec_resin.forward_planned(h, plan, ea, halo=halo, sorted_edges=sorted_edges,
+                                                   final_projection=final_proj)
+        head_tables = self.ec_resin.network.final_tables
         nvtx.range_pop()
         nvtx.range_push("gtb.ec.w_head")
         # W head over cat[h[src], h[dst], e_0 .. e_L] (edge_classifier.py:108-117), walked in
@@ -82,7 +92,8 @@ class ECForGraphTCN(nn.Module, HyperparametersMixin):
                        Block(h, plan.dst_sorted, sorted_index=True)]
         blocks += [Block(t, None) if has_sorted_edges(t) else Block(t, plan.perm, unique_index=True)
                    for t in (eas if self.hparams.use_intermediate_edge_embeddings else [ea])]
-        w = self.W.forward_blocks(blocks, e, final_act=ACT_SIGMOID_AFFINE, act_eps=0.001, out_index=plan.perm)
+        kw = {} if head_tables is None else {"tables": {0: head_tables[0], 1: head_tables[1]}}
+        w = self.W.forward_blocks(blocks, e, final_act=ACT_SIGMOID_AFFINE, act_eps=0.001, out_index=plan.perm, **kw)
         nvtx.range_pop()
         return {"W": w.squeeze(), "node_embedding": h, "edge_embedding": ea}
 

@@ -14,7 +14,7 @@ from .._hparams import HyperparametersMixin
 from ..ops import Block
 from ..plan import GraphPlan, get_plan
 from ..utils.asserts import assert_feat_dim
-from .mlp import MLP, autocast_bf16
+from .mlp import MLP, autocast_bf16, projection_packs
 
 
 class InteractionNetwork(nn.Module, HyperparametersMixin):
@@ -64,6 +64,42 @@ class InteractionNetwork(nn.Module, HyperparametersMixin):
         x_tilde = self.object_model.forward_blocks([Block(x, None, relu_x), Block(aggr)], n,
                                                    res=res, res_a=res_a, res_b=res_b)
         return x_tilde, e_tilde
+
+    # ------------------------------------------------------------------ fused node side (64-wide layers, no grad)
+    def fused_wide(self) -> bool:
+        """True when both models have the 64 / 64 / 64 shape ``forward_fused`` covers."""
+        hp = self.hparams
+        return (hp.node_indim == hp.edge_indim == hp.node_outdim == hp.edge_outdim == hp.node_hidden_dim
+                == hp.edge_hidden_dim == 64 and len(self.relational_model.linears) == 3
+                and len(self.object_model.linears) == 3)
+
+    def input_projection(self):
+        """The packed projections of this layer's two gathered node blocks (``ops.in_node_fused`` of the
+        PREVIOUS layer computes them), or None."""
+        return projection_packs(self.relational_model, (64, 64, 64))
+
+    def forward_fused(self, x: Tensor, plan: GraphPlan, edge_attr: Tensor, *, relu_x: bool, relu_e: bool,
+                      res: Tensor | None, res_a: float, res_b: float, e_sorted: bool, out_sorted: bool,
+                      tables: tuple[Tensor, Tensor] | None, aggr: Tensor, nxt=None, nxt_relu: bool = True):
+        """The layer as two launches (no-grad fp32, ``fused_wide()`` shapes): the edge kernel on the
+        pre-projected node tables ``tables`` = (P_i, P_j) it is handed, and ONE node launch
+        (``ops.in_node_fused``) that runs the object model with the residual, hands ``aggr`` back zeroed
+        and computes the tables of the next consumer ``nxt`` (a pair of packed projections: the next
+        layer's ``input_projection()`` or the W head's).  Returns ``(x_tilde, e_tilde, next_tables)``."""
+        n, e = x.size(0), edge_attr.size(0)
+        if tables is None:  # first layer of a stack: projection-only launch
+            _, pa, pb = ops.in_node_fused(x, False, proj=self.input_projection(), proj_relu=relu_x)
+            tables = (pa, pb)
+        e_tilde = self.relational_model.forward_blocks(
+            [Block(x, plan.dst_sorted, relu_x, sorted_index=True), Block(x, plan.src_sorted, relu_x),
+             Block(edge_attr, None, relu_e) if e_sorted else Block(edge_attr, plan.perm, relu_e, unique_index=True)],
+            e, out_index=None if out_sorted else plan.perm, aggr=aggr, seg_id=plan.dst_sorted, rowptr=plan.rowptr,
+            tables={0: tables[0], 1: tables[1]})
+        obj = self.object_model
+        packed_obj = obj._cache.get(obj.linears, (64, 64), (False, False))[0][0]
+        x_tilde, pa, pb = ops.in_node_fused(x, relu_x, aggr=aggr, zero_aggr=True, packed_obj=packed_obj, res=res,
+                                            res_a=res_a, res_b=res_b, proj=nxt, proj_relu=nxt_relu)
+        return x_tilde, e_tilde, (None if nxt is None else (pa, pb))
 
     # ------------------------------------------------------------------ bf16 (torch.autocast) path
     def _bf16_wide(self) -> bool:

@@ -158,7 +158,7 @@ def _run_autocast(linears: Sequence[nn.Linear], blocks: Sequence[Block], n_rows:
 
 
 def _run_nograd(cache: PackedCache, linears: Sequence[nn.Linear], blocks: Sequence[Block], n_rows: int,
-                *, final_act: int = ACT_NONE, **epilogue) -> Tensor | None:
+                *, final_act: int = ACT_NONE, tables: dict | None = None, **epilogue) -> Tensor | None:
     """Linear/ReLU chain over concatenated column blocks; <= 3 Linear layers per
     fused launch, longer chains are split with the intermediate kept in HBM.
 
@@ -176,10 +176,18 @@ def _run_nograd(cache: PackedCache, linears: Sequence[nn.Linear], blocks: Sequen
     packed, proj = cache.get(linears, widths, projected)
     cur: list = [None] * len(blocks)
     pending = []
+    # ``tables``: {block position: its pre-projected table}, already computed by the producer of the block's
+    # tensor (``ops.in_node_fused``: the previous layer's node kernel) -- no projection launch here
+    for i, table in (tables or {}).items():
+        if not projected[i] or blocks[i].extend is not None:
+            raise AssertionError("a pre-projected table was supplied for a block this call does not project")
+        cur[i] = Block(table, blocks[i].index, False, projected=True, sorted_index=blocks[i].sorted_index)
     # blocks that cross the halo exchange of a node-partitioned graph first: their transfer runs under the
     # launches of the other blocks' projections
     for i in sorted(range(len(blocks)), key=lambda i: blocks[i].extend is None):
         b = blocks[i]
+        if cur[i] is not None:
+            continue
         ext = b.extend
         start = getattr(ext, "__self__", None).start if hasattr(getattr(ext, "__self__", None), "start") else None
         if projected[i]:
@@ -208,12 +216,34 @@ def _run_nograd(cache: PackedCache, linears: Sequence[nn.Linear], blocks: Sequen
     raise AssertionError("unreachable")
 
 
+def projection_pattern(widths: Sequence[int], n_projected: int = 2) -> tuple[tuple[int, ...], tuple[bool, ...]]:
+    """The calling pattern ``_run_nograd`` derives for a consumer whose first ``n_projected`` blocks are gathered
+    rows of a small table (x[dst], x[src]) and whose other blocks are streamed: the key of its ``PackedCache``."""
+    widths = tuple(widths)
+    return widths, (True,) * n_projected + (False,) * (len(widths) - n_projected)
+
+
+def projection_packs(mlp: "MLP", widths: Sequence[int]):
+    """Packed single-Linear projections of the first two blocks of ``mlp``'s first Linear (the node column
+    blocks a relational model / the W head gathers), or None when they are not 64 -> 64 tensor-core packs."""
+    if len(mlp.linears) < 2:
+        return None
+    w, pr = projection_pattern(widths)
+    packed, proj = mlp._cache.get(mlp.linears, w, pr)
+    pa, pb = proj.get(0), proj.get(1)
+    if pa is None or pb is None or any(p.impl != ops.IMPL_TCGEN05 or p.dims != (64, 64) for p in (pa, pb)):
+        return None
+    return pa, pb
+
+
 def run_linears(cache: PackedCache, linears: Sequence[nn.Linear], blocks: Sequence[Block], n_rows: int,
                 *, final_act: int = ACT_NONE, aggr_rows: int | None = None, **epilogue):
     """``_run_nograd`` plus autograd (``autograd.FusedMLPFunction``, recompute-based backward through
     the same kernels) when a block, a weight or the residual requires a gradient.  With
     ``aggr_rows`` the per-destination sum is returned as well: ``(out, aggr)``."""
     if autocast_bf16():
+        if epilogue.get("tables"):
+            raise AssertionError("pre-projected tables belong to the fp32 no-grad path")
         return _run_autocast(linears, blocks, n_rows, final_act=final_act, aggr_rows=aggr_rows, **epilogue)
     res = epilogue.get("res")
     needs_grad = torch.is_grad_enabled() and (
@@ -234,7 +264,7 @@ def run_linears(cache: PackedCache, linears: Sequence[nn.Linear], blocks: Sequen
         blocks = [b if b.extend is None else
                   Block(halo_extend(b.tensor, b.extend.__self__), b.index, b.relu, sorted_index=b.sorted_index)
                   for b in blocks]
-    bad = [k for k in ("row_scale", "out_scale", "out", "gate", "aggr") if epilogue.get(k) is not None]
+    bad = [k for k in ("row_scale", "out_scale", "out", "gate", "aggr", "tables") if epilogue.get(k) is not None]
     if bad or epilogue.get("want_out") is False:
         raise NotImplementedError(f"backward with the epilogue options {bad or ['want_out=False']} is not implemented")
     if not hasattr(cache, "bwd"):

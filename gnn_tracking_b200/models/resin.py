@@ -6,15 +6,18 @@ activation), so a layer is exactly two launches and no elementwise pass."""
 from __future__ import annotations
 
 import math
+import os
 from abc import ABC, abstractmethod
 from itertools import pairwise
 
 import torch
 from torch import Tensor, nn
 
+from .. import ops
 from .._hparams import HyperparametersMixin
 from ..plan import GraphPlan, get_plan
 from .interaction_network import InteractionNetwork
+from .mlp import autocast_bf16
 
 
 def _res_coeffs(alpha: float) -> tuple[float, float] | None:
@@ -46,29 +49,70 @@ class ResidualNetwork(ABC, nn.Module):
     def forward(self, x: Tensor, edge_index: Tensor, edge_attr: Tensor) -> tuple[Tensor, Tensor, list[Tensor] | None]:
         return self._forward(x, get_plan(edge_index, x.size(0)), edge_attr)
 
-    def forward_planned(self, x: Tensor, plan: GraphPlan, edge_attr: Tensor, halo=None, sorted_edges: bool = False):
+    def forward_planned(self, x: Tensor, plan: GraphPlan, edge_attr: Tensor, halo=None, sorted_edges: bool = False,
+                        final_projection=None):
         """``sorted_edges``: ``edge_attr`` is given in the plan's destination-sorted edge order and every
         edge tensor of the stack EXCEPT the final one stays in that order (contiguous tiles instead of a
         gather / scatter through ``perm`` per layer).  The final ``edge_attr`` is in the caller's order
         as always; the entries of the returned ``edge_attrs`` list answer ``has_sorted_edges`` where
-        they are in sorted order."""
+        they are in sorted order.
+
+        ``final_projection``: a pair of packed projections (``mlp.projection_packs`` of the consumer of the
+        final node embedding: the W head).  When the stack runs its fused node launches the last one
+        computes them too and ``self.final_tables`` holds the two tables afterwards (else None)."""
         self._halo = halo
         self._sorted = sorted_edges and len(self.layers) > 0
         self._calls_left = self._n_layer_calls()
+        self.final_tables = None
+        self._fused = self._fused_state(x, final_projection) if self.fused_ok(x, edge_attr, halo) else None
         try:
             if self._sorted:
                 edge_attr = mark_sorted_edges(edge_attr)
-            return self._forward(x, plan, edge_attr)
+            out = self._forward(x, plan, edge_attr)
+            if self._fused is not None:  # every node launch handed the aggregate back zeroed: keep it for the next graph
+                self.__dict__["_aggr_buf"] = self._fused["aggr"]
+            return out
         finally:
             self._halo = None
             self._sorted = False
+            self._fused = None
 
     _halo = None
     _sorted = False
     _calls_left = 0
+    _fused = None
+    final_tables = None
 
     def _n_layer_calls(self) -> int:
         return len(self.layers)
+
+    def _call_sequence(self) -> list[int]:
+        """Layer index of every ``_layer`` call of ``_forward``, in order."""
+        return list(range(len(self.layers)))
+
+    def fused_ok(self, x: Tensor, edge_attr: Tensor, halo=None) -> bool:
+        """Does the two-launches-per-layer path (``InteractionNetwork.forward_fused``) apply?  fp32 without
+        autograd on one GPU, every layer 64 / 64 / 64 on the tensor-core tiles, at least two edges per node
+        (the condition under which the node blocks are pre-projected at all)."""
+        if (halo is not None or len(self.layers) == 0 or os.environ.get("GTB_NO_NODE_WS") or autocast_bf16()
+                or 2 * x.size(0) > edge_attr.size(0) or x.size(0) == 0 or ops.default_impl() == ops.IMPL_FFMA):
+            return False
+        if torch.is_grad_enabled() and (x.requires_grad or edge_attr.requires_grad
+                                        or any(p.requires_grad for p in self.parameters())):
+            return False
+        return all(isinstance(l, InteractionNetwork) and l.fused_wide() for l in self.layers)
+
+    def _fused_state(self, x: Tensor, final_projection):
+        seq = self._call_sequence()
+        projs = {i: self.layers[i].input_projection() for i in set(seq)}
+        if any(v is None for v in projs.values()):
+            return None
+        # the zero-filled aggregate of the previous forward is reused when it fits (popped: an exception in the
+        # middle of a stack leaves it dirty and it is then simply dropped)
+        aggr = self.__dict__.pop("_aggr_buf", None)
+        if aggr is None or aggr.size(0) != x.size(0) or aggr.device != x.device:
+            aggr = torch.zeros((x.size(0), 64), dtype=torch.float32, device=x.device)
+        return {"seq": seq, "k": 0, "projs": projs, "final": final_projection, "tables": None, "x": None, "aggr": aggr}
 
     def _layer(self, i: int, x: Tensor, plan: GraphPlan, e: Tensor, *, first: bool, residue: Tensor | None):
         """IN layer i on (act(x), act(e)) with the residual onto the un-activated
@@ -85,8 +129,24 @@ class ResidualNetwork(ABC, nn.Module):
         return xo, (mark_sorted_edges(eo) if out_sorted else eo)
 
     def _layer_call(self, i, x, plan, e, first, out_sorted, kw):
-        return self.layers[i].forward_planned(x, plan, e, relu_x=not first, relu_e=not first, halo=self._halo,
-                                                e_sorted=has_sorted_edges(e), out_sorted=out_sorted, **kw)
+        f = self._fused
+        if f is None:
+            return self.layers[i].forward_planned(x, plan, e, relu_x=not first, relu_e=not first, halo=self._halo,
+                                                    e_sorted=has_sorted_edges(e), out_sorted=out_sorted, **kw)
+        k = f["k"]
+        assert f["seq"][k] == i
+        last = k + 1 == len(f["seq"])
+        nxt = f["final"] if last else f["projs"][f["seq"][k + 1]]
+        # the tables computed by the previous call belong to ITS output: any other input projects for itself
+        tables = f["tables"] if f["x"] is x else None
+        xo, eo, nt = self.layers[i].forward_fused(
+            x, plan, e, relu_x=not first, relu_e=not first, res=kw.get("res"), res_a=kw.get("res_a", 0.0),
+            res_b=kw.get("res_b", 1.0), e_sorted=has_sorted_edges(e), out_sorted=out_sorted, tables=tables,
+            aggr=f["aggr"], nxt=nxt, nxt_relu=not last)
+        f["k"], f["tables"], f["x"] = k + 1, nt, xo
+        if last:
+            self.final_tables = nt
+        return xo, eo
 
     @abstractmethod
     def _forward(self, x: Tensor, plan: GraphPlan, edge_attr: Tensor):
@@ -122,6 +182,9 @@ class Skip2ResidualNetwork(ResidualNetwork):
 
     def _n_layer_calls(self) -> int:
         return 2 * max(len(self.layers) - 1, 0)
+
+    def _call_sequence(self) -> list[int]:
+        return [i for pair in pairwise(range(len(self.layers))) for i in pair]
 
     def _forward(self, x, plan, edge_attr):
         edge_attrs = [edge_attr] if self._collect_hidden_edge_embeds else None
@@ -190,5 +253,7 @@ class ResIN(nn.Module, HyperparametersMixin):
     def forward(self, x: Tensor, edge_index: Tensor, edge_attr: Tensor):
         return self.network.forward(x, edge_index, edge_attr)
 
-    def forward_planned(self, x: Tensor, plan: GraphPlan, edge_attr: Tensor, halo=None, sorted_edges: bool = False):
-        return self.network.forward_planned(x, plan, edge_attr, halo=halo, sorted_edges=sorted_edges)
+    def forward_planned(self, x: Tensor, plan: GraphPlan, edge_attr: Tensor, halo=None, sorted_edges: bool = False,
+                        final_projection=None):
+        return self.network.forward_planned(x, plan, edge_attr, halo=halo, sorted_edges=sorted_edges,
+                                            final_projection=final_projection)

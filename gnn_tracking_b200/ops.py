@@ -16,7 +16,7 @@ from ._lib import (ACT_NONE, ACT_RELU, ACT_SIGMOID_AFFINE, IMPL_AUTO, IMPL_FFMA,
 
 __all__ = ["ACT_NONE", "ACT_RELU", "ACT_SIGMOID_AFFINE", "IMPL_AUTO", "IMPL_FFMA", "IMPL_TCGEN05", "Block",
            "PackedMLP", "fused_mlp", "pack_linears", "require_cuda", "default_impl", "launch_count", "rows_gather",
-           "tc_slots", "in_edge_bf16", "pack_in_edge_bf16"]
+           "tc_slots", "in_edge_bf16", "pack_in_edge_bf16", "in_node_fused"]
 
 _LAUNCHES = 0  # kernels launched through the C ABI by this process (bench.py reports it)
 
@@ -238,6 +238,42 @@ def fused_mlp(blocks: Sequence[Block], n_rows: int, packed: PackedMLP, *, final_
         _count(1)
     del keep
     return out if want_out else None
+
+
+def in_node_fused(x: Tensor, relu_x: bool, *, aggr: Tensor | None = None, zero_aggr: bool = True,
+                  packed_obj: PackedMLP | None = None, res: Tensor | None = None, res_a: float = 0.0, res_b: float = 1.0,
+                  proj: tuple[PackedMLP, PackedMLP] | None = None, proj_relu: bool = False):
+    """Node side of a 64-wide Interaction-Network layer in one launch (``gtb_in_node_fused_f32`` in
+    include/gtb200.h): returns ``(x_out, p_a, p_b)`` -- the object model's output with the residual fused in
+    (None without ``packed_obj``: projection only) and the two per-node products the next consumer gathers
+    (None without ``proj``).  ``aggr`` is handed back zeroed."""
+    x = _f32c(x)
+    dev = require_cuda(x, aggr, res)
+    n = x.size(0)
+    if x.size(1) != 64 or (aggr is not None and tuple(aggr.shape) != (n, 64)):
+        raise ValueError("in_node_fused takes 64-column tables")
+    for pk, dims in ((packed_obj, (128, 64, 64, 64)), (proj[0] if proj else None, (64, 64)), (proj[1] if proj else None, (64, 64))):
+        if pk is not None and (pk.impl != IMPL_TCGEN05 or pk.dims != dims):
+            raise ValueError(f"in_node_fused: weights must be tcgen05 packs of dims {dims}, got {pk.dims} (impl {pk.impl})")
+    if packed_obj is not None and packed_obj.block_widths != (64, 64):
+        raise ValueError("in_node_fused: the object model must be packed for the blocks (64, 64)")
+    x_out = torch.empty((n, 64), dtype=torch.float32, device=dev) if packed_obj is not None else None
+    p_a = torch.empty((n, 64), dtype=torch.float32, device=dev) if proj else None
+    p_b = torch.empty((n, 64), dtype=torch.float32, device=dev) if proj else None
+    if res is not None:
+        res = _f32c(res)
+    if n:
+        with on_device(dev):
+            check(lib().gtb_in_node_fused_f32(
+                x.data_ptr(), x.stride(0), int(relu_x), aggr.data_ptr() if aggr is not None else None,
+                aggr.stride(0) if aggr is not None else 0, int(zero_aggr), n,
+                packed_obj.buf.data_ptr() if packed_obj is not None else None, res_a, res_b,
+                res.data_ptr() if res is not None else None, res.stride(0) if res is not None else 0,
+                x_out.data_ptr() if x_out is not None else None, 64,
+                proj[0].buf.data_ptr() if proj else None, proj[1].buf.data_ptr() if proj else None, int(proj_relu),
+                p_a.data_ptr() if proj else None, 64, p_b.data_ptr() if proj else None, 64, stream_ptr(dev)))
+        _count(1)
+    return x_out, p_a, p_b
 
 
 def pack_in_edge_bf16(weights: Sequence[Tensor], biases: Sequence[Tensor | None]) -> Tensor:

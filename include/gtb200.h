@@ -207,6 +207,22 @@ int gtb_in_node_forward_f32(const float* x, int32_t x_ld, int32_t relu_x,
                             float res_a, float res_b, const float* res, int32_t res_ld,
                             float* x_out, int32_t xo_ld, void* stream);
 
+/* Node side of one 64-wide Interaction-Network layer in ONE launch (csrc/node_ws.cu): the object model with
+ * the residual of the stack, the two per-node products the NEXT consumer gathers (GTB_SRC_PROJECTED blocks of
+ * the next layer's relational model, interaction_network.py:75-89, or of the W head, edge_classifier.py:108-117),
+ * and the aggregate handed back zeroed for the next layer's edge kernel:
+ *   x_out = res_a * res + res_b * MLP_obj(cat[act(x), aggr])     (interaction_network.py:92-103, resin.py:17-42)
+ *   p_a   = act'(x_out) Wa^T,  p_b = act'(x_out) Wb^T            (act' = ReLU iff proj_relu)
+ *   aggr  = 0                                                     (iff zero_aggr)
+ * packed_obj: gtb_mlp_pack image (GTB_IMPL_TCGEN05) of dims {128, 64, 64, 64} with blocks {64, 64}; NULL:
+ * projection only, p_a / p_b of act'(x).  packed_pa / packed_pb: gtb_mlp_pack images of one bias-free Linear
+ * {64, 64} each; NULL: no projections.  All tables fp32, 64 columns, row strides in elements (multiples of 4),
+ * pointers 16-byte aligned; res may be NULL (no residual term) or alias x. */
+int gtb_in_node_fused_f32(const float* x, int32_t x_ld, int32_t relu_x, float* aggr, int32_t aggr_ld, int32_t zero_aggr,
+                          int64_t n_nodes, const void* packed_obj, float res_a, float res_b, const float* res, int32_t res_ld,
+                          float* x_out, int32_t xo_ld, const void* packed_pa, const void* packed_pb, int32_t proj_relu,
+                          float* p_a, int32_t pa_ld, float* p_b, int32_t pb_ld, void* stream);
+
 /* bf16 variant of the edge kernel for the reference's mixed-precision runs (torch.autocast(bfloat16) around
  * models/interaction_network.py:75-89; BASELINE config 3: GraphTCN with node = edge = hidden width 128).
  * All feature tables are bf16 [*, ld] (ld in elements, 16-byte multiples), fp32 accumulation on the tensor
