@@ -74,6 +74,7 @@ SIGNATURES = {
                                           _f32, _f32, _vp, _i32, _vp, _i32, _vp]),
     "gtb_in_node_fused_f32": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _i64, _vp, _f32, _f32, _vp, _i32, _vp, _i32, _vp, _vp,
                                         _i32, _vp, _i32, _vp, _i32, _vp]),
+    "gtb_edge_encoder_f32": (C.c_int, [_vp, _i32, _vp, _i64, _i64, _vp, _vp, _vp, _i32, _vp, _i32, _vp]),
     "gtb_in_edge_bf16_packed_bytes": (_sz, []),
     "gtb_in_edge_bf16_pack": (C.c_int, [C.POINTER(_vp), C.POINTER(_vp), _vp, _vp]),
     "gtb_in_edge_forward_bf16": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _vp,

@@ -38,6 +38,9 @@ int tc_timeout_flag(int*);
 int in_node_ws(const float*, int32_t, int32_t, float*, int32_t, int32_t, int64_t, const void*, float, float, const float*, int32_t,
                float*, int32_t, const void*, const void*, int32_t, float*, int32_t, float*, int32_t, cudaStream_t);
 int nw_fault_flag(int*);
+int edge_encoder_ws(const float*, int32_t, const int32_t*, int64_t, int64_t, const float*, const float*, const void*, int32_t, float*,
+                    int32_t, cudaStream_t);
+int en_fault_flag(int*);
 int oc_potentials_grad(const float*, const float*, int32_t, const int64_t*, const int32_t*, int64_t, const int32_t*, int32_t,
                        float, int64_t, const float*, float*, float*, float*, cudaStream_t);
 int dbscan(const float*, int, int64_t, double, int, unsigned char*, int*, int*, cudaStream_t);
@@ -114,7 +117,9 @@ int gtb_debug_tc_timeout(int* flag) {
   int rc = tc_timeout_flag(&a);
   if (rc == GTB_OK) rc = ew_fault_flag(&b);
   if (rc == GTB_OK) rc = nw_fault_flag(&c);
-  *flag = a ? a : (b ? 16 + b : (c ? 32 + c : 0));
+  int d = 0;
+  if (rc == GTB_OK) rc = en_fault_flag(&d);
+  *flag = a ? a : (b ? 16 + b : (c ? 32 + c : (d ? 48 + d : 0)));
   return rc;
 }
 int gtb_debug_tc_profile(int enable, long long* out32) {
@@ -146,6 +151,11 @@ int gtb_in_node_fused_f32(const float* x, int32_t x_ld, int32_t relu_x, float* a
                           float* p_a, int32_t pa_ld, float* p_b, int32_t pb_ld, void* stream) {
   return in_node_ws(x, x_ld, relu_x, aggr, aggr_ld, zero_aggr, n_nodes, packed_obj, res_a, res_b, res, res_ld, x_out, xo_ld,
                     packed_pa, packed_pb, proj_relu, p_a, pa_ld, p_b, pb_ld, static_cast<cudaStream_t>(stream));
+}
+
+int gtb_edge_encoder_f32(const float* x, int32_t x_ld, const int32_t* index, int64_t n_rows, int64_t x_rows, const float* w0,
+                         const float* b0, const void* packed_w1, int32_t final_relu, float* out, int32_t out_ld, void* stream) {
+  return edge_encoder_ws(x, x_ld, index, n_rows, x_rows, w0, b0, packed_w1, final_relu, out, out_ld, static_cast<cudaStream_t>(stream));
 }
 
 size_t gtb_dbscan_grid_workspace_bytes(int64_t n) { return dbscan_grid_workspace_bytes(n); }

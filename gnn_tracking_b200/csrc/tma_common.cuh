@@ -32,7 +32,8 @@ inline EncodeTiledFn encode_fn() {
 // instruction supplies four row coordinates and moves four box_cols-wide rows.
 // Returns false when the driver refuses the map (bad alignment, unsupported driver).
 inline bool make_map_2d(CUtensorMap* map, const void* base, CUtensorMapDataType dt, int elem_bytes, uint64_t rows,
-                        uint64_t cols, uint64_t ld, uint32_t box_cols, uint32_t box_rows) {
+                        uint64_t cols, uint64_t ld, uint32_t box_cols, uint32_t box_rows,
+                        CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) return false;
   const cuuint64_t dims[2] = {cols, rows};
@@ -40,7 +41,7 @@ inline bool make_map_2d(CUtensorMap* map, const void* base, CUtensorMapDataType 
   const cuuint32_t box[2] = {box_cols, box_rows};
   const cuuint32_t estr[2] = {1, 1};
   return fn(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+            swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // ----------------------------------------------------------------------------- device

@@ -67,8 +67,11 @@ class ECForGraphTCN(nn.Module, HyperparametersMixin):
         # gathers its 4 input columns through ``perm``): every layer then streams contiguous tiles.  Only
         # the final embedding -- the one the caller sees -- is written back in the caller's order.
         sorted_edges = len(self.ec_resin.network.layers) > 0
-        ea = self.ec_edge_encoder.forward_blocks(
-            [Block(edge_attr, plan.perm, unique_index=True) if sorted_edges else Block(edge_attr)], e, final_act=ACT_RELU)
+        if self.ec_edge_encoder.k4_ok(edge_attr):  # 4 -> 64 -> 64: the dedicated one-launch encoder
+            ea = self.ec_edge_encoder.forward_k4(edge_attr, plan.perm if sorted_edges else None, e, final_relu=True)
+        else:
+            ea = self.ec_edge_encoder.forward_blocks(
+                [Block(edge_attr, plan.perm, unique_index=True) if sorted_edges else Block(edge_attr)], e, final_act=ACT_RELU)
         nvtx.range_pop()
         nvtx.range_push("gtb.ec.resin")
         # the last node launch of the stack also multiplies the final node embedding by the head's two node

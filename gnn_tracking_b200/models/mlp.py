@@ -3,6 +3,7 @@ names (reference models/mlp.py:18-120), evaluated by the fused row-MLP kernel.""
 from __future__ import annotations
 
 import math
+import os
 from typing import Sequence
 
 import torch
@@ -337,6 +338,24 @@ class MLP(_PackedWeightsMixin, nn.Module):
 
     def forward(self, x: Tensor) -> Tensor:
         return self.forward_blocks([Block(x)], x.size(0))
+
+    # ---- the 4 -> 64 -> 64 shape of the edge classifier's edge encoder: one warp-specialised launch
+    def k4_ok(self, x: Tensor) -> bool:
+        lin = self.linears
+        if (len(lin) != 2 or lin[0].in_features != 4 or lin[0].out_features != 64 or lin[1].out_features != 64
+                or os.environ.get("GTB_NO_ENC_WS") or autocast_bf16() or ops.default_impl() == ops.IMPL_FFMA
+                or x.dim() != 2 or x.size(1) != 4 or x.dtype != torch.float32):
+            return False
+        return not (torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())))
+
+    def forward_k4(self, x: Tensor, index: Tensor | None, n_rows: int, *, final_relu: bool) -> Tensor:
+        """``act(MLP(x[index]))`` for the shape ``k4_ok`` accepts (``ops.edge_encoder``): the K = 4 first Linear
+        on the CUDA cores, the 64 x 64 Linear on the tensor core, rows gathered by TMA."""
+        if "_cache_k4" not in self.__dict__:
+            self.__dict__["_cache_k4"] = PackedCache()
+        lin = self.linears
+        packed = self._cache_k4.get([lin[1]], impl=ops.IMPL_TCGEN05)[0][0]
+        return ops.edge_encoder(x, index, n_rows, lin[0].weight, lin[0].bias, packed, final_relu or self._last_act)
 
 
 class ResFCNN(_PackedWeightsMixin, nn.Module):

@@ -16,7 +16,7 @@ from ._lib import (ACT_NONE, ACT_RELU, ACT_SIGMOID_AFFINE, IMPL_AUTO, IMPL_FFMA,
 
 __all__ = ["ACT_NONE", "ACT_RELU", "ACT_SIGMOID_AFFINE", "IMPL_AUTO", "IMPL_FFMA", "IMPL_TCGEN05", "Block",
            "PackedMLP", "fused_mlp", "pack_linears", "require_cuda", "default_impl", "launch_count", "rows_gather",
-           "tc_slots", "in_edge_bf16", "pack_in_edge_bf16", "in_node_fused"]
+           "tc_slots", "in_edge_bf16", "pack_in_edge_bf16", "in_node_fused", "edge_encoder"]
 
 _LAUNCHES = 0  # kernels launched through the C ABI by this process (bench.py reports it)
 
@@ -274,6 +274,28 @@ def in_node_fused(x: Tensor, relu_x: bool, *, aggr: Tensor | None = None, zero_a
                 p_a.data_ptr() if proj else None, 64, p_b.data_ptr() if proj else None, 64, stream_ptr(dev)))
         _count(1)
     return x_out, p_a, p_b
+
+
+def edge_encoder(x: Tensor, index: Tensor | None, n_rows: int, w0: Tensor, b0: Tensor | None, packed_w1: PackedMLP,
+                 final_relu: bool) -> Tensor:
+    """Two-Linear encoder 4 -> 64 -> 64 over gathered rows in one launch (``gtb_edge_encoder_f32`` in
+    include/gtb200.h): ``act(W1 relu(W0 x[index] + b0) + b1)``."""
+    x = _f32c(x)
+    dev = require_cuda(x, index, w0, b0)
+    if x.size(1) != 4 or tuple(w0.shape) != (64, 4) or packed_w1.impl != IMPL_TCGEN05 or packed_w1.dims != (64, 64):
+        raise ValueError("edge_encoder takes 4 feature columns, a [64, 4] first Linear and a tcgen05 pack of a 64 -> 64 Linear")
+    if x.stride(0) % 4:
+        x = x.contiguous()
+    w0 = w0.detach().to(torch.float32).contiguous()
+    b0 = None if b0 is None else b0.detach().to(torch.float32).contiguous()
+    out = torch.empty((n_rows, 64), dtype=torch.float32, device=dev)
+    if n_rows:
+        with on_device(dev):
+            check(lib().gtb_edge_encoder_f32(x.data_ptr(), x.stride(0), _idx(index), n_rows, x.size(0), w0.data_ptr(),
+                                             b0.data_ptr() if b0 is not None else None, packed_w1.buf.data_ptr(),
+                                             int(final_relu), out.data_ptr(), out.stride(0), stream_ptr(dev)))
+        _count(1)
+    return out
 
 
 def pack_in_edge_bf16(weights: Sequence[Tensor], biases: Sequence[Tensor | None]) -> Tensor:

@@ -207,6 +207,16 @@ int gtb_in_node_forward_f32(const float* x, int32_t x_ld, int32_t relu_x,
                             float res_a, float res_b, const float* res, int32_t res_ld,
                             float* x_out, int32_t xo_ld, void* stream);
 
+/* Edge encoder of the edge classifier in one launch (csrc/enc_ws.cu): a two-Linear MLP 4 -> 64 -> 64 over gathered
+ * rows (edge_classifier.py:103 `relu(ec_edge_encoder(edge_attr))`, models/mlp.py:18-62 with L = 2):
+ *   out[r] = act(W1 relu(W0 x[index ? index[r] : r] + b0) + b1),   act = ReLU iff final_relu
+ * x fp32 [x_rows, x_ld] with 4 feature columns (x_rows: rows of the gathered table, 0 = unknown), index int32 [n_rows]
+ * or NULL, w0 fp32 [64, 4] and b0 fp32 [64] / NULL in nn.Linear layout (the first Linear runs on the CUDA cores),
+ * packed_w1: gtb_mlp_pack image (GTB_IMPL_TCGEN05) of the one Linear {64, 64}, out fp32 [n_rows, out_ld].
+ * Row strides in elements, multiples of 4; pointers 16-byte aligned. */
+int gtb_edge_encoder_f32(const float* x, int32_t x_ld, const int32_t* index, int64_t n_rows, int64_t x_rows, const float* w0,
+                         const float* b0, const void* packed_w1, int32_t final_relu, float* out, int32_t out_ld, void* stream);
+
 /* Node side of one 64-wide Interaction-Network layer in ONE launch (csrc/node_ws.cu): the object model with
  * the residual of the stack, the two per-node products the NEXT consumer gathers (GTB_SRC_PROJECTED blocks of
  * the next layer's relational model, interaction_network.py:75-89, or of the W head, edge_classifier.py:108-117),

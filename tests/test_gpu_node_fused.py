@@ -126,3 +126,42 @@ def test_fused_path_is_off_under_grad_and_small_graphs():
     out = m.forward_tensors(x, ei, torch.randn(1000, 4, device="cuda"))
     out["W"].sum().backward()  # the autograd path still works on the same module
     assert m.W.layers[0].weight.grad is not None
+
+
+@pytest.mark.parametrize("n", [1, 127, 128, 300, 70001])
+@pytest.mark.parametrize("gather,bias,final_relu", [(True, False, True), (False, True, False), (True, True, True)])
+def test_edge_encoder_vs_float64(n, gather, bias, final_relu):
+    """``gtb_edge_encoder_f32`` (csrc/enc_ws.cu): 4 -> 64 -> 64 over rows gathered through a permutation."""
+    from gnn_tracking_b200 import ops
+    gen = torch.Generator().manual_seed(5 * n + gather)
+    x = torch.randn(n, 4, generator=gen) * 2
+    (w0, b0), (w1, b1) = _lin(gen, 64, 4, bias), _lin(gen, 64, 64, bias)
+    perm = torch.randperm(n, generator=gen).to(torch.int32) if gather else None
+    packed = ops.pack_linears([w1.cuda()], [b1.cuda() if bias else None], ops.IMPL_TCGEN05)
+    out = ops.edge_encoder(x.cuda(), perm.cuda() if gather else None, n, w0.cuda(), b0.cuda() if bias else None, packed, final_relu)
+    torch.cuda.synchronize()
+    d = torch.float64
+    xs = x[perm.long()] if gather else x
+    h = xs.to(d) @ w0.to(d).T
+    if bias:
+        h = h + b0.to(d)
+    y = torch.relu(h) @ w1.to(d).T
+    if bias:
+        y = y + b1.to(d)
+    close(out, torch.relu(y) if final_relu else y, what="encoder")
+
+
+def test_ec_uses_the_one_launch_encoder(monkeypatch):
+    from gnn_tracking_b200 import ops
+    m = _ec("skip1", 1).cuda()
+    x = torch.randn(500, 14, device="cuda")
+    ei = torch.randint(0, 500, (2, 6000), device="cuda")
+    ea = torch.randn(6000, 4, device="cuda")
+    with torch.no_grad():
+        assert m.ec_edge_encoder.k4_ok(ea)
+        a = m.forward_tensors(x, ei, ea)
+        monkeypatch.setenv("GTB_NO_ENC_WS", "1")
+        assert not m.ec_edge_encoder.k4_ok(ea)
+        b = m.forward_tensors(x, ei, ea)
+    for k in ("W", "node_embedding", "edge_embedding"):
+        close(a[k], b[k], tol=2e-6, what=k)
