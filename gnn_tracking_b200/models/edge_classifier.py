@@ -81,7 +81,8 @@ class ECForGraphTCN(nn.Module, HyperparametersMixin):
                 if hp.use_intermediate_edge_embeddings else 1)
         final_proj = None
         if hp.use_node_embedding and self.ec_resin.network.fused_ok(h, ea, halo):
-            final_proj = projection_packs(self.W, [hp.interaction_node_dim] * 2 + [hp.interaction_edge_dim] * n_eb)
+            packs = projection_packs(self.W, [hp.interaction_node_dim] * 2 + [hp.interaction_edge_dim] * n_eb)
+            final_proj = None if packs is None else (packs, 0)  # the head's blocks: [h[src], h[dst], e_0 ..]
         h, ea, eas = self.ec_resin.forward_planned(h, plan, ea, halo=halo, sorted_edges=sorted_edges,
                                                    final_projection=final_proj)
         head_tables = self.ec_resin.network.final_tables

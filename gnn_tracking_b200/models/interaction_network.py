@@ -17,6 +17,21 @@ from ..utils.asserts import assert_feat_dim
 from .mlp import MLP, autocast_bf16, projection_packs
 
 
+def _project_pair(x: Tensor, fused: dict | None, packs, proj_relu: bool, src_side: int, halo, relu_x: bool = False):
+    """One ``ops.in_node_fused`` launch -- projection only (``fused`` None: returns the pair of tables of
+    ``act(x)``) or object model + projections (returns ``(x_out, pair)``) -- with the source-side table
+    of the pair written into the halo exchange's extended table and completed by the exchange."""
+    outs = [None, None]
+    if halo is not None:
+        outs[src_side] = halo.buffer(64, x)
+    xo, pa, pb = ops.in_node_fused(x, relu_x, proj=packs, proj_relu=proj_relu, out_pa=outs[0], out_pb=outs[1],
+                                   **(fused or {}))
+    pair = [pa, pb]
+    if halo is not None:
+        pair[src_side] = halo.finish(halo.start(pair[src_side]))
+    return tuple(pair) if fused is None else (xo, tuple(pair))
+
+
 class InteractionNetwork(nn.Module, HyperparametersMixin):
     def __init__(self, *, node_indim: int, edge_indim: int, node_outdim: int = 3, edge_outdim: int = 4,
                  node_hidden_dim: int = 40, edge_hidden_dim: int = 40, aggr: str = "add"):
@@ -80,26 +95,33 @@ class InteractionNetwork(nn.Module, HyperparametersMixin):
 
     def forward_fused(self, x: Tensor, plan: GraphPlan, edge_attr: Tensor, *, relu_x: bool, relu_e: bool,
                       res: Tensor | None, res_a: float, res_b: float, e_sorted: bool, out_sorted: bool,
-                      tables: tuple[Tensor, Tensor] | None, aggr: Tensor, nxt=None, nxt_relu: bool = True):
+                      tables: tuple[Tensor, Tensor] | None, aggr: Tensor, nxt=None, nxt_relu: bool = True,
+                      nxt_src_side: int = 1, halo=None):
         """The layer as two launches (no-grad fp32, ``fused_wide()`` shapes): the edge kernel on the
         pre-projected node tables ``tables`` = (P_i, P_j) it is handed, and ONE node launch
         (``ops.in_node_fused``) that runs the object model with the residual, hands ``aggr`` back zeroed
         and computes the tables of the next consumer ``nxt`` (a pair of packed projections: the next
-        layer's ``input_projection()`` or the W head's).  Returns ``(x_tilde, e_tilde, next_tables)``."""
+        layer's ``input_projection()`` or the W head's).  Returns ``(x_tilde, e_tilde, next_tables)``.
+
+        ``halo`` (node-partitioned graph): the table gathered by SOURCE ids -- position ``nxt_src_side`` of
+        the next consumer's pair, position 1 of this layer's -- is written into the extended table of the
+        exchange and completed with the other ranks' rows (one all-to-all-v) before it is handed on."""
         n, e = x.size(0), edge_attr.size(0)
         if tables is None:  # first layer of a stack: projection-only launch
-            _, pa, pb = ops.in_node_fused(x, False, proj=self.input_projection(), proj_relu=relu_x)
-            tables = (pa, pb)
+            tables = _project_pair(x, None, self.input_projection(), relu_x, 1, halo)
         e_tilde = self.relational_model.forward_blocks(
-            [Block(x, plan.dst_sorted, relu_x, sorted_index=True), Block(x, plan.src_sorted, relu_x),
+            [Block(x, plan.dst_sorted, relu_x, sorted_index=True),
+             Block(x, plan.src_sorted, relu_x, extend=None if halo is None else halo.extend),
              Block(edge_attr, None, relu_e) if e_sorted else Block(edge_attr, plan.perm, relu_e, unique_index=True)],
             e, out_index=None if out_sorted else plan.perm, aggr=aggr, seg_id=plan.dst_sorted, rowptr=plan.rowptr,
             tables={0: tables[0], 1: tables[1]})
         obj = self.object_model
         packed_obj = obj._cache.get(obj.linears, (64, 64), (False, False))[0][0]
-        x_tilde, pa, pb = ops.in_node_fused(x, relu_x, aggr=aggr, zero_aggr=True, packed_obj=packed_obj, res=res,
-                                            res_a=res_a, res_b=res_b, proj=nxt, proj_relu=nxt_relu)
-        return x_tilde, e_tilde, (None if nxt is None else (pa, pb))
+        fused = dict(aggr=aggr, zero_aggr=True, packed_obj=packed_obj, res=res, res_a=res_a, res_b=res_b)
+        if nxt is None:
+            return ops.in_node_fused(x, relu_x, **fused)[0], e_tilde, None
+        x_tilde, nt = _project_pair(x, fused, nxt, nxt_relu, nxt_src_side, halo, relu_x=relu_x)
+        return x_tilde, e_tilde, nt
 
     # ------------------------------------------------------------------ bf16 (torch.autocast) path
     def _bf16_wide(self) -> bool:

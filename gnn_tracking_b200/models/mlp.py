@@ -180,8 +180,9 @@ def _run_nograd(cache: PackedCache, linears: Sequence[nn.Linear], blocks: Sequen
     # ``tables``: {block position: its pre-projected table}, already computed by the producer of the block's
     # tensor (``ops.in_node_fused``: the previous layer's node kernel) -- no projection launch here
     for i, table in (tables or {}).items():
-        if not projected[i] or blocks[i].extend is not None:
+        if not projected[i]:
             raise AssertionError("a pre-projected table was supplied for a block this call does not project")
+        # (a block that crosses a halo exchange comes with its table already extended by the owned + halo rows)
         cur[i] = Block(table, blocks[i].index, False, projected=True, sorted_index=blocks[i].sorted_index)
     # blocks that cross the halo exchange of a node-partitioned graph first: their transfer runs under the
     # launches of the other blocks' projections

@@ -57,9 +57,10 @@ class ResidualNetwork(ABC, nn.Module):
         as always; the entries of the returned ``edge_attrs`` list answer ``has_sorted_edges`` where
         they are in sorted order.
 
-        ``final_projection``: a pair of packed projections (``mlp.projection_packs`` of the consumer of the
-        final node embedding: the W head).  When the stack runs its fused node launches the last one
-        computes them too and ``self.final_tables`` holds the two tables afterwards (else None)."""
+        ``final_projection``: ``(pair of packed projections, position of the SOURCE-gathered block in the
+        pair)`` -- ``mlp.projection_packs`` of the consumer of the final node embedding: the W head.  When the
+        stack runs its fused node launches the last one computes them too and ``self.final_tables`` holds
+        the two tables afterwards (else None)."""
         self._halo = halo
         self._sorted = sorted_edges and len(self.layers) > 0
         self._calls_left = self._n_layer_calls()
@@ -92,9 +93,9 @@ class ResidualNetwork(ABC, nn.Module):
 
     def fused_ok(self, x: Tensor, edge_attr: Tensor, halo=None) -> bool:
         """Does the two-launches-per-layer path (``InteractionNetwork.forward_fused``) apply?  fp32 without
-        autograd on one GPU, every layer 64 / 64 / 64 on the tensor-core tiles, at least two edges per node
+        autograd, every layer 64 / 64 / 64 on the tensor-core tiles, at least two edges per (owned) node
         (the condition under which the node blocks are pre-projected at all)."""
-        if (halo is not None or len(self.layers) == 0 or os.environ.get("GTB_NO_NODE_WS") or autocast_bf16()
+        if (len(self.layers) == 0 or os.environ.get("GTB_NO_NODE_WS") or autocast_bf16()
                 or 2 * x.size(0) > edge_attr.size(0) or x.size(0) == 0 or ops.default_impl() == ops.IMPL_FFMA):
             return False
         if torch.is_grad_enabled() and (x.requires_grad or edge_attr.requires_grad
@@ -112,7 +113,9 @@ class ResidualNetwork(ABC, nn.Module):
         aggr = self.__dict__.pop("_aggr_buf", None)
         if aggr is None or aggr.size(0) != x.size(0) or aggr.device != x.device:
             aggr = torch.zeros((x.size(0), 64), dtype=torch.float32, device=x.device)
-        return {"seq": seq, "k": 0, "projs": projs, "final": final_projection, "tables": None, "x": None, "aggr": aggr}
+        final, side = final_projection if final_projection is not None else (None, 1)
+        return {"seq": seq, "k": 0, "projs": projs, "final": final, "final_src_side": side, "tables": None, "x": None,
+                "aggr": aggr}
 
     def _layer(self, i: int, x: Tensor, plan: GraphPlan, e: Tensor, *, first: bool, residue: Tensor | None):
         """IN layer i on (act(x), act(e)) with the residual onto the un-activated
@@ -142,7 +145,7 @@ class ResidualNetwork(ABC, nn.Module):
         xo, eo, nt = self.layers[i].forward_fused(
             x, plan, e, relu_x=not first, relu_e=not first, res=kw.get("res"), res_a=kw.get("res_a", 0.0),
             res_b=kw.get("res_b", 1.0), e_sorted=has_sorted_edges(e), out_sorted=out_sorted, tables=tables,
-            aggr=f["aggr"], nxt=nxt, nxt_relu=not last)
+            aggr=f["aggr"], nxt=nxt, nxt_relu=not last, nxt_src_side=f["final_src_side"] if last else 1, halo=self._halo)
         f["k"], f["tables"], f["x"] = k + 1, nt, xo
         if last:
             self.final_tables = nt

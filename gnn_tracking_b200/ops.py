@@ -242,11 +242,13 @@ def fused_mlp(blocks: Sequence[Block], n_rows: int, packed: PackedMLP, *, final_
 
 def in_node_fused(x: Tensor, relu_x: bool, *, aggr: Tensor | None = None, zero_aggr: bool = True,
                   packed_obj: PackedMLP | None = None, res: Tensor | None = None, res_a: float = 0.0, res_b: float = 1.0,
-                  proj: tuple[PackedMLP, PackedMLP] | None = None, proj_relu: bool = False):
+                  proj: tuple[PackedMLP, PackedMLP] | None = None, proj_relu: bool = False,
+                  out_pa: Tensor | None = None, out_pb: Tensor | None = None):
     """Node side of a 64-wide Interaction-Network layer in one launch (``gtb_in_node_fused_f32`` in
     include/gtb200.h): returns ``(x_out, p_a, p_b)`` -- the object model's output with the residual fused in
     (None without ``packed_obj``: projection only) and the two per-node products the next consumer gathers
-    (None without ``proj``).  ``aggr`` is handed back zeroed."""
+    (None without ``proj``).  ``aggr`` is handed back zeroed.  ``out_pa`` / ``out_pb``: tables of at least as many
+    rows to write the products into (the extended table of a halo exchange: the owned rows in place)."""
     x = _f32c(x)
     dev = require_cuda(x, aggr, res)
     n = x.size(0)
@@ -258,8 +260,14 @@ def in_node_fused(x: Tensor, relu_x: bool, *, aggr: Tensor | None = None, zero_a
     if packed_obj is not None and packed_obj.block_widths != (64, 64):
         raise ValueError("in_node_fused: the object model must be packed for the blocks (64, 64)")
     x_out = torch.empty((n, 64), dtype=torch.float32, device=dev) if packed_obj is not None else None
-    p_a = torch.empty((n, 64), dtype=torch.float32, device=dev) if proj else None
-    p_b = torch.empty((n, 64), dtype=torch.float32, device=dev) if proj else None
+    p_a = p_b = None
+    if proj:
+        for o in (out_pa, out_pb):
+            if o is not None and (o.dtype != torch.float32 or o.dim() != 2 or o.size(0) < n or o.size(1) != 64
+                                  or not o.is_contiguous() or o.device != dev):
+                raise ValueError("in_node_fused: out_pa / out_pb must be contiguous fp32 [>= n, 64] tables on the same device")
+        p_a = out_pa if out_pa is not None else torch.empty((n, 64), dtype=torch.float32, device=dev)
+        p_b = out_pb if out_pb is not None else torch.empty((n, 64), dtype=torch.float32, device=dev)
     if res is not None:
         res = _f32c(res)
     if n:
