@@ -432,9 +432,8 @@ def run_ours(args) -> None:
         ms_e2e_serial, _ = timed(step_e2e, args.steps, max(1, args.warmup))
     # outside the sampler: an nvidia-smi query takes ~100 ms and holds up kernel launches while it runs; the
     # legs above ride through that on their launch backlog, the throttled loader loop (two steps ahead) cannot
-    # N > 1: the loader's host throttle and the per-layer halo exchanges (ranks in lock step) do not mix --
-    # 9 ms/step measured at N = 2 -- so the multi-GPU line carries the serial loop only
-    ms_e2e = timed_e2e_pipelined(args.steps, max(1, args.warmup)) if world == 1 else None
+    # (at N > 1 as well: every rank runs its own loader loop, the halo exchanges keep the ranks in step)
+    ms_e2e = timed_e2e_pipelined(args.steps, max(1, args.warmup)) if not os.environ.get("GTB_BENCH_NO_PIPELINED") else None
 
     # ---- dominant kernel alone (rank 0's graph)
     dn, de = (HIDDEN, HIDDEN) if args.dims == "wide" else (5, 4)
