@@ -41,6 +41,7 @@ int nw_fault_flag(int*);
 int edge_encoder_ws(const float*, int32_t, const int32_t*, int64_t, int64_t, const float*, const float*, const void*, int32_t, float*,
                     int32_t, cudaStream_t);
 int en_fault_flag(int*);
+int at_fault_flag(int*);
 int oc_potentials_grad(const float*, const float*, int32_t, const int64_t*, const int32_t*, int64_t, const int32_t*, int32_t,
                        float, int64_t, const float*, float*, float*, float*, cudaStream_t);
 int dbscan(const float*, int, int64_t, double, int, unsigned char*, int*, int*, cudaStream_t);
@@ -119,7 +120,9 @@ int gtb_debug_tc_timeout(int* flag) {
   if (rc == GTB_OK) rc = nw_fault_flag(&c);
   int d = 0;
   if (rc == GTB_OK) rc = en_fault_flag(&d);
-  *flag = a ? a : (b ? 16 + b : (c ? 32 + c : (d ? 48 + d : 0)));
+  int e = 0;
+  if (rc == GTB_OK) rc = at_fault_flag(&e);
+  *flag = a ? a : (b ? 16 + b : (c ? 32 + c : (d ? 48 + d : (e ? 64 + e : 0))));
   return rc;
 }
 int gtb_debug_tc_profile(int enable, long long* out32) {

@@ -10,6 +10,8 @@
 
 namespace gtb {
 
+int rows_atb_tc(const float*, int, const int32_t*, int, int, const float*, int, int, int64_t, float*, int, float*, cudaStream_t, bool*);
+
 constexpr int ATB_ROWS = 64;     // rows per staged tile
 constexpr int ATB_THREADS = 256;
 
@@ -123,6 +125,11 @@ int rows_atb(const float* A, int a_ld, const int32_t* a_index, int a_relu, int k
   GTB_REQUIRE(A && B && out && ka >= 1 && ka <= 64 && nb >= 1 && nb <= 64 && a_ld >= ka && b_ld >= nb && out_ld >= nb,
               GTB_ERR_BAD_ARG, "gtb_rows_atb_f32: widths must be in [1, 64] (got %d x %d)", ka, nb);
   if (n_rows == 0) return GTB_OK;
+  {  // 64 x 64 blocks over many rows: the tensor-core kernel (atb_tc.cu)
+    bool handled = false;
+    const int rc = rows_atb_tc(A, a_ld, a_index, a_relu, ka, B, b_ld, nb, n_rows, out, out_ld, colsum, st, &handled);
+    if (rc != GTB_OK || handled) return rc;
+  }
   const int64_t n_tiles = (n_rows + ATB_ROWS - 1) / ATB_ROWS;
   // every CTA ends with 64 x 64 atomics onto the same addresses: at least 16 tiles per CTA, and no
   // more CTAs than are resident at once (3 per SM: __launch_bounds__(256, 3) -> 79 registers, no spills)
