@@ -852,8 +852,11 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
     const bool want_aggr = p.aggr != nullptr;
     const float oscale = p.out_scale ? __ldg(p.out_scale) : 1.f;
     const bool touch = p.res != nullptr || p.res_b != 1.f || p.out_scale != nullptr;
-    // a gate (backward launches only) takes the plain scalar path below
-    const bool vec = p.gate == nullptr && (N & 3) == 0 &&
+    // a gate (backward launches: the ReLU mask of the recomputed activation) rides on the 64-wide vector path;
+    // other widths take the plain scalar path below
+    const bool gate_vec = p.gate == nullptr || (N == 64 && p.out_mode != 2 && (p.gate_ld & 3) == 0 &&
+                                                (reinterpret_cast<uintptr_t>(p.gate) & 15) == 0);
+    const bool vec = gate_vec && (N & 3) == 0 &&
                      (p.out == nullptr || ((p.out_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0)) &&
                      (p.res == nullptr || ((p.res_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.res) & 15) == 0));
     if (p.out != nullptr || touch || p.gate != nullptr) {
@@ -884,6 +887,11 @@ __global__ void __launch_bounds__(2 * TC_TEAM, 1) fused_mlp_tc_kernel(const __gr
               unpack2(lo2, v.x, v.y);
               unpack2(hi2, v.z, v.w);
               if (want_aggr) sts128(sp0 + j * 4096, v);
+            }
+            if (p.gate) {  // out = gate > 0 ? value : 0 (never combined with an aggregate)
+              const float4 gq = __ldg(reinterpret_cast<const float4*>(row_ptr(p.gate + (c << 2), row0 + rr, (uint32_t)p.gate_ld * 4u)));
+              v.x = gq.x > 0.f ? v.x : 0.f; v.y = gq.y > 0.f ? v.y : 0.f;
+              v.z = gq.z > 0.f ? v.z : 0.f; v.w = gq.w > 0.f ? v.w : 0.f;
             }
             if (p.out) *reinterpret_cast<float4*>(const_cast<float*>(row_ptr(p.out + (c << 2), orow, old4))) = v;
           }
