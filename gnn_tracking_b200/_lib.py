@@ -100,6 +100,7 @@ SIGNATURES = {
     "gtb_rows_scatter_add_f32": (C.c_int, [_vp, _i32, _vp, _i64, _i32, _vp, _i32, _vp]),
     "gtb_rows_gather_f32": (C.c_int, [_vp, _i32, _vp, _i64, _i32, _vp, _i32, _vp]),
     "gtb_rows_scatter_f32": (C.c_int, [_vp, _i32, _vp, _i64, _i32, _vp, _i32, _vp]),
+    "gtb_rows_gather_add_f32": (C.c_int, [_vp, _i32, _vp, _i64, _i32, _vp, _i32, _vp]),
 }
 
 

@@ -79,7 +79,9 @@ class FusedMLPFunction(torch.autograd.Function):
         else:
             dy = _gather_rows(g_out.reshape(-1, dims[-1]).to(torch.float32), cfg["out_index"])
         if g_aggr is not None and cfg["seg_id"] is not None:
-            dy = dy + ops.rows_gather(g_aggr.contiguous(), cfg["seg_id"])
+            if dy is g_out or dy.data_ptr() == g_out.data_ptr():
+                dy = dy.clone()  # the incoming gradient is not ours to write into
+            dy = ops.rows_gather_add(g_aggr.contiguous(), cfg["seg_id"], dy.contiguous())
         grads: list = [None] * len(tensors)
         if cfg["has_res"]:
             if ctx.needs_input_grad[1 + len(tensors) - 1]:
@@ -89,7 +91,7 @@ class FusedMLPFunction(torch.autograd.Function):
             dy = dy * cfg["res_b"]
         if cfg["final_act"] == ACT_RELU:
             a_rows = _gather_rows(out.reshape(-1, dims[-1]), cfg["out_index"])
-            dy = dy * (a_rows > 0)
+            dy = torch.ops.aten.threshold_backward(dy, a_rows, 0.0)  # dy where the activation was positive, else 0
         elif cfg["final_act"] == ACT_SIGMOID_AFFINE:
             eps = cfg["act_eps"]
             s = (_gather_rows(out.reshape(-1, dims[-1]), cfg["out_index"]) - eps) / (1.0 - 2.0 * eps)
@@ -151,13 +153,13 @@ class FusedMLPFunction(torch.autograd.Function):
                     elif unique and t2.size(0) == n_rows:
                         gt = ops.fused_mlp([Block(dz)], n_rows, wslice_t, out_index=index)
                         if relu:
-                            gt = gt * (t2 > 0)
+                            gt = torch.ops.aten.threshold_backward(gt, t2, 0.0)
                     else:
                         rows = ops.fused_mlp([Block(dz)], n_rows, wslice_t)
                         gt = torch.zeros_like(t2)
                         ops.rows_scatter_add(rows, index, gt)
                         if relu:
-                            gt = gt * (t2 > 0)
+                            gt = torch.ops.aten.threshold_backward(gt, t2, 0.0)
                     grads[i] = gt if grads[i] is None else grads[i] + gt
             off += w
         if not bias_done:  # every block was a small table: the bias gradient is the plain column sum

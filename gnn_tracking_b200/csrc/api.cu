@@ -23,6 +23,7 @@ int plan_filter(const uint8_t*, int64_t, int64_t, const int32_t*, const int32_t*
                 int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, void*, size_t, cudaStream_t);
 int rows_inv_l2norm(const gtb_src_t*, int, int64_t, float, float*, cudaStream_t);
 int rows_move(const float*, int, const int32_t*, int64_t, int, float*, int, bool, cudaStream_t);
+int rows_gather_add(const float*, int, const int32_t*, int64_t, int, float*, int, cudaStream_t);
 int pack_ffma(int, const int32_t*, const float* const*, const float* const*, void*, cudaStream_t);
 int fused_mlp_ffma(const gtb_mlp_desc_t&, cudaStream_t);
 size_t tc_packed_bytes(int, const int32_t*, int, const int32_t*);
@@ -394,6 +395,11 @@ int gtb_rows_inv_l2norm_f32(const gtb_src_t* srcs, int32_t n_srcs, int64_t n_row
 int gtb_rows_gather_f32(const float* src, int32_t src_ld, const int32_t* index, int64_t n_rows, int32_t width,
                         float* dst, int32_t dst_ld, void* stream) {
   return rows_move(src, src_ld, index, n_rows, width, dst, dst_ld, false, static_cast<cudaStream_t>(stream));
+}
+
+int gtb_rows_gather_add_f32(const float* src, int32_t src_ld, const int32_t* index, int64_t n_rows, int32_t width,
+                            float* dst, int32_t dst_ld, void* stream) {
+  return rows_gather_add(src, src_ld, index, n_rows, width, dst, dst_ld, static_cast<cudaStream_t>(stream));
 }
 
 int gtb_rows_scatter_f32(const float* src, int32_t src_ld, const int32_t* index, int64_t n_rows, int32_t width,

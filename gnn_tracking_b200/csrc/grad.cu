@@ -150,10 +150,32 @@ __global__ void rows_scatter_add_kernel(const float* __restrict__ src, int src_l
   }
 }
 
+// 16-byte pieces: one vector reduction (red.global.add.v4.f32) per float4 of a row
+__global__ void rows_scatter_add_v4_kernel(const float* __restrict__ src, int src_ld, const int32_t* __restrict__ index,
+                                           int64_t n_rows, int w4, float* __restrict__ dst, int dst_ld) {
+  const int64_t total = n_rows * w4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t r = i / w4;
+    const int c = (int)(i - r * w4) << 2;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src + (size_t)r * src_ld + c));
+    float* d = dst + (size_t)__ldg(index + r) * dst_ld + c;
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(d), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+  }
+}
+
 int rows_scatter_add(const float* src, int src_ld, const int32_t* index, int64_t n_rows, int width, float* dst,
                      int dst_ld, cudaStream_t st) {
   GTB_REQUIRE(src && index && dst && width >= 1, GTB_ERR_BAD_ARG, "gtb_rows_scatter_add_f32: bad arguments");
   if (n_rows == 0) return GTB_OK;
+  if ((width & 3) == 0 && (src_ld & 3) == 0 && (dst_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    const int64_t total4 = n_rows * (width >> 2);
+    const int blocks4 = (int)imin64((total4 + 255) / 256, (int64_t)kNumSMs * 16);
+    rows_scatter_add_v4_kernel<<<blocks4, 256, 0, st>>>(src, src_ld, index, n_rows, width >> 2, dst, dst_ld);
+    GTB_CHECK_LAUNCH("rows_scatter_add_v4_kernel");
+    return GTB_OK;
+  }
   const int64_t total = n_rows * width;
   const int blocks = (int)imin64((total + 255) / 256, (int64_t)kNumSMs * 32);
   rows_scatter_add_kernel<<<blocks, 256, 0, st>>>(src, src_ld, index, n_rows, width, dst, dst_ld);

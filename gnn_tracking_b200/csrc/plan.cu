@@ -190,9 +190,75 @@ __global__ void rows_gather_kernel(const float* __restrict__ src, int src_ld, co
   }
 }
 
+// 16-byte pieces: thread = one float4 of a row.  MODE 0: dst[r] = src[index[r]], 1: dst[index[r]] = src[r],
+// 2: dst[r] += src[index[r]] (the gathered per-node gradient added onto the per-edge one in the backward pass)
+template <int MODE>
+__global__ void rows_move_v4_kernel(const float* __restrict__ src, int src_ld, const int32_t* __restrict__ index,
+                                    int64_t n_rows, int w4, float* __restrict__ dst, int dst_ld) {
+  const int64_t total = n_rows * w4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t r = i / w4;
+    const int c = (int)(i - r * w4) << 2;
+    const int64_t ir = __ldg(index + r);
+    if (MODE == 1) {
+      *reinterpret_cast<float4*>(dst + (size_t)ir * dst_ld + c) = __ldg(reinterpret_cast<const float4*>(src + (size_t)r * src_ld + c));
+    } else {
+      float4 v = __ldg(reinterpret_cast<const float4*>(src + (size_t)ir * src_ld + c));
+      float4* d = reinterpret_cast<float4*>(dst + (size_t)r * dst_ld + c);
+      if (MODE == 2) {
+        const float4 o = *d;
+        v = make_float4(o.x + v.x, o.y + v.y, o.z + v.z, o.w + v.w);
+      }
+      *d = v;
+    }
+  }
+}
+
+__global__ void rows_gather_add_kernel(const float* __restrict__ src, int src_ld, const int32_t* __restrict__ index,
+                                       int64_t n_rows, int width, float* __restrict__ dst, int dst_ld) {
+  const int64_t total = n_rows * width;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t r = i / width;
+    const int c = (int)(i - r * width);
+    dst[(size_t)r * dst_ld + c] += src[(size_t)index[r] * src_ld + c];
+  }
+}
+
+static bool rows_v4_ok(const float* src, int src_ld, int width, const float* dst, int dst_ld) {
+  return (width & 3) == 0 && (src_ld & 3) == 0 && (dst_ld & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
+         (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+}
+
+int rows_gather_add(const float* src, int src_ld, const int32_t* index, int64_t n_rows, int width, float* dst, int dst_ld,
+                    cudaStream_t st) {
+  GTB_REQUIRE(src && index && dst && width >= 1, GTB_ERR_BAD_ARG, "gtb_rows_gather_add_f32: bad arguments");
+  if (n_rows == 0) return GTB_OK;
+  if (rows_v4_ok(src, src_ld, width, dst, dst_ld)) {
+    const int64_t total = n_rows * (width >> 2);
+    const int blocks = (int)imin64((total + 255) / 256, (int64_t)kNumSMs * 16);
+    rows_move_v4_kernel<2><<<blocks, 256, 0, st>>>(src, src_ld, index, n_rows, width >> 2, dst, dst_ld);
+  } else {
+    const int64_t total = n_rows * width;
+    const int blocks = (int)imin64((total + 255) / 256, (int64_t)kNumSMs * 32);
+    rows_gather_add_kernel<<<blocks, 256, 0, st>>>(src, src_ld, index, n_rows, width, dst, dst_ld);
+  }
+  GTB_CHECK_LAUNCH("rows_gather_add_kernel");
+  return GTB_OK;
+}
+
 int rows_move(const float* src, int src_ld, const int32_t* index, int64_t n_rows, int width, float* dst,
               int dst_ld, bool scatter, cudaStream_t st) {
   if (n_rows == 0 || width == 0) return GTB_OK;
+  if (rows_v4_ok(src, src_ld, width, dst, dst_ld)) {
+    const int64_t total4 = n_rows * (width >> 2);
+    const int blocks4 = (int)imin64((total4 + 255) / 256, (int64_t)kNumSMs * 16);
+    if (scatter) rows_move_v4_kernel<1><<<blocks4, 256, 0, st>>>(src, src_ld, index, n_rows, width >> 2, dst, dst_ld);
+    else         rows_move_v4_kernel<0><<<blocks4, 256, 0, st>>>(src, src_ld, index, n_rows, width >> 2, dst, dst_ld);
+    GTB_CHECK_LAUNCH("rows_move_v4_kernel");
+    return GTB_OK;
+  }
   const int64_t total = n_rows * width;
   const int blocks = (int)imin64((total + 255) / 256, (int64_t)kNumSMs * 32);
   rows_gather_kernel<<<blocks, 256, 0, st>>>(src, src_ld, index, n_rows, width, dst, dst_ld, scatter);

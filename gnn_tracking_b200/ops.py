@@ -390,6 +390,20 @@ def rows_gather(table: Tensor, index: Tensor, out: Tensor | None = None) -> Tens
     return out
 
 
+def rows_gather_add(table: Tensor, index: Tensor, dst: Tensor) -> Tensor:
+    """``dst[i] += table[index[i]]`` in place (int32 index); returns ``dst``."""
+    table = _f32c(table)
+    dev = require_cuda(table, index, dst)
+    if dst.dtype != torch.float32 or dst.dim() != 2 or dst.stride(1) != 1 or dst.size(1) != table.size(1):
+        raise TypeError("rows_gather_add: dst must be a row-major fp32 table of the source's width")
+    n = index.numel()
+    if n:
+        check(lib().gtb_rows_gather_add_f32(table.data_ptr(), table.stride(0), _idx(index), n, table.size(1), dst.data_ptr(),
+                                            dst.stride(0), stream_ptr(dev)))
+        _count(1)
+    return dst
+
+
 def rows_inv_l2norm(blocks: Sequence[Block], n_rows: int, eps: float = 1e-12) -> Tensor:
     tensors = [_f32c(b.tensor) for b in blocks]
     dev = require_cuda(*tensors)

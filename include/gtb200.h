@@ -383,6 +383,10 @@ int gtb_rows_gather_f32(const float* src, int32_t src_ld, const int32_t* index, 
                         int32_t width, float* dst, int32_t dst_ld, void* stream);
 int gtb_rows_scatter_f32(const float* src, int32_t src_ld, const int32_t* index, int64_t n_rows,
                          int32_t width, float* dst, int32_t dst_ld, void* stream);
+/* dst[r] += src[index[r]]: the gradient of the per-destination aggregate (SumAggregation,
+ * interaction_network.py:22,36) gathered back onto the edges and added to their own gradient. */
+int gtb_rows_gather_add_f32(const float* src, int32_t src_ld, const int32_t* index, int64_t n_rows,
+                            int32_t width, float* dst, int32_t dst_ld, void* stream);
 
 /* ------------------------------------------------------------- backward blocks
  * out[Ka, Nb] += sum_r act(A[ia(r), 0:Ka])^T B[r, 0:Nb] and (colsum != NULL) colsum[Nb] += sum_r B[r]:
