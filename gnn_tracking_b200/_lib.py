@@ -61,6 +61,8 @@ SIGNATURES = {
     "gtb_plan_build": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gtb_plan_filter_workspace_bytes": (_sz, [_i64, _i64]),
     "gtb_plan_filter": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "gtb_plan_prune_workspace_bytes": (_sz, [_i64]),
+    "gtb_plan_prune_orphans": (C.c_int, [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gtb_mlp_packed_bytes": (_sz, [C.c_int, C.POINTER(_i32), C.c_int, C.POINTER(_i32), C.c_int]),
     "gtb_mlp_pack": (C.c_int, [C.c_int, C.POINTER(_i32), C.c_int, C.POINTER(_i32), C.POINTER(_vp), C.POINTER(_vp),
                                C.c_int, _vp, _vp]),

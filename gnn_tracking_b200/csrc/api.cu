@@ -21,6 +21,9 @@ int plan_build(const int64_t*, int64_t, int64_t, int32_t*, int32_t*, int32_t*, i
 size_t plan_filter_workspace_bytes(int64_t, int64_t);
 int plan_filter(const uint8_t*, int64_t, int64_t, const int32_t*, const int32_t*, const int32_t*, int32_t*,
                 int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, void*, size_t, cudaStream_t);
+size_t plan_prune_workspace_bytes(int64_t);
+int plan_prune(int64_t, int64_t, const int32_t*, const int32_t*, const int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*,
+               int32_t*, void*, size_t, cudaStream_t);
 int rows_inv_l2norm(const gtb_src_t*, int, int64_t, float, float*, cudaStream_t);
 int rows_move(const float*, int, const int32_t*, int64_t, int, float*, int, bool, cudaStream_t);
 int rows_gather_add(const float*, int, const int32_t*, int64_t, int, float*, int, cudaStream_t);
@@ -390,6 +393,15 @@ int gtb_dbscan_f32(const float* x, int32_t d, int64_t n, double eps, int32_t min
 int gtb_rows_inv_l2norm_f32(const gtb_src_t* srcs, int32_t n_srcs, int64_t n_rows, float eps, float* inv_norm,
                             void* stream) {
   return rows_inv_l2norm(srcs, n_srcs, n_rows, eps, inv_norm, static_cast<cudaStream_t>(stream));
+}
+
+size_t gtb_plan_prune_workspace_bytes(int64_t n_nodes) { return plan_prune_workspace_bytes(n_nodes); }
+
+int gtb_plan_prune_orphans(int64_t n_nodes, int64_t n_edges, const int32_t* rowptr, const int32_t* src_sorted,
+                           const int32_t* dst_sorted, int32_t* new_id, int32_t* node_ids, int32_t* rowptr_out, int32_t* src_out,
+                           int32_t* dst_out, int32_t* n_kept_out, void* workspace, size_t workspace_bytes, void* stream) {
+  return plan_prune(n_nodes, n_edges, rowptr, src_sorted, dst_sorted, new_id, node_ids, rowptr_out, src_out, dst_out, n_kept_out,
+                    workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int gtb_rows_gather_f32(const float* src, int32_t src_ld, const int32_t* index, int64_t n_rows, int32_t width,

@@ -177,6 +177,87 @@ int plan_filter(const uint8_t* keep, int64_t n_nodes, int64_t n_edges, const int
   return GTB_OK;
 }
 
+// ----------------------------------------------------------------------------- orphan pruning
+// Nodes without any edge are dropped and the others relabelled in increasing order (reference
+// models/track_condensation_networks.py:254-259: unique endpoints of the surviving edges).  The relabelling is
+// monotone, so the destination-sorted order of the plan survives: the plan of the pruned graph is this plan with
+// relabelled endpoints and a compacted rowptr -- no second sort.
+__global__ void prune_mark_kernel(const int32_t* __restrict__ src, const int32_t* __restrict__ dst, int64_t n_edges,
+                                  int32_t* __restrict__ flag) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_edges; i += stride) {
+    flag[src[i]] = 1;  // same value from every writer
+    flag[dst[i]] = 1;
+  }
+}
+
+__global__ void prune_nodes_kernel(const int32_t* __restrict__ flag, const int32_t* __restrict__ pos, const int32_t* __restrict__ rowptr,
+                                   int64_t n_nodes, int32_t* __restrict__ new_id, int32_t* __restrict__ node_ids,
+                                   int32_t* __restrict__ rowptr_out, int32_t* __restrict__ n_kept) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_nodes; v += stride) {
+    const bool keep = flag[v] != 0;
+    new_id[v] = keep ? pos[v] : -1;
+    if (keep) {
+      node_ids[pos[v]] = (int32_t)v;
+      rowptr_out[pos[v]] = rowptr[v];  // a dropped node has no incoming edge: the segments in between are empty
+    }
+    if (v == n_nodes - 1) {
+      const int32_t k = pos[v] + (keep ? 1 : 0);
+      *n_kept = k;
+      rowptr_out[k] = rowptr[n_nodes];
+    }
+  }
+}
+
+__global__ void prune_relabel_kernel(const int32_t* __restrict__ new_id, const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
+                                     int64_t n_edges, int32_t* __restrict__ src_out, int32_t* __restrict__ dst_out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_edges; i += stride) {
+    src_out[i] = new_id[src[i]];
+    dst_out[i] = new_id[dst[i]];
+  }
+}
+
+size_t plan_prune_workspace_bytes(int64_t n_nodes) {
+  size_t cub_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (const int32_t*)nullptr, (int32_t*)nullptr, (int)n_nodes);
+  return align256(cub_bytes) + 2 * align256((size_t)n_nodes * 4) + 256;
+}
+
+int plan_prune(int64_t n_nodes, int64_t n_edges, const int32_t* rowptr, const int32_t* src_sorted, const int32_t* dst_sorted,
+               int32_t* new_id, int32_t* node_ids, int32_t* rowptr_out, int32_t* src_out, int32_t* dst_out, int32_t* n_kept_out,
+               void* ws, size_t ws_bytes, cudaStream_t st) {
+  GTB_REQUIRE(n_nodes >= 0 && n_edges >= 0 && rowptr && new_id && node_ids && rowptr_out && n_kept_out && ws, GTB_ERR_BAD_ARG,
+              "gtb_plan_prune_orphans: bad arguments");
+  GTB_REQUIRE(ws_bytes >= plan_prune_workspace_bytes(n_nodes), GTB_ERR_WORKSPACE, "gtb_plan_prune_orphans: workspace too small");
+  if (n_nodes == 0) return check_cuda(cudaMemsetAsync(n_kept_out, 0, 4, st), "memset n_kept");
+  const int threads = 256;
+  char* p = static_cast<char*>(ws);
+  const size_t seg = align256((size_t)n_nodes * 4);
+  int32_t* flag = reinterpret_cast<int32_t*>(p);
+  int32_t* pos = reinterpret_cast<int32_t*>(p + seg);
+  void* cub_ws = p + 2 * seg;
+  size_t cub_bytes = ws_bytes - 2 * seg;
+  int rc = check_cuda(cudaMemsetAsync(flag, 0, (size_t)n_nodes * 4, st), "memset flags");
+  if (rc) return rc;
+  const int eb = (int)imin64((n_edges + threads) / threads, (int64_t)kNumSMs * 16);
+  const int nb = (int)imin64((n_nodes + threads) / threads, (int64_t)kNumSMs * 16);
+  if (n_edges > 0) {
+    prune_mark_kernel<<<eb, threads, 0, st>>>(src_sorted, dst_sorted, n_edges, flag);
+    GTB_CHECK_LAUNCH("prune_mark_kernel");
+  }
+  rc = check_cuda(cub::DeviceScan::ExclusiveSum(cub_ws, cub_bytes, flag, pos, (int)n_nodes, st), "cub::DeviceScan::ExclusiveSum");
+  if (rc) return rc;
+  prune_nodes_kernel<<<nb, threads, 0, st>>>(flag, pos, rowptr, n_nodes, new_id, node_ids, rowptr_out, n_kept_out);
+  GTB_CHECK_LAUNCH("prune_nodes_kernel");
+  if (n_edges > 0) {
+    prune_relabel_kernel<<<eb, threads, 0, st>>>(new_id, src_sorted, dst_sorted, n_edges, src_out, dst_out);
+    GTB_CHECK_LAUNCH("prune_relabel_kernel");
+  }
+  return GTB_OK;
+}
+
 // ----------------------------------------------------------------------------- row ops
 __global__ void rows_gather_kernel(const float* __restrict__ src, int src_ld, const int32_t* __restrict__ index,
                                    int64_t n_rows, int width, float* __restrict__ dst, int dst_ld, bool scatter) {

@@ -16,7 +16,7 @@ from torch import Tensor, nn
 from .. import ops
 from .._hparams import HyperparametersMixin
 from ..ops import ACT_RELU, ACT_SIGMOID_AFFINE, Block
-from ..plan import build_plan, get_plan
+from ..plan import build_plan, get_plan, prune_orphans
 from .edge_classifier import ECForGraphTCN, PerfectEdgeClassification
 from .mlp import MLP, ResFCNN
 from .resin import ResIN
@@ -86,15 +86,10 @@ class ModularGraphTCN(nn.Module, HyperparametersMixin):
             plan, _, kept = plan.filtered(edge_mask.reshape(-1))
             if hp.mask_orphan_nodes:
                 # unique endpoints of the surviving edges, relabelled in increasing order (:254-259)
-                hit_mask = torch.zeros(n, dtype=torch.bool, device=dev)
-                hit_mask[plan.src_sorted.long()] = True
-                hit_mask[plan.dst_sorted.long()] = True
-                connected = torch.nonzero(hit_mask).flatten()
-                relabel = torch.cumsum(hit_mask, 0) - 1
-                sub_ei = relabel[edge_index[:, kept.long()]]
-                node_ids = connected.to(torch.int32)
-                n = connected.numel()
-                plan = build_plan(sub_ei, n)
+                # (a compaction of the filtered plan: the relabelling is monotone, nothing is sorted again)
+                plan, node_ids, new_id = prune_orphans(plan)
+                hit_mask = new_id >= 0
+                n = plan.n_nodes
             else:
                 hit_mask = torch.ones(n, dtype=torch.bool, device=dev)
         elif hp.feed_edge_weights:

@@ -63,6 +63,33 @@ class GraphPlan:
         return sub, new_id, kept[:k]
 
 
+def prune_orphans(plan: GraphPlan) -> tuple[GraphPlan, Tensor, Tensor]:
+    """Plan of the graph without its edge-less nodes, the others relabelled in increasing order (reference
+    models/track_condensation_networks.py:254-259), derived from ``plan`` without sorting again: the
+    relabelling is monotone, so ``perm`` stays valid, the endpoints are relabelled and ``rowptr`` compacted
+    (``gtb_plan_prune_orphans``).  Returns ``(plan', node_ids int32 [N'], new_id int32 [N])``: original id of
+    every surviving node, and new id of every node (-1 for an orphan).  One host sync to learn N' (the
+    reference's ``unique`` syncs at the same place: the outputs' shapes depend on it)."""
+    dev = plan.perm.device
+    n, e = plan.n_nodes, plan.n_edges
+    i32 = dict(dtype=torch.int32, device=dev)
+    new_id = torch.empty(n, **i32)
+    node_ids = torch.empty(n, **i32)
+    rowptr = torch.empty(n + 1, **i32)
+    src = torch.empty(e, **i32)
+    dst = torch.empty(e, **i32)
+    n_kept = torch.zeros(1, **i32)
+    ws_bytes = lib().gtb_plan_prune_workspace_bytes(n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with ops.on_device(dev):
+        check(lib().gtb_plan_prune_orphans(n, e, plan.rowptr.data_ptr(), plan.src_sorted.data_ptr(), plan.dst_sorted.data_ptr(),
+                                           new_id.data_ptr(), node_ids.data_ptr(), rowptr.data_ptr(), src.data_ptr(),
+                                           dst.data_ptr(), n_kept.data_ptr(), ws.data_ptr(), ws_bytes, ops.stream_ptr(dev)))
+    ops._count(4)
+    k = int(n_kept.item())
+    return GraphPlan(k, e, plan.perm, rowptr[:k + 1], src, dst, torch.zeros(1, **i32)), node_ids[:k], new_id
+
+
 def build_plan(edge_index: Tensor, n_nodes: int) -> GraphPlan:
     dev = ops.require_cuda(edge_index)
     if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.size(0) != 2:

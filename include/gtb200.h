@@ -83,6 +83,18 @@ int gtb_plan_filter(const uint8_t* keep, int64_t n_nodes, int64_t n_edges,
                     int32_t* src_sorted_out, int32_t* dst_sorted_out, int32_t* n_kept_out,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* Plan of the graph with its orphan nodes removed (track_condensation_networks.py:254-259: the unique
+ * endpoints of the surviving edges, relabelled in increasing order).  The relabelling is monotone, so the
+ * plan keeps its order: `perm` stays valid as it is, the endpoints are relabelled and rowptr compacted.
+ * new_id: int32 [N] new id of every node (-1 for an orphan); node_ids: int32 [N], original id of new node
+ * j in its first n_kept entries; rowptr_out: int32 [N + 1] (n_kept + 1 used); n_kept_out: int32 [1]. */
+size_t gtb_plan_prune_workspace_bytes(int64_t n_nodes);
+int gtb_plan_prune_orphans(int64_t n_nodes, int64_t n_edges, const int32_t* rowptr,
+                           const int32_t* src_sorted, const int32_t* dst_sorted,
+                           int32_t* new_id, int32_t* node_ids, int32_t* rowptr_out,
+                           int32_t* src_sorted_out, int32_t* dst_sorted_out, int32_t* n_kept_out,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------ packed MLP weights
  * An MLP of the path (models/mlp.py:18-62: Linear/ReLU chain, nn.Linear weights
  * [out, in] row-major, optional bias) is repacked once per weight version into the
