@@ -46,6 +46,8 @@ int edge_encoder_ws(const float*, int32_t, const int32_t*, int64_t, int64_t, con
                     int32_t, cudaStream_t);
 int en_fault_flag(int*);
 int at_fault_flag(int*);
+int ec_head_ws(const gtb_mlp_desc_t&, cudaStream_t, bool*);
+int hw_fault_flag(int*);
 int oc_potentials_grad(const float*, const float*, int32_t, const int64_t*, const int32_t*, int64_t, const int32_t*, int32_t,
                        float, int64_t, const float*, float*, float*, float*, cudaStream_t);
 int dbscan(const float*, int, int64_t, double, int, unsigned char*, int*, int*, cudaStream_t);
@@ -124,9 +126,10 @@ int gtb_debug_tc_timeout(int* flag) {
   if (rc == GTB_OK) rc = nw_fault_flag(&c);
   int d = 0;
   if (rc == GTB_OK) rc = en_fault_flag(&d);
-  int e = 0;
+  int e = 0, f = 0;
   if (rc == GTB_OK) rc = at_fault_flag(&e);
-  *flag = a ? a : (b ? 16 + b : (c ? 32 + c : (d ? 48 + d : (e ? 64 + e : 0))));
+  if (rc == GTB_OK) rc = hw_fault_flag(&f);
+  *flag = a ? a : (b ? 16 + b : (c ? 32 + c : (d ? 48 + d : (e ? 64 + e : (f ? 80 + f : 0)))));
   return rc;
 }
 int gtb_debug_tc_profile(int enable, long long* out32) {
@@ -234,7 +237,10 @@ int gtb_fused_mlp_f32(const gtb_mlp_desc_t* desc, void* stream) {
   if (desc->impl == GTB_IMPL_TCGEN05) {
     // the wide Interaction-Network edge shape has its own warp-specialised kernel (edge_ws.cu)
     bool handled = false;
-    const int rc = in_edge_ws(*desc, static_cast<cudaStream_t>(stream), &handled);
+    int rc = in_edge_ws(*desc, static_cast<cudaStream_t>(stream), &handled);
+    if (rc != GTB_OK || handled) return rc;
+    // ... and so has the wide W head of the edge classifier (head_ws.cu)
+    rc = ec_head_ws(*desc, static_cast<cudaStream_t>(stream), &handled);
     if (rc != GTB_OK || handled) return rc;
     return fused_mlp_tc(*desc, static_cast<cudaStream_t>(stream));
   }
