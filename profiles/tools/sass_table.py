@@ -15,7 +15,7 @@ ROOT = Path(__file__).resolve().parents[2]
 LIB = ROOT / "gnn_tracking_b200" / "csrc" / "libgtb200.so"
 MNEMONICS = ["UTCHMMA", "LDTM", "STTM", "UTCBAR", "UTMALDG", "UTMALDG.2D.GATHER4", "UTMASTG", "UTMASTG.2D.SCATTER4", "UBLKCP",
              "SYNCS", "LDGSTS", "REDG", "FFMA2", "FADD2", "HMMA"]
-KERNELS = re.compile(r"in_edge_ws_kernel|fused_mlp_tc_kernel")
+KERNELS = re.compile(r"in_edge_ws_kernel|fused_mlp_tc_kernel|in_node_ws_kernel|edge_encoder_ws_kernel|ec_head_ws_kernel|rows_atb_tc_kernel")
 
 
 def main():
