@@ -12,7 +12,7 @@
 //       warps 0-15  : 512 row owners (thread = row x 16-column quarter).  ALL of them work on one
 //                     stage of one context at a time and ping-pong between the contexts: while the
 //                     tensor core runs a Linear of context A they run a stage of context B --
-//                        E0(A) E0(B) E1(A) E1(B) E2(A) C0(A') E2(B) AG(A) C0(B') AG(B)
+//                        E0(A) E0(B) E1(A) E1(B) E2(A) E2(B) AG(A) RF(A) C0(A') AG(B) RF(B) C0(B')
 //                     C0: tf32 hi / lo split of the edge-feature tile into TMEM; E0 / E1: accumulator
 //                     + bias (+ P_i[dst] + P_j[src]) -> ReLU -> next A operand; E2: output tile into
 //                     shared memory; AG: store of the tile, in-tile segmented sum by destination, and
@@ -91,6 +91,20 @@ struct EwParams {
 
 __device__ __noinline__ void ew_timeout();
 __device__ __forceinline__ void ew_wait(uint32_t bar, uint32_t parity) {
+  // First try outside the loop: mbarrier.try_wait blocks in hardware for a while, and a load issued in front of
+  // the wait (P_i[dst] in E0) has its scoreboard wait parked at the next basic-block boundary -- with the first
+  // try peeled that boundary lies BEHIND one blocking try, so the load's latency runs under the barrier wait.
+  {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
   // NOT unrolled: ptxas otherwise replicates the try_wait 64 times per wait site (100 KB of SASS: every
   // stage change then misses the instruction cache)
 #pragma unroll 1
@@ -106,6 +120,29 @@ __device__ __forceinline__ void ew_wait(uint32_t bar, uint32_t parity) {
     if (ok) return;
   }
   ew_timeout();
+}
+
+// two barriers at once: both (blocking) first tries in straight-line code before the first branch, so that loads issued
+// in front of the call stay in flight under BOTH waits
+__device__ __forceinline__ void ew_wait2(uint32_t bar_a, uint32_t par_a, uint32_t bar_b, uint32_t par_b) {
+  uint32_t ok_a, ok_b;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok_a)
+      : "r"(bar_a), "r"(par_a)
+      : "memory");
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok_b)
+      : "r"(bar_b), "r"(par_b)
+      : "memory");
+  if (ok_a & ok_b) return;
+  if (!ok_a) ew_wait(bar_a, par_a);
+  if (!ok_b) ew_wait(bar_b, par_b);
 }
 
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
@@ -169,8 +206,8 @@ struct EwOwner {
     return reinterpret_cast<const char*>(p.pi) + (uint64_t)(uint32_t)d * ((uint32_t)p.pi_ld * ES) + 64u * (uint32_t)qd;
   }
   // ---- bf16 variant: own 32 columns
-  __device__ __forceinline__ void acc_load32(int c, int t, int l, float (&v)[32]) {
-    ew_wait(bar(c, 4), (uint32_t)(t + l) & 1u);
+  __device__ __forceinline__ void acc_load32(int c, int t, int l, float (&v)[32], bool waited = false) {
+    if (!waited) ew_wait(bar(c, 4), (uint32_t)(t + l) & 1u);
     tc_fence_after_sync();
     uint32_t a0[16], a1[16];
     tmem_ld16(tm_lane(c) + TD + 32 * qd, a0);
@@ -199,8 +236,8 @@ struct EwOwner {
     add16(v, lds128(ba), lds128(ba + 16), lds128(ba + 32), lds128(ba + 48));
   }
   // accumulator of the own 16 columns, once the l-th Linear of tile iteration t has completed
-  __device__ __forceinline__ void acc_load(int c, int t, int l, float (&v)[16]) {
-    ew_wait(bar(c, 4), (uint32_t)(t + l) & 1u);  // completion number 3 t + l
+  __device__ __forceinline__ void acc_load(int c, int t, int l, float (&v)[16], bool waited = false) {
+    if (!waited) ew_wait(bar(c, 4), (uint32_t)(t + l) & 1u);  // completion number 3 t + l
     tc_fence_after_sync();
     uint32_t acc[16];
     tmem_ld16(tm_lane(c) + EW_D + 16 * qd, acc);
@@ -261,16 +298,8 @@ struct EwOwner {
     const uint32_t row0 = (uint32_t)tile * EW_TM;
     const int rows_here = (int)min((int64_t)EW_TM, p.n_rows - (int64_t)row0);
     const uint32_t sl = slot(c, ((uint32_t)t & 1u) ^ 1u);
-    uint4 pre[4];  // own 64 bytes of P_i[dst]: destination-sorted rows, neighbouring lanes repeat lines
-    {
-      int32_t d = 0;
-      if (rows_here == EW_TM) d = lds_i32(ids(c) + 4 * r);
-      else if (r < rows_here) d = __ldg(p.dst + row0 + r);
-      const uint4* rowp = reinterpret_cast<const uint4*>(pi_row(d));
-#pragma unroll
-      for (int q = 0; q < 4; ++q) pre[q] = __ldg(rowp + q);
-    }
-    {  // segment ids of the rows this lane sums in AG: rows 8 w + 4 (lane >> 4) + i (the ids leave with P_j)
+    {  // segment ids of the rows this lane sums in AG: rows 8 w + 4 (lane >> 4) + i (the ids leave with P_j).
+       // In FRONT of the P_i loads and without a branch on the context: a branch behind a load waits for it.
       const int rr0 = 8 * w + 4 * (lane >> 4);
       int4 s;
       if (rows_here == EW_TM) {
@@ -281,15 +310,25 @@ struct EwOwner {
         s.z = rr0 + 2 < rows_here ? __ldg(p.dst + row0 + rr0 + 2) : -1;
         s.w = rr0 + 3 < rows_here ? __ldg(p.dst + row0 + rr0 + 3) : -1;
       }
-      if (c) { sgB[0] = s.x; sgB[1] = s.y; sgB[2] = s.z; sgB[3] = s.w; }
-      else   { sgA[0] = s.x; sgA[1] = s.y; sgA[2] = s.z; sgA[3] = s.w; }
+      const bool cb = c != 0;
+      sgA[0] = cb ? sgA[0] : s.x; sgA[1] = cb ? sgA[1] : s.y; sgA[2] = cb ? sgA[2] : s.z; sgA[3] = cb ? sgA[3] : s.w;
+      sgB[0] = cb ? s.x : sgB[0]; sgB[1] = cb ? s.y : sgB[1]; sgB[2] = cb ? s.z : sgB[2]; sgB[3] = cb ? s.w : sgB[3];
+    }
+    uint4 pre[4];  // own 64 bytes of P_i[dst]: destination-sorted rows, neighbouring lanes repeat lines
+    {
+      int32_t d = 0;
+      if (rows_here == EW_TM) d = lds_i32(ids(c) + 4 * r);
+      else if (r < rows_here) d = __ldg(p.dst + row0 + r);
+      const uint4* rowp = reinterpret_cast<const uint4*>(pi_row(d));
+#pragma unroll
+      for (int q = 0; q < 4; ++q) pre[q] = __ldg(rowp + q);
     }
     EW_PROF(3);
-    ew_wait(bar(c, 1), (uint32_t)t & 1u);
+    ew_wait2(bar(c, 1), (uint32_t)t & 1u, bar(c, 4), (uint32_t)t & 1u);  // P_j rows landed; first Linear complete
     EW_PROF(4);
     if constexpr (BF) {
       float v[32];
-      acc_load32(c, t, 0, v);
+      acc_load32(c, t, 0, v, true);
       EW_PROF(5);
       uint4 x[4];
 #pragma unroll
@@ -302,7 +341,7 @@ struct EwOwner {
       act_store32(c, v);
     } else {
       float v[16];
-      acc_load(c, t, 0, v);
+      acc_load(c, t, 0, v, true);
       EW_PROF(5);
       float4 x[4];
 #pragma unroll
@@ -522,10 +561,17 @@ struct EwOwner {
     }
     EW_PROF(15);
     if (p.debug_bar) asm volatile("bar.sync 1, 512;" ::: "memory");
+  }
+
+  // ---- RF: the band this warp stored in AG takes the next tile's P_j rows, once the store has READ it.
+  // `newer`: bulk groups this thread committed after that store that may stay pending.  (Running RF one stage later,
+  // behind the other context's AG, was measured: 197 us against 190 us -- the gather then lands too late for E0.)
+  __device__ __forceinline__ void rf(int c, int t, int newer) {
     if (t + 1 < n_of(c)) {
-      tma::bulk_wait_read0();  // this warp's store has read its band: the band is free
+      if (newer) tma::bulk_wait_read1();
+      else tma::bulk_wait_read0();
       __syncwarp();
-      load_pj(c, t + 1, sl);
+      load_pj(c, t + 1, slot(c, (uint32_t)t & 1u));
     }
     EW_PROF(16);
   }
@@ -596,8 +642,8 @@ __global__ void __launch_bounds__(EW_THREADS, 1) in_edge_ws_kernel(const __grid_
 #pragma unroll 1
     for (int c = 0; c < 2; ++c)
       if (o.n_of(c) > 0) o.c0(c, 0);
-    // stage order of one round (two tiles): E0 E0' E1 E1' E2 E2' AG C0+ AG' C0'+  -- a stage of one context runs
-    // under the Linear of the other; AG sits two stages in front of the E0 that needs the rows it gathers
+    // stage order of one round (two tiles): E0 E0' E1 E1' E2 E2' AG RF C0+ AG' RF' C0'+  -- a stage of one context runs
+    // under the Linear of the other; RF (the P_j gather of the next tile) sits two stages in front of the E0 that needs it
 #pragma unroll 1
     for (int t = 0; t < o.nA; ++t) {
 #pragma unroll 1
@@ -611,7 +657,10 @@ __global__ void __launch_bounds__(EW_THREADS, 1) in_edge_ws_kernel(const __grid_
         if (t < o.n_of(c)) o.e2(c, t);
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
-        if (t < o.n_of(c)) o.ag(c, t);
+        if (t < o.n_of(c)) {
+          o.ag(c, t);
+          o.rf(c, t, 0);
+        }
         if (t + 1 < o.n_of(c)) o.c0(c, t + 1);
       }
       if (PROF && prof_on) g_ew_prof[31] += 1;

@@ -60,6 +60,17 @@ __device__ __noinline__ void en_timeout() {
   __trap();
 }
 __device__ __forceinline__ void en_wait(uint32_t bar, uint32_t parity) {
+  {  // first try outside the loop: loads issued in front of the wait stay in flight under one blocking try (see edge_ws.cu)
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
 #pragma unroll 1
   for (uint32_t i = 0; i < 20000000u; ++i) {
     uint32_t ok;

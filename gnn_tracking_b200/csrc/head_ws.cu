@@ -70,6 +70,17 @@ __device__ __noinline__ void hw_timeout() {
   __trap();
 }
 __device__ __forceinline__ void hw_wait(uint32_t bar, uint32_t parity) {
+  {  // first try outside the loop: loads issued in front of the wait stay in flight under one blocking try (see edge_ws.cu)
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
 #pragma unroll 1
   for (uint32_t i = 0; i < 20000000u; ++i) {
     uint32_t ok;
@@ -171,8 +182,19 @@ struct HwOwner {
 #pragma unroll
       for (int q = 0; q < 4; ++q) pre[q] = __ldg(rowp + q);
     }
-    hw_wait(bar(c, 0), hw_use(t, 4) & 1u);  // T_src rows (item 4, slot 0)
-    wait_d(c, t, 3);
+    {  // T_src rows (item 4, slot 0) and the last K chunk's MMAs: both first tries in front of the first branch
+      const uint32_t ba = bar(c, 0), pa = hw_use(t, 4) & 1u, bb = bar(c, 5), pb = (uint32_t)(5 * t + 3) & 1u;
+      uint32_t ok_a, ok_b;
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(ok_a) : "r"(ba), "r"(pa) : "memory");
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(ok_b) : "r"(bb), "r"(pb) : "memory");
+      if (!(ok_a & ok_b)) {
+        if (!ok_a) hw_wait(ba, pa);
+        if (!ok_b) hw_wait(bb, pb);
+      }
+      tc_fence_after_sync();
+    }
     float v[16];
     acc_load(c, v);
     const uint32_t sl = slot(c, 0);
