@@ -294,6 +294,36 @@ def edge_kernel_time(model, x_dim, plan, n, e, dev, flush, reps, sorted_edges=Tr
     return statistics.mean(ts), ("tcgen05" if packed[0].impl == ops.IMPL_TCGEN05 else "ffma")
 
 
+def layer_time(model, plan, n, e, dev, flush, reps):
+    """One whole middle IN layer of the stack as the forward runs it (B_layer / t_layer): the fused
+    edge launch + the one-launch node side (object model, residual, the next layer's two pre-projections, the
+    aggregate handed back zeroed), timed together with CUDA events, L2 flushed before every repetition.
+    None when the layer is not on the two-launch path (reference-default widths)."""
+    from gnn_tracking_b200 import ops
+    net = model.ec_resin.network
+    gen = torch.Generator(device="cpu").manual_seed(2)
+    xx = torch.randn(n, HIDDEN, generator=gen).to(dev)
+    ee = torch.randn(e, HIDDEN, generator=gen).to(dev)
+    with torch.no_grad():
+        if len(net.layers) < 3 or not net.fused_ok(xx, ee):
+            return None
+        layer, nxt = net.layers[1], net.layers[2].input_projection()
+        aggr = torch.zeros((n, HIDDEN), device=dev)
+        _, pa, pb = ops.in_node_fused(xx, False, proj=layer.input_projection(), proj_relu=True)
+        ts = []
+        for i in range(3 + reps):
+            flush.zero_()
+            s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            layer.forward_fused(xx, plan, ee, relu_x=True, relu_e=True, res=xx, res_a=0.7071067811865476, res_b=0.7071067811865476,
+                                e_sorted=True, out_sorted=True, tables=(pa, pb), aggr=aggr, nxt=nxt, nxt_relu=True)
+            t.record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                ts.append(s.elapsed_time(t))
+    return statistics.mean(ts)
+
+
 def run_ours(args) -> None:
     import torch.distributed as dist
     from gnn_tracking_b200 import ops
@@ -380,8 +410,9 @@ def run_ours(args) -> None:
         Every step copies its own inputs from pinned host memory and reads its result back; the copy
         of step k + 1 is in flight on the loader's side stream while step k computes.  One event pair
         around all ``steps`` steps (pipeline fill, per-step L2 flush and result copies included)."""
-        from gnn_tracking_b200.graph_store import DevicePrefetcher, GraphData
+        from gnn_tracking_b200.graph_store import DevicePrefetcher, GraphData, ResultReader
         host_graph = GraphData(x=hx, edge_index=hei, edge_attr=hea)
+        reader = ResultReader(hw, dev)
 
         def run(k):
             for data in DevicePrefetcher((host_graph for _ in range(k)), dev):
@@ -389,7 +420,8 @@ def run_ours(args) -> None:
                 clear_plan_cache()
                 with torch.no_grad():
                     out = model.forward_tensors(data.x, data.edge_index, data.edge_attr, halo=halo)
-                hw.copy_(out["W"], non_blocking=True)
+                reader.read(out["W"])  # read-back of step k on its own stream, under step k + 1
+            reader.wait()              # the timed region ends behind the last read-back
 
         run(warmup)
         barrier()
@@ -440,6 +472,7 @@ def run_ours(args) -> None:
     plan = build_plan(ei, n)
     k_ms, k_impl = edge_kernel_time(model, (dn, de), plan, n, e, dev, flush, args.steps, sorted_edges=True)
     k_ms_perm, _ = edge_kernel_time(model, (dn, de), plan, n, e, dev, flush, args.steps, sorted_edges=False)
+    l_ms = layer_time(model, plan, n, e, dev, flush, args.steps) if args.dims == "wide" and halo is None else None
     if world > 1:
         hf = torch.tensor([halo_frac], device=dev, dtype=torch.float64)
         dist.all_reduce(hf, op=dist.ReduceOp.MAX)
@@ -487,9 +520,9 @@ def run_ours(args) -> None:
         "e2e": {"value": e2e_val, "unit": "edges/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": hx.numel() * 4 + hei.numel() * 8 + hea.numel() * 4, "d2h_bytes_per_step": e * 4,
                 "how": "every step copies its inputs from pinned host memory and reads W back; value = the faster of "
-                       "(a) graph_store.DevicePrefetcher loop (copy of step k+1 on a side stream under step k; one event "
-                       "pair around all steps, L2 flush inside) and (b) serial copy -> forward -> read back with "
-                       "per-step events",
+                       "(a) graph_store.DevicePrefetcher / ResultReader loop (copy of step k+1 and read-back of step k-1 on "
+                       "side streams under step k; one event pair around all steps, L2 flush inside, the last read-back "
+                       "inside) and (b) serial copy -> forward -> read back with per-step events",
                 "pipelined_value": e2e_pipelined_val,
                 "pipelined_ms_per_step": ms_e2e / args.steps if ms_e2e is not None else None,
                 "serial_value": e2e_serial_val, "serial_ms_per_step": ms_e2e_serial / args.steps},
@@ -501,7 +534,9 @@ def run_ours(args) -> None:
                                "edge order through perm, as the last layer does)",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "algorithmic_bytes_per_launch": alg, "kernel_ms": k_ms, "kernel_ms_perm": k_ms_perm,
-                     "frac_perm": alg / (k_ms_perm * 1e-3) / 1e9 / peak, "peak_source": peak_src},
+                     "frac_perm": alg / (k_ms_perm * 1e-3) / 1e9 / peak, "peak_source": peak_src,
+                     # the whole layer (edge launch + one-launch node side) against the same bytes
+                     "layer_ms": l_ms, "layer_frac": (alg / (l_ms * 1e-3) / 1e9 / peak) if l_ms else None},
         "clocks": clocks.summary(),
     }
     if multi_parity is not None:

@@ -168,6 +168,48 @@ def _side_stream(device: torch.device) -> "torch.cuda.Stream":
     return _SIDE_STREAMS[key]
 
 
+class ResultReader:
+    """Device-to-host read-back of a step's result on its own stream, so that it runs under the NEXT step's
+    kernels instead of holding the compute stream (the mirror image of ``DevicePrefetcher``):
+
+        reader = ResultReader(pinned_host_buffer)
+        for data in DevicePrefetcher(...):
+            out = model(data)
+            reader.read(out["W"])      # returns at once; the copy waits for the kernels that produced W
+        reader.wait()                  # host_buffer holds the LAST result
+
+    Copies are ordered among themselves (one stream), so one host buffer is enough as long as the consumer takes
+    a result before the next ``read``; ``wait(stream)`` makes a stream (default: the current one) wait instead of
+    the host."""
+
+    def __init__(self, host: Tensor, device: torch.device | str = "cuda"):
+        self.host = host
+        self.device = torch.device(device)
+        self._stream = None
+        self._done = None
+
+    def read(self, t: Tensor) -> None:
+        if self._stream is None:
+            self._stream = torch.cuda.Stream(self.device)
+        cur = torch.cuda.current_stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        t.record_stream(self._stream)  # the allocator must not hand the block out again while the copy reads it
+        with torch.cuda.stream(self._stream):
+            self._stream.wait_event(ready)
+            self.host[: t.numel()].view(t.shape).copy_(t, non_blocking=True)
+            self._done = torch.cuda.Event()
+            self._done.record(self._stream)
+
+    def wait(self, stream=None, host: bool = False) -> None:
+        if self._done is None:
+            return
+        if host:
+            self._done.synchronize()
+        else:
+            (stream or torch.cuda.current_stream(self.device)).wait_event(self._done)
+
+
 class DevicePrefetcher:
     """Yields device-resident graphs from an iterable of host-side ones, with the host-to-device
     copy of graph k + 1 issued on a side stream BEFORE graph k is handed to the caller, so the copy

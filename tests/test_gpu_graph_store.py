@@ -68,3 +68,19 @@ def test_prefetched_graphs_give_the_same_results(tmp_path):
         assert len(got) == 5
         for a, b in zip(got, want):
             assert torch.allclose(a, b, rtol=0, atol=1e-6)
+
+
+def test_result_reader_returns_every_step_result():
+    """``ResultReader``: the read-back of step k runs on its own stream under step k + 1; every result arrives
+    intact even though the device tensor is dropped right after ``read``."""
+    from gnn_tracking_b200.graph_store import ResultReader
+    host = torch.empty(1 << 20, dtype=torch.float32).pin_memory()
+    reader = ResultReader(host, "cuda")
+    big = torch.randn(4096, 4096, device="cuda")
+    for k in range(6):
+        w = torch.full((1 << 20,), float(k), device="cuda") + 0.5
+        (big @ big).sum()  # work behind which the copy may hide
+        reader.read(w)
+        del w
+        reader.wait(host=True)
+        assert float(host[0]) == k + 0.5 and float(host[-1]) == k + 0.5 and float(host.sum()) == (k + 0.5) * (1 << 20)
