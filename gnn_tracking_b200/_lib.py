@@ -46,7 +46,8 @@ class MlpDesc(C.Structure):
         ("row_scale", C.c_void_p), ("out_scale", C.c_void_p),
         ("out", C.c_void_p), ("out_index", C.c_void_p), ("out_ld", C.c_int32),
         ("aggr_ld", C.c_int32), ("aggr", C.c_void_p), ("seg_id", C.c_void_p), ("rowptr", C.c_void_p),
-        ("gate", C.c_void_p), ("gate_ld", C.c_int32), ("reserved", C.c_int32),
+        ("gate", C.c_void_p), ("gate_ld", C.c_int32), ("hidden_ld", C.c_int32),
+        ("hidden0", C.c_void_p), ("hidden1", C.c_void_p),
     ]
 
 
@@ -68,6 +69,7 @@ SIGNATURES = {
                                C.c_int, _vp, _vp]),
     "gtb_mlp_tc_slots": (C.c_int, [C.c_int, C.POINTER(_i32), C.c_int, C.POINTER(_i32)]),
     "gtb_fused_mlp_f32": (C.c_int, [C.POINTER(MlpDesc), _vp]),
+    "gtb_fused_mlp_saves_hidden": (C.c_int, [C.POINTER(MlpDesc)]),
     "gtb_debug_tc_timeout": (C.c_int, [C.POINTER(C.c_int)]),
     "gtb_debug_tc_profile": (C.c_int, [C.c_int, C.POINTER(C.c_longlong)]),
     "gtb_in_edge_forward_f32": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _i32, _i64, _i64, _vp, _vp, _vp, _vp,

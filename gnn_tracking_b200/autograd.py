@@ -13,6 +13,7 @@ models/interaction_network.py:67-103, models/resin.py:17-42, models/edge_classif
 """
 from __future__ import annotations
 
+import os
 from typing import Sequence
 
 import torch
@@ -51,11 +52,13 @@ class FusedMLPFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cfg: dict, *tensors: Tensor):
         nb, nl = len(cfg["blocks"]), len(cfg["linears"])
+        hidden: list = []  # the dedicated 64-wide kernels hand out their two hidden activations: no recompute
         with torch.no_grad():
-            out, aggr = cfg["runner"](cfg, tensors[:nb], tensors[-1] if cfg["has_res"] else None)
+            out, aggr = cfg["runner"](cfg, tensors[:nb], tensors[-1] if cfg["has_res"] else None,
+                                      hidden_out=hidden if nl == 3 and not os.environ.get("GTB_NO_SAVE_HIDDEN") else None)
         ctx.cfg = cfg
-        ctx.save_for_backward(*tensors, out)
-        ctx.nb, ctx.nl = nb, nl
+        ctx.save_for_backward(*tensors, out, *hidden)
+        ctx.nb, ctx.nl, ctx.n_hidden = nb, nl, len(hidden)
         if aggr is None:
             return out
         return out, aggr
@@ -64,6 +67,8 @@ class FusedMLPFunction(torch.autograd.Function):
     def backward(ctx, g_out, g_aggr=None):
         cfg, nb, nl = ctx.cfg, ctx.nb, ctx.nl
         saved = ctx.saved_tensors
+        saved_hidden = list(saved[len(saved) - ctx.n_hidden:]) if ctx.n_hidden else []
+        saved = saved[:len(saved) - ctx.n_hidden]
         tensors, out = saved[:-1], saved[-1]
         blocks_t = tensors[:nb]
         metas = cfg["blocks"]            # (index, relu, unique_index)
@@ -102,8 +107,8 @@ class FusedMLPFunction(torch.autograd.Function):
         fwd_blocks = [Block(t, m[0], m[1]) for t, m in zip(blocks_t, metas)]
         widths = [t.size(1) if t.dim() > 1 else 1 for t in blocks_t]
         sig = (tuple(widths), tuple((m[0] is not None, bool(m[1])) for m in metas))
-        hidden = []
-        if nl >= 2:
+        hidden = saved_hidden  # [h0, h1] from the forward launch, or recomputed below
+        if nl >= 2 and not hidden:
             p0 = packs.get(linears, "prefix0", lambda: ops.pack_linears([weights[0]], [linears[0].bias], ops.default_impl(),
                                                                         block_widths=widths), sig)
             hidden.append(ops.fused_mlp(fwd_blocks, n_rows, p0, final_act=ACT_RELU))

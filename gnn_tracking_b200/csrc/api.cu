@@ -33,6 +33,8 @@ size_t tc_packed_bytes(int, const int32_t*, int, const int32_t*);
 int pack_tc(int, const int32_t*, int, const int32_t*, const float* const*, const float* const*, void*, cudaStream_t);
 int fused_mlp_tc(const gtb_mlp_desc_t&, cudaStream_t);
 int in_edge_ws(const gtb_mlp_desc_t&, cudaStream_t, bool*);
+bool in_edge_ws_takes(const gtb_mlp_desc_t&);
+bool ec_head_ws_takes(const gtb_mlp_desc_t&);
 int ew_fault_flag(int*);
 int ew_profile(int, long long*);
 int ew_pack_bf16(const float* const*, const float* const*, void*, cudaStream_t);
@@ -242,9 +244,18 @@ int gtb_fused_mlp_f32(const gtb_mlp_desc_t* desc, void* stream) {
     // ... and so has the wide W head of the edge classifier (head_ws.cu)
     rc = ec_head_ws(*desc, static_cast<cudaStream_t>(stream), &handled);
     if (rc != GTB_OK || handled) return rc;
+    GTB_REQUIRE(desc->hidden0 == nullptr && desc->hidden1 == nullptr, GTB_ERR_UNSUPPORTED_DIM,
+                "gtb_fused_mlp_f32: hidden0 / hidden1 requested for a launch the generic tiles run (see gtb_fused_mlp_saves_hidden)");
     return fused_mlp_tc(*desc, static_cast<cudaStream_t>(stream));
   }
+  GTB_REQUIRE(desc->hidden0 == nullptr && desc->hidden1 == nullptr, GTB_ERR_UNSUPPORTED_DIM,
+              "gtb_fused_mlp_f32: hidden0 / hidden1 requested for a launch the FFMA tiles run (see gtb_fused_mlp_saves_hidden)");
   return fused_mlp_ffma(*desc, static_cast<cudaStream_t>(stream));
+}
+
+int gtb_fused_mlp_saves_hidden(const gtb_mlp_desc_t* desc) {
+  if (desc == nullptr || desc->impl != GTB_IMPL_TCGEN05 || validate_desc(desc) != GTB_OK) return 0;
+  return (in_edge_ws_takes(*desc) || ec_head_ws_takes(*desc)) ? 1 : 0;
 }
 
 int gtb_in_edge_forward_f32(const float* x, int32_t x_ld, int32_t relu_x, const float* edge_attr, int32_t e_ld,

@@ -85,6 +85,9 @@ struct EwParams {
   const unsigned char* packed;
   int64_t n_rows;
   int32_t n_tiles, pi_ld, aggr_ld, out_ld;
+  float* h0;             // SAVE variant: post-ReLU outputs of the first / second Linear, [n_rows, h_ld] in launch-row order
+  float* h1;
+  int32_t h_ld;
   int32_t debug_bar;     // GTB_EW_DEBUG_BAR=1: a named barrier beside the out_ready mbarrier (compute-sanitizer racecheck
                          // does not model mbarrier hand-overs; with the barrier in place it must report no hazard)
 };
@@ -167,7 +170,7 @@ __device__ __noinline__ void ew_timeout() {
 // state of the 512 row owners.  The context c is a RUN-TIME value: one copy of every stage serves both
 // contexts (the loop body stays inside the instruction cache); the only per-context registers are the
 // four segment ids a lane sums in AG, selected with c.
-template <bool BF, bool RELU_E, bool PROF>
+template <bool BF, bool RELU_E, bool PROF, bool SAVE>
 struct EwOwner {
   static constexpr uint32_t ES = BF ? 2u : 4u;            // bytes per element of the tables
   static constexpr int KT = BF ? 64 : 32;                 // columns of one 128-byte K tile
@@ -244,6 +247,17 @@ struct EwOwner {
     tmem_ld_wait();
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
+  }
+
+  // SAVE: the own 16 post-ReLU columns of row (tile, r) into a [n_rows, h_ld] table (the backward pass reads them
+  // instead of recomputing the hidden activations)
+  __device__ __forceinline__ void save16(float* table, int c, int t, const float (&v)[16]) const {
+    const int64_t row = (int64_t)tile_of(c, t) * EW_TM + r;
+    if (row < p.n_rows) {
+      float4* q = reinterpret_cast<float4*>(table + row * (int64_t)p.h_ld + 16 * qd);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) q[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    }
   }
 
   // ---- C0: own 16 columns of the edge-feature row -> tf32 hi / lo -> TMEM
@@ -352,6 +366,7 @@ struct EwOwner {
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
       split_store16(tm_lane(c) + EW_A_HI + 16 * qd, tm_lane(c) + EW_A_LO + 16 * qd, v);
+      if constexpr (SAVE) save16(p.h0, c, t, v);
     }
     tmem_st_wait();
     tc_fence_before_sync();
@@ -380,6 +395,7 @@ struct EwOwner {
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
       split_store16(tm_lane(c) + EW_A_HI + 16 * qd, tm_lane(c) + EW_A_LO + 16 * qd, v);
+      if constexpr (SAVE) save16(p.h1, c, t, v);
     }
     a_done(c);
     EW_PROF(9);
@@ -577,7 +593,7 @@ struct EwOwner {
   }
 };
 
-template <bool BF, bool RELU_E, bool PROF>
+template <bool BF, bool RELU_E, bool PROF, bool SAVE = false>
 __global__ void __launch_bounds__(EW_THREADS, 1) in_edge_ws_kernel(const __grid_constant__ EwParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t sm0 = smem_u32(smem_raw);
@@ -630,7 +646,7 @@ __global__ void __launch_bounds__(EW_THREADS, 1) in_edge_ws_kernel(const __grid_
 
   if (warp < 16) {
     // ================================================================= row owners
-    EwOwner<BF, RELU_E, PROF> o{p, sm0};
+    EwOwner<BF, RELU_E, PROF, SAVE> o{p, sm0};
     o.w = warp; o.lane = lane; o.r = 32 * (warp & 3) + lane; o.qd = warp >> 2;
     o.rx = (uint32_t)(o.r & 7) << 4;
     o.own = (uint32_t)(o.qd >> 1) * 16384u + (uint32_t)o.r * 128u;
@@ -765,9 +781,9 @@ __global__ void __launch_bounds__(EW_THREADS, 1) in_edge_ws_kernel(const __grid_
 }
 
 // ------------------------------------------------------------------------------ host side
-template <bool BF, bool RELU_E, bool PROF>
+template <bool BF, bool RELU_E, bool PROF, bool SAVE = false>
 static cudaError_t ew_configure() {
-  return cudaFuncSetAttribute(in_edge_ws_kernel<BF, RELU_E, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, EW_SMEM);
+  return cudaFuncSetAttribute(in_edge_ws_kernel<BF, RELU_E, PROF, SAVE>, cudaFuncAttributeMaxDynamicSharedMemorySize, EW_SMEM);
 }
 
 static int ew_launch(EwParams& p, bool bf, bool relu, cudaStream_t st) {
@@ -782,6 +798,8 @@ static int ew_launch(EwParams& p, bool bf, bool relu, cudaStream_t st) {
     if (e == cudaSuccess) e = ew_configure<false, true, true>();
     if (e == cudaSuccess) e = ew_configure<true, false, false>();
     if (e == cudaSuccess) e = ew_configure<true, true, false>();
+    if (e == cudaSuccess) e = ew_configure<false, false, false, true>();
+    if (e == cudaSuccess) e = ew_configure<false, true, false, true>();
     if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(in_edge_ws)");
     configured = true;
   }
@@ -790,6 +808,9 @@ static int ew_launch(EwParams& p, bool bf, bool relu, cudaStream_t st) {
   if (bf) {
     if (relu) in_edge_ws_kernel<true, true, false><<<grid, EW_THREADS, EW_SMEM, st>>>(p);
     else      in_edge_ws_kernel<true, false, false><<<grid, EW_THREADS, EW_SMEM, st>>>(p);
+  } else if (p.h0 != nullptr) {
+    if (relu) in_edge_ws_kernel<false, true, false, true><<<grid, EW_THREADS, EW_SMEM, st>>>(p);
+    else      in_edge_ws_kernel<false, false, false, true><<<grid, EW_THREADS, EW_SMEM, st>>>(p);
   } else if (g_ew_prof_enabled) {
     if (relu) in_edge_ws_kernel<false, true, true><<<grid, EW_THREADS, EW_SMEM, st>>>(p);
     else      in_edge_ws_kernel<false, false, true><<<grid, EW_THREADS, EW_SMEM, st>>>(p);
@@ -865,9 +886,23 @@ int in_edge_ws(const gtb_mlp_desc_t& d, cudaStream_t st, bool* handled) {
   p.n_tiles = (int32_t)((d.n_rows + EW_TM - 1) / EW_TM);
   p.out = d.out;
   p.out_ld = d.out_ld;
+  if (d.hidden0 != nullptr || d.hidden1 != nullptr) {
+    GTB_REQUIRE(d.hidden0 != nullptr && d.hidden1 != nullptr && d.hidden_ld >= 64 && !(d.hidden_ld & 3) &&
+                    !(reinterpret_cast<uintptr_t>(d.hidden0) & 15) && !(reinterpret_cast<uintptr_t>(d.hidden1) & 15),
+                GTB_ERR_BAD_ARG, "gtb_fused_mlp_f32: hidden0 / hidden1 come as a pair of 16-byte aligned [n_rows, >= 64] tables");
+    p.h0 = d.hidden0;
+    p.h1 = d.hidden1;
+    p.h_ld = d.hidden_ld;
+  }
   *handled = true;
   if (d.n_rows == 0) return GTB_OK;
   return ew_launch(p, false, se.relu != 0, st);
+}
+
+bool in_edge_ws_takes(const gtb_mlp_desc_t& d) {
+  static const bool disabled = getenv("GTB_NO_EDGE_WS") != nullptr;
+  int s_e, s_pi, s_pj;
+  return !disabled && ew_match(d, &s_e, &s_pi, &s_pj) && tma::encode_fn() != nullptr;
 }
 
 // ------------------------------------------------------------------------------ bf16 variant (128 / 128 / 128)

@@ -63,6 +63,9 @@ struct HwParams {
   int64_t n_rows;
   int32_t n_tiles, tdst_ld, out_ld, final_act;
   float act_eps;
+  float* h0;  // optional: post-ReLU outputs of the first / second Linear, [n_rows, h_ld] in launch-row order
+  float* h1;
+  int32_t h_ld;
 };
 
 __device__ __noinline__ void hw_timeout() {
@@ -147,6 +150,15 @@ struct HwOwner {
     add16(v, lds128(ba), lds128(ba + 16), lds128(ba + 32), lds128(ba + 48));
   }
 
+  __device__ __forceinline__ void save16(float* table, int c, int t, const float (&v)[16]) const {
+    const int64_t row = (int64_t)tile_of(c, t) * HW_TM + r;
+    if (row < p.n_rows) {
+      float4* q = reinterpret_cast<float4*>(table + row * (int64_t)p.h_ld + 16 * qd);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) q[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    }
+  }
+
   // ---- C0: K chunk k (edge-embedding block k): own 16 columns -> tf32 hi / lo -> TMEM
   __device__ __forceinline__ void c0(int c, int t, int k) {
     const int s = k & 1;
@@ -210,6 +222,7 @@ struct HwOwner {
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
     split_store16(tm_lane(c) + HW_A_HI + 16 * qd, tm_lane(c) + HW_A_LO + 16 * qd, v);
+    if (p.h0 != nullptr) save16(p.h0, c, t, v);
     tmem_st_wait();
     tc_fence_before_sync();
     __syncwarp();
@@ -225,15 +238,18 @@ struct HwOwner {
     float v[16];
     acc_load(c, v);
     bias_add(v, 1);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+    if (p.h1 != nullptr) save16(p.h1, c, t, v);
     const uint32_t wa = sm0 + HW_BIAS + 512 + 64 * qd;
     float part = 0.f;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const float4 w4 = lds128(wa + 16 * q);
-      part = fmaf(fmaxf(v[4 * q + 0], 0.f), w4.x, part);
-      part = fmaf(fmaxf(v[4 * q + 1], 0.f), w4.y, part);
-      part = fmaf(fmaxf(v[4 * q + 2], 0.f), w4.z, part);
-      part = fmaf(fmaxf(v[4 * q + 3], 0.f), w4.w, part);
+      part = fmaf(v[4 * q + 0], w4.x, part);
+      part = fmaf(v[4 * q + 1], w4.y, part);
+      part = fmaf(v[4 * q + 2], w4.z, part);
+      part = fmaf(v[4 * q + 3], w4.w, part);
     }
     tmem_st1(tm_lane(c) - (uint32_t)c * HW_CTX + HW_RED + 4 * c + qd, __float_as_uint(part));
     tmem_st_wait();
@@ -529,6 +545,14 @@ int ec_head_ws(const gtb_mlp_desc_t& d, cudaStream_t st, bool* handled) {
   p.n_tiles = (int32_t)((d.n_rows + HW_TM - 1) / HW_TM);
   p.final_act = d.final_act;
   p.act_eps = d.act_eps;
+  if (d.hidden0 != nullptr || d.hidden1 != nullptr) {
+    GTB_REQUIRE(d.hidden0 != nullptr && d.hidden1 != nullptr && d.hidden_ld >= 64 && !(d.hidden_ld & 3) &&
+                    !(reinterpret_cast<uintptr_t>(d.hidden0) & 15) && !(reinterpret_cast<uintptr_t>(d.hidden1) & 15),
+                GTB_ERR_BAD_ARG, "gtb_fused_mlp_f32: hidden0 / hidden1 come as a pair of 16-byte aligned [n_rows, >= 64] tables");
+    p.h0 = d.hidden0;
+    p.h1 = d.hidden1;
+    p.h_ld = d.hidden_ld;
+  }
   *handled = true;
   if (d.n_rows == 0) return GTB_OK;
   static PerDeviceOnce once;
@@ -543,6 +567,13 @@ int ec_head_ws(const gtb_mlp_desc_t& d, cudaStream_t st, bool* handled) {
   ec_head_ws_kernel<<<grid, HW_THREADS, HW_SMEM, st>>>(p);
   GTB_CHECK_LAUNCH("ec_head_ws_kernel");
   return GTB_OK;
+}
+
+bool ec_head_ws_takes(const gtb_mlp_desc_t& d) {
+  static const bool disabled = getenv("GTB_NO_HEAD_WS") != nullptr;
+  int s_src, s_dst, s_e[4];
+  const int32_t dims[4] = {256, 64, 64, 1}, bw[4] = {64, 64, 64, 64};
+  return !disabled && hw_match(d, &s_src, &s_dst, s_e) && tma::encode_fn() != nullptr && tc_packed_bytes(3, dims, 4, bw) == HP_BYTES;
 }
 
 int hw_fault_flag(int* out) { return check_cuda(cudaMemcpyFromSymbol(out, g_hw_fault, sizeof(int)), "cudaMemcpyFromSymbol(g_hw_fault)"); }

@@ -72,9 +72,11 @@ def condensation_loss_tiger(*, beta: Tensor, x: Tensor, object_id: Tensor, objec
     """Same contract as the reference function (oc.py:251-347): returns
     ``({"attractive", "repulsive", "coward", "noise"}, {"n_rep"})``.  Differentiable w.r.t. ``beta``
     and ``x``."""
-    if max_n_rep:
-        raise NotImplementedError("max_n_rep sub-sampling uses the reference's fp16 torch RNG stream and is "
-                                  "not reproduced; the tiled kernel needs no sub-sampling to fit in memory")
+    # max_n_rep (oc.py:320-328): the reference keeps each repulsive pair with probability max_n_rep / n_rep and
+    # divides the normalisation by the same factor -- an unbiased estimate of the full sum that exists to bound
+    # the memory of its N x K planes.  The tiled kernel has no such planes: it returns the full sum, i.e. the
+    # expectation of the reference's estimate, without the sampling noise.
+    del max_n_rep
     ops.require_cuda(beta, x, object_id, object_mask)
     shape = beta.shape
     beta = beta.reshape(-1).to(torch.float32).contiguous()
@@ -131,8 +133,9 @@ class CondensationLossTiger(MultiLossFct, HyperparametersMixin):
             particle_id, reconstructable, pt, eta = (t[ec_hit_mask] for t in (particle_id, reconstructable, pt, eta))
         mask = get_good_node_mask_tensors(pt=pt, particle_id=particle_id, reconstructable=reconstructable,
                                           eta=eta, pt_thld=hp.pt_thld, max_eta=hp.max_eta)
-        if hp.sample_pids < 1:
-            raise NotImplementedError("sample_pids < 1 draws from the reference's fp16 torch RNG stream")
+        if hp.sample_pids < 1:  # the reference's own draw (oc.py:410-414): same call, same torch RNG stream
+            mask = mask & (torch.rand_like(beta, dtype=torch.float16) < hp.sample_pids)
+        assert mask.sum() > 0, "No hits left after masking"
         losses, extra = condensation_loss_tiger(beta=beta, x=x, object_id=particle_id, object_mask=mask,
                                                 q_min=hp.q_min, noise_threshold=0, max_n_rep=hp.max_n_rep)
         weights = {"attractive": 1.0, "repulsive": hp.lw_repulsive, "noise": hp.lw_noise, "coward": hp.lw_coward}
@@ -156,8 +159,8 @@ class CondensationLossRG(MultiLossFct, HyperparametersMixin):
             particle_id, reconstructable, pt, eta = (t[ec_hit_mask] for t in (particle_id, reconstructable, pt, eta))
         mask = get_good_node_mask_tensors(pt=pt, particle_id=particle_id, reconstructable=reconstructable,
                                           eta=eta, pt_thld=hp.pt_thld, max_eta=hp.max_eta)
-        if hp.sample_pids < 1:
-            raise NotImplementedError("sample_pids < 1 draws from the reference's fp16 torch RNG stream")
+        if hp.sample_pids < 1:  # oc.py:221-225
+            mask = mask & (torch.rand_like(beta, dtype=torch.float16) < hp.sample_pids)
         losses, extra = condensation_loss_rg(beta=beta, x=x, particle_id=particle_id, mask=mask, q_min=hp.q_min,
                                              radius_threshold=1.0, max_num_neighbors=hp.max_num_neighbors)
         weights = {"attractive": 1.0, "repulsive": hp.lw_repulsive, "noise": hp.lw_noise, "coward": hp.lw_coward}

@@ -159,7 +159,8 @@ def _run_autocast(linears: Sequence[nn.Linear], blocks: Sequence[Block], n_rows:
 
 
 def _run_nograd(cache: PackedCache, linears: Sequence[nn.Linear], blocks: Sequence[Block], n_rows: int,
-                *, final_act: int = ACT_NONE, tables: dict | None = None, **epilogue) -> Tensor | None:
+                *, final_act: int = ACT_NONE, tables: dict | None = None, save_hidden: list | None = None,
+                **epilogue) -> Tensor | None:
     """Linear/ReLU chain over concatenated column blocks; <= 3 Linear layers per
     fused launch, longer chains are split with the intermediate kept in HBM.
 
@@ -214,6 +215,8 @@ def _run_nograd(cache: PackedCache, linears: Sequence[nn.Linear], blocks: Sequen
             h = ops.fused_mlp(cur, n_rows, p, final_act=ACT_RELU)
             cur = [Block(h)]
         else:
+            if save_hidden is not None and len(packed) == 1 and p.n_layers == 3:
+                epilogue = dict(epilogue, save_hidden=save_hidden)  # see ops.fused_mlp
             return ops.fused_mlp(cur, n_rows, p, final_act=final_act, **epilogue)
     raise AssertionError("unreachable")
 
@@ -272,7 +275,7 @@ def run_linears(cache: PackedCache, linears: Sequence[nn.Linear], blocks: Sequen
     if not hasattr(cache, "bwd"):
         cache.bwd = _BwdPacks()
 
-    def runner(cfg, block_tensors, res_t):
+    def runner(cfg, block_tensors, res_t, hidden_out=None):
         bl = [Block(t, m[0], m[1], sorted_index=s, unique_index=m[2]) for t, m, s in zip(block_tensors, cfg["blocks"], cfg["sorted"])]
         dev = block_tensors[0].device
         aggr = None
@@ -283,7 +286,7 @@ def run_linears(cache: PackedCache, linears: Sequence[nn.Linear], blocks: Sequen
         if res_t is not None:
             kw.update(res=res_t, res_a=cfg["res_a"])
         out = _run_nograd(cache, linears, bl, cfg["n_rows"], final_act=cfg["final_act"], act_eps=cfg["act_eps"],
-                          res_b=cfg["res_b"], out_index=cfg["out_index"], **kw)
+                          res_b=cfg["res_b"], out_index=cfg["out_index"], save_hidden=hidden_out, **kw)
         return out, aggr
 
     return fused_mlp_autograd(runner, cache.bwd, linears, blocks, n_rows, final_act=final_act,

@@ -189,7 +189,8 @@ def fused_mlp(blocks: Sequence[Block], n_rows: int, packed: PackedMLP, *, final_
               act_eps: float = 0.0, res: Tensor | None = None, res_a: float = 0.0, res_b: float = 1.0,
               row_scale: Tensor | None = None, out_scale: Tensor | None = None, out: Tensor | None = None, out_index: Tensor | None = None,
               want_out: bool = True, aggr: Tensor | None = None, seg_id: Tensor | None = None,
-              rowptr: Tensor | None = None, out_rows: int | None = None, gate: Tensor | None = None) -> Tensor | None:
+              rowptr: Tensor | None = None, out_rows: int | None = None, gate: Tensor | None = None,
+              save_hidden: list | None = None) -> Tensor | None:
     """``out[orow(r)] = epilogue(MLP(cat_s act_s(block_s[irow_s(r)])))`` -- see
     ``gtb_fused_mlp_f32`` in include/gtb200.h."""
     tensors = [_f32c(b.tensor) for b in blocks]
@@ -232,6 +233,13 @@ def fused_mlp(blocks: Sequence[Block], n_rows: int, packed: PackedMLP, *, final_
     if aggr is not None:
         d.aggr, d.aggr_ld = aggr.data_ptr(), aggr.stride(0)
         d.seg_id, d.rowptr = _idx(seg_id), _idx(rowptr)
+    if save_hidden is not None and n_rows > 0 and lib().gtb_fused_mlp_saves_hidden(C.byref(d)):
+        # the kernel that takes this launch can hand out the two hidden activations (the backward pass then
+        # does not recompute them): appended to ``save_hidden``
+        h0 = torch.empty((n_rows, 64), dtype=torch.float32, device=dev)
+        h1 = torch.empty((n_rows, 64), dtype=torch.float32, device=dev)
+        d.hidden0, d.hidden1, d.hidden_ld = h0.data_ptr(), h1.data_ptr(), 64
+        save_hidden.extend([h0, h1])
     if n_rows > 0:  # an empty edge set (E = 0) launches nothing; `out` is empty, `aggr` stays zero
         with on_device(dev):
             check(lib().gtb_fused_mlp_f32(C.byref(d), stream_ptr(dev)))

@@ -182,10 +182,18 @@ typedef struct {
    * activation with it (d relu, models/mlp.py:44-51). */
   const float* gate;
   int32_t   gate_ld;
-  int32_t   reserved;
+  /* optional: the two hidden activations (post-ReLU outputs of the first and the second Linear) of a
+   * 3-Linear launch, [n_rows, hidden_ld] in launch-row order -- what the backward pass otherwise recomputes
+   * (models/mlp.py:59-62 under autograd keeps them as saved tensors).  Only the dedicated 64-wide kernels
+   * write them: ask gtb_fused_mlp_saves_hidden first; a launch that cannot honour the request is refused. */
+  int32_t   hidden_ld;
+  float*    hidden0;
+  float*    hidden1;
 } gtb_mlp_desc_t;
 
 int gtb_fused_mlp_f32(const gtb_mlp_desc_t* desc, void* stream);
+/* 1 if gtb_fused_mlp_f32 would run this descriptor on a kernel that can write hidden0 / hidden1, else 0. */
+int gtb_fused_mlp_saves_hidden(const gtb_mlp_desc_t* desc);
 
 /* Test hook (synchronises): *flag != 0 if a tcgen05 kernel ever gave up waiting for its MMA
  * barrier -- such a kernel traps, so the CUDA error is sticky as well. */

@@ -16,12 +16,25 @@ def _graph(n, e, dn, de, seed=0):
     return ei, torch.randn(n, dn, generator=gen), torch.randn(e, de, generator=gen), gen
 
 
-def _check(name, got, ref, rtol=RTOL):
+def _check(name, got, ref, rtol=RTOL, kink_frob=None):
+    """Elementwise: max|got - ref| <= rtol * max|ref|.  ``kink_frob``: the derivative of ReLU jumps at 0, and a hidden
+    pre-activation within fp32 noise of zero (~1e-6; an instance with 1.2 M hidden units has a couple that close)
+    lands on either side depending on the summation order -- the oracle's, the recomputing backward's, or the forward
+    kernel's whose activations the backward reuses.  One such unit flips a whole gradient column by O(1) while
+    everything else agrees to fp32 noise: where the elementwise bound fails, the Frobenius error must stay below
+    ``kink_frob`` (a wrong backward is off by O(1) there too)."""
     assert got is not None, f"{name}: no gradient"
     got, ref = got.detach().cpu().double(), ref.detach().cpu().double()
     assert got.shape == ref.shape, (name, got.shape, ref.shape)
     scale = float(ref.abs().max())
     err = float((got - ref).abs().max())
+    if err <= rtol * scale + 1e-7:
+        return
+    if kink_frob is not None:
+        frob = float((got - ref).norm() / ref.norm().clamp_min(1e-30))
+        n_off = int(((got - ref).abs() > rtol * scale + 1e-7).sum())
+        assert frob <= kink_frob, f"{name}: relative Frobenius error {frob:.3e} ({n_off} of {got.numel()} elements off)"
+        return
     assert err <= rtol * scale + 1e-7, f"{name}: max|d|={err:.3e} scale={scale:.3e}"
 
 
@@ -31,14 +44,20 @@ def impl(request, monkeypatch):
     return request.param
 
 
+@pytest.mark.parametrize("save_hidden", [False, True])
 @pytest.mark.parametrize("dims", [(64, 64, 64), (5, 4, 64), (8, 4, 40)])
-def test_in_layer_backward(dims, impl):
+def test_in_layer_backward(dims, impl, save_hidden, monkeypatch):
+    """``save_hidden`` False: the backward recomputes the hidden activations (strict elementwise bound);
+    True: it reuses the ones the dedicated forward kernels hand out (64-wide shapes on the tensor-core path:
+    ReLU masks consistent with the forward that ran; kink-tolerant bound, see ``_check``)."""
+    if not save_hidden:
+        monkeypatch.setenv("GTB_NO_SAVE_HIDDEN", "1")
     from gnn_tracking_b200.models.interaction_network import InteractionNetwork
     from oracle import in_oracle as O
     dn, de, h = dims
-    ei, x, ea, gen = _graph(700, 9000, dn, de, seed=1)
     torch.manual_seed(2)
     m = InteractionNetwork(node_indim=dn, edge_indim=de, node_outdim=dn, edge_outdim=de, node_hidden_dim=h, edge_hidden_dim=h)
+    ei, x, ea, gen = _graph(700, 9000, dn, de, seed=1)
     gx, ge = torch.randn(700, dn, generator=gen), torch.randn(9000, de, generator=gen)
     sd = {k: v.detach().double().requires_grad_() for k, v in m.state_dict().items()}
     xr, er = x.double().requires_grad_(), ea.double().requires_grad_()
@@ -49,10 +68,11 @@ def test_in_layer_backward(dims, impl):
     xc, ec = x.cuda().requires_grad_(), ea.cuda().requires_grad_()
     xt2, et2 = m(xc, ei.cuda(), ec)
     ((xt2 * gx.cuda()).sum() + (et2 * ge.cuda()).sum()).backward()
-    _check("x", xc.grad, xr.grad)
-    _check("edge_attr", ec.grad, er.grad)
+    kink = 1e-2 if save_hidden else None
+    _check("x", xc.grad, xr.grad, kink_frob=kink)
+    _check("edge_attr", ec.grad, er.grad, kink_frob=kink)
     for k, p in m.named_parameters():
-        _check(k, p.grad, sd[k].grad)
+        _check(k, p.grad, sd[k].grad, kink_frob=kink)
 
 
 @pytest.mark.parametrize("kw", [dict(interaction_node_dim=64, interaction_edge_dim=64, hidden_dim=64, L_ec=2),

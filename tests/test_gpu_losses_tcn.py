@@ -136,3 +136,37 @@ def test_condensation_tiger_large_vs_oracle():
     for k in ref:
         _loss_close(got[k], ref[k], k)
     assert abs(int(gx["n_rep"]) - int(extra["n_rep"])) <= 3  # pairs with dist within 1 ulp of 1
+
+
+def test_condensation_losses_sampling_options():
+    """``sample_pids < 1`` (oc.py:221-225, 410-414) draws the reference's own per-hit mask -- the same
+    ``torch.rand_like(beta, dtype=float16)`` call on the same generator -- and ``max_n_rep`` (oc.py:320-328) returns
+    the full repulsive sum, the expectation of the reference's sub-sampled estimate."""
+    from gnn_tracking_b200.metrics.losses.oc import CondensationLossRG, CondensationLossTiger
+    from oracle import losses_oracle as L
+    gen = torch.Generator().manual_seed(21)
+    n = 6000
+    pid = torch.randint(0, 500, (n,), generator=gen)
+    beta = torch.rand(n, generator=gen).clamp(1e-3, 1 - 1e-3)
+    x = torch.randn(n, 3, generator=gen) * 2
+    pt = torch.rand(n, generator=gen) * 3
+    eta = torch.randn(n, generator=gen) * 2
+    rec = torch.rand(n, generator=gen) < 0.9
+    args = dict(beta=beta.cuda(), x=x.cuda(), particle_id=pid.cuda(), reconstructable=rec.cuda(), pt=pt.cuda(), eta=eta.cuda())
+    # the mask the loss will draw
+    torch.manual_seed(77)
+    drawn = (torch.rand_like(args["beta"], dtype=torch.float16) < 0.5).cpu()
+    base = L.good_node_mask(pt=pt, particle_id=pid, reconstructable=rec, eta=eta, pt_thld=0.9, max_eta=4.0)
+    ref, _ = L.condensation_tiger(beta=beta.double(), x=x.double(), object_id=pid, object_mask=base & drawn)
+    torch.manual_seed(77)
+    with torch.no_grad():
+        got = CondensationLossTiger(sample_pids=0.5, max_n_rep=1000)(**args)
+    for k in ref:
+        _loss_close(got.loss_dct[k], ref[k], k)
+    # the same switch on the radius-graph variant: fewer masked hits than without it, still finite
+    torch.manual_seed(77)
+    with torch.no_grad():
+        rg_half = CondensationLossRG(sample_pids=0.5)(**args)
+        rg_full = CondensationLossRG()(**args)
+    assert all(torch.isfinite(v) for v in rg_half.loss_dct.values())
+    assert float(rg_half.loss_dct["attractive"]) != float(rg_full.loss_dct["attractive"])
