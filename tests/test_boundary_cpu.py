@@ -29,7 +29,8 @@ def test_desc_struct_matches_header_layout():
     assert _lib.MlpDesc.srcs.offset == 16
     assert _lib.MlpDesc.dims.offset == 16 + 32 * 16
     assert _lib.MlpDesc.packed.offset == 544
-    assert _lib.C.sizeof(_lib.MlpDesc) == 664 and _lib.MlpDesc.gate.offset == 648
+    assert _lib.MlpDesc.gate.offset == 648 and _lib.MlpDesc.hidden_ld.offset == 660
+    assert _lib.MlpDesc.hidden0.offset == 664 and _lib.MlpDesc.hidden1.offset == 672 and _lib.C.sizeof(_lib.MlpDesc) == 680
 
 
 def test_packed_bytes_host_logic():
