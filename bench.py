@@ -370,16 +370,30 @@ def run_ours(args) -> None:
     hw = torch.empty(e, dtype=torch.float32).pin_memory()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    def step_resident():
+    def step_eager():
         clear_plan_cache()
         with torch.no_grad():
             return model.forward_tensors(x, ei, ea, halo=halo)
 
+    # The step as ONE CUDA graph launch (graphs.CapturedForward: plan build + forward recorded over static input
+    # buffers, replayed per step; same kernels, same work, no per-launch host time).  GTB_BENCH_NO_GRAPH=1: eager.
+    # N > 1: the NCCL exchanges would have to be captured too -- eager unless GTB_BENCH_GRAPH_MULTI=1.
+    cap = None
+    if not os.environ.get("GTB_BENCH_NO_GRAPH") and (world == 1 or os.environ.get("GTB_BENCH_GRAPH_MULTI")):
+        from gnn_tracking_b200.graphs import CapturedForward
+        cap = CapturedForward(model, x, ei, ea, halo=halo)
+
+    def step_resident():
+        return cap.replay() if cap is not None else step_eager()
+
     def step_e2e():
-        clear_plan_cache()
-        dx, dei, dea = hx.to(dev, non_blocking=True), hei.to(dev, non_blocking=True), hea.to(dev, non_blocking=True)
-        with torch.no_grad():
-            out = model.forward_tensors(dx, dei, dea, halo=halo)
+        if cap is not None:  # pinned host -> the graph's static input buffers -> replay -> read back
+            out = cap(hx, hei, hea)
+        else:
+            clear_plan_cache()
+            dx, dei, dea = hx.to(dev, non_blocking=True), hei.to(dev, non_blocking=True), hea.to(dev, non_blocking=True)
+            with torch.no_grad():
+                out = model.forward_tensors(dx, dei, dea, halo=halo)
         hw.copy_(out["W"], non_blocking=True)
         return out
 
@@ -417,10 +431,15 @@ def run_ours(args) -> None:
         def run(k):
             for data in DevicePrefetcher((host_graph for _ in range(k)), dev):
                 flush.zero_()
-                clear_plan_cache()
-                with torch.no_grad():
-                    out = model.forward_tensors(data.x, data.edge_index, data.edge_attr, halo=halo)
-                reader.read(out["W"])  # read-back of step k on its own stream, under step k + 1
+                if cap is not None:
+                    # the prefetched graph into the static inputs (device copies, 37.6 MB), one graph launch; W leaves
+                    # the static output buffer before the next replay overwrites it
+                    w = cap(data.x, data.edge_index, data.edge_attr)["W"].clone()
+                else:
+                    clear_plan_cache()
+                    with torch.no_grad():
+                        w = model.forward_tensors(data.x, data.edge_index, data.edge_attr, halo=halo)["W"]
+                reader.read(w)  # read-back of step k on its own stream, under step k + 1
             reader.wait()              # the timed region ends behind the last read-back
 
         run(warmup)
@@ -516,6 +535,9 @@ def run_ours(args) -> None:
                                 workload_name(args.dims, int(N_NODES * args.total_scale), int(N_EDGES * args.total_scale))
                                 + f" partitioned over {world} ranks"),
                    "l2": "flushed between timed iterations (256 MB write)", "multi_gpu": multi,
+                   "launch": ("one CUDA graph launch per step (graphs.CapturedForward: plan build + forward over static "
+                              "input buffers, %d library kernels per replay)" % cap.launches) if cap is not None else
+                             "eager: one host launch per kernel",
                    "impl": os.environ.get("GTB_IMPL", "auto")},
         "e2e": {"value": e2e_val, "unit": "edges/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": hx.numel() * 4 + hei.numel() * 8 + hea.numel() * 4, "d2h_bytes_per_step": e * 4,

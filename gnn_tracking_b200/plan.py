@@ -138,7 +138,8 @@ def _remember(edge_index: Tensor, n_nodes: int, plan: GraphPlan) -> None:
 
 
 def get_plan(edge_index: Tensor, n_nodes: int) -> GraphPlan:
-    _poll_status()
+    if not torch.cuda.is_current_stream_capturing():
+        _poll_status()
     hit = _CACHE.get(id(edge_index))
     if hit is not None:
         ref, version, n, plan = hit
@@ -174,6 +175,8 @@ _status_next = 0
 
 def _defer_status_check(status: Tensor) -> None:
     global _status_host, _status_next
+    if torch.cuda.is_current_stream_capturing():
+        return  # inside a CUDA graph (graphs.CapturedForward): the flag stays on the device, ``validate`` reads it
     if _status_host is None:
         _status_host = torch.zeros(_STATUS_SLOTS, dtype=torch.int32).pin_memory()
     if len(_status_pending) >= _STATUS_SLOTS:  # ring full: settle the oldest check now
