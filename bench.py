@@ -381,7 +381,11 @@ def run_ours(args) -> None:
     cap = None
     if not os.environ.get("GTB_BENCH_NO_GRAPH") and (world == 1 or os.environ.get("GTB_BENCH_GRAPH_MULTI")):
         from gnn_tracking_b200.graphs import CapturedForward
-        cap = CapturedForward(model, x, ei, ea, halo=halo)
+        try:
+            cap = CapturedForward(model, x, ei, ea, halo=halo)
+        except Exception as exc:  # noqa: BLE001 - a capture that fails must not take the measurement down: eager launches
+            print(f"bench: CUDA graph capture failed ({type(exc).__name__}: {exc}); running eagerly", file=sys.stderr)
+            cap = None
 
     def step_resident():
         return cap.replay() if cap is not None else step_eager()

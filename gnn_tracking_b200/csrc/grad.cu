@@ -120,6 +120,80 @@ __global__ void __launch_bounds__(ATB_THREADS, 3) rows_atb_kernel(const float* _
   if (colsum != nullptr && tid < nb) atomicAdd(colsum + tid, csum);
 }
 
+// One side at most 4 columns wide (the K = 4 first Linear of the edge encoder, the 64 -> 1 last Linear of the W head):
+// a matrix-vector-like product that the 64 x 64 tiles above pad sixteen-fold.  Thread = one column of the WIDE side
+// with <= 4 accumulators, four row groups per block; the narrow side's row is a broadcast load.  Memory-bound.
+template <bool NARROW_A>
+__global__ void __launch_bounds__(256) rows_atb_narrow_kernel(const float* __restrict__ A, int a_ld, const int32_t* __restrict__ a_index,
+                                                              int a_relu, int ka, const float* __restrict__ B, int b_ld, int nb,
+                                                              int64_t n_rows, float* __restrict__ out, int out_ld,
+                                                              float* __restrict__ colsum) {
+  __shared__ float red[4][64][4];
+  const int c = threadIdx.x & 63, g = threadIdx.x >> 6;
+  const int wide = NARROW_A ? nb : ka, narrow = NARROW_A ? ka : nb;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f}, cs[4] = {0.f, 0.f, 0.f, 0.f};
+  // four rows per trip, their loads issued together (the trip is latency-bound otherwise: one 4-byte load per thread)
+  const int64_t step = (int64_t)gridDim.x * 4;
+  for (int64_t r0 = (int64_t)blockIdx.x * 4 + g; r0 < n_rows; r0 += 4 * step) {
+    float wv[4], nv[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t r = r0 + u * step;
+      const bool ok = r < n_rows;
+      const int64_t rc = ok ? r : n_rows - 1;  // clamped: no branch between the loads; the contribution is zeroed below
+      const int64_t ar = a_index ? (int64_t)__ldg(a_index + rc) : rc;
+      if (NARROW_A) {
+        wv[u] = (ok && c < wide) ? __ldg(B + (size_t)rc * b_ld + c) : 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) nv[u][k] = k < narrow ? __ldg(A + (size_t)ar * a_ld + k) : 0.f;
+      } else {
+        wv[u] = (ok && c < wide) ? __ldg(A + (size_t)ar * a_ld + c) : 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) nv[u][k] = (ok && k < narrow) ? __ldg(B + (size_t)rc * b_ld + k) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (NARROW_A) {
+        cs[0] += wv[u];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[k] = fmaf(a_relu ? fmaxf(nv[u][k], 0.f) : nv[u][k], wv[u], acc[k]);
+      } else {
+        const float a = a_relu ? fmaxf(wv[u], 0.f) : wv[u];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          acc[k] = fmaf(a, nv[u][k], acc[k]);
+          cs[k] += nv[u][k];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) red[g][c][k] = acc[k];
+  __syncthreads();
+  if (g == 0 && c < wide) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k < narrow) {
+        const float v = red[0][c][k] + red[1][c][k] + red[2][c][k] + red[3][c][k];
+        if (NARROW_A) atomicAdd(out + (size_t)k * out_ld + c, v);
+        else          atomicAdd(out + (size_t)c * out_ld + k, v);
+      }
+    }
+  }
+  if (colsum != nullptr) {
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) red[g][c][k] = cs[k];
+    __syncthreads();
+    if (NARROW_A) {
+      if (g == 0 && c < wide) atomicAdd(colsum + c, red[0][c][0] + red[1][c][0] + red[2][c][0] + red[3][c][0]);
+    } else if (g == 0 && c == 0) {  // every thread of a row group summed the same b values: take column 0's
+      for (int j = 0; j < narrow; ++j) atomicAdd(colsum + j, red[0][0][j] + red[1][0][j] + red[2][0][j] + red[3][0][j]);
+    }
+  }
+}
+
 int rows_atb(const float* A, int a_ld, const int32_t* a_index, int a_relu, int ka, const float* B, int b_ld, int nb,
              int64_t n_rows, float* out, int out_ld, float* colsum, cudaStream_t st) {
   GTB_REQUIRE(A && B && out && ka >= 1 && ka <= 64 && nb >= 1 && nb <= 64 && a_ld >= ka && b_ld >= nb && out_ld >= nb,
@@ -129,6 +203,13 @@ int rows_atb(const float* A, int a_ld, const int32_t* a_index, int a_relu, int k
     bool handled = false;
     const int rc = rows_atb_tc(A, a_ld, a_index, a_relu, ka, B, b_ld, nb, n_rows, out, out_ld, colsum, st, &handled);
     if (rc != GTB_OK || handled) return rc;
+  }
+  if ((ka <= 4 || nb <= 4) && n_rows >= 1024) {
+    const int grid = (int)imin64((n_rows + 63) / 64, (int64_t)kNumSMs * 8);
+    if (ka <= 4) rows_atb_narrow_kernel<true><<<grid, 256, 0, st>>>(A, a_ld, a_index, a_relu, ka, B, b_ld, nb, n_rows, out, out_ld, colsum);
+    else         rows_atb_narrow_kernel<false><<<grid, 256, 0, st>>>(A, a_ld, a_index, a_relu, ka, B, b_ld, nb, n_rows, out, out_ld, colsum);
+    GTB_CHECK_LAUNCH("rows_atb_narrow_kernel");
+    return GTB_OK;
   }
   const int64_t n_tiles = (n_rows + ATB_ROWS - 1) / ATB_ROWS;
   // every CTA ends with 64 x 64 atomics onto the same addresses: at least 16 tiles per CTA, and no

@@ -17,3 +17,13 @@ for label, kw in (("plain", {}), ("relu+colsum", dict(a_relu=True, colsum=cs)), 
         if i >= 3: ts.append(s.elapsed_time(e))
     t = sum(ts) / len(ts)
     print(f"rows_atb {label}: {t * 1e3:.1f} us per launch, {n * 512 / t / 1e6:.0f} GB/s")
+for label, (ka, nb) in (("64x1", (64, 1)), ("4x64", (4, 64))):
+    aa, bb = torch.randn(n, ka, device="cuda"), torch.randn(n, nb, device="cuda")
+    oo = torch.zeros(ka, nb, device="cuda")
+    ts = []
+    for i in range(8):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); ops.rows_atb(aa, bb, oo); e.record(); torch.cuda.synchronize()
+        if i >= 3: ts.append(s.elapsed_time(e))
+    print(f"rows_atb {label}: {sum(ts) / len(ts) * 1e3:.1f} us per launch")

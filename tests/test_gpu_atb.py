@@ -40,7 +40,8 @@ def test_rows_atb_tensor_core(n, gather, relu, with_colsum):
     _check(n, 64, 64, gather, relu, with_colsum)
 
 
-@pytest.mark.parametrize("n,ka,nb", [(100, 64, 64), (3000, 64, 64), (5000, 14, 64), (5000, 64, 1), (5000, 4, 64), (5000, 40, 24)])
+@pytest.mark.parametrize("n,ka,nb", [(100, 64, 64), (3000, 64, 64), (5000, 14, 64), (5000, 64, 1), (5000, 4, 64), (5000, 40, 24),
+                                     (70001, 64, 1), (70001, 4, 64), (70001, 3, 40), (70001, 40, 2), (500, 4, 64), (70001, 1, 1)])
 def test_rows_atb_cuda_core_shapes(n, ka, nb):
     _check(n, ka, nb, gather=True, relu=True, with_colsum=True)
 
