@@ -170,8 +170,11 @@ struct HwOwner {
       const float4 a = lds128(sl + own + chunk(q));
       v[4 * q + 0] = a.x; v[4 * q + 1] = a.y; v[4 * q + 2] = a.z; v[4 * q + 3] = a.w;
     }
+    uint32_t hi[16], lo[16];
+    split16(v, hi, lo);              // in front of the wait: only the two TMEM stores are left behind it
     if (k > 0) wait_d(c, t, k - 1);  // the previous chunk's MMAs have read the A columns
-    split_store16(tm_lane(c) + HW_A_HI + 16 * qd, tm_lane(c) + HW_A_LO + 16 * qd, v);
+    tmem_st16(tm_lane(c) + HW_A_HI + 16 * qd, hi);
+    tmem_st16(tm_lane(c) + HW_A_LO + 16 * qd, lo);
     tmem_st_wait();
     tc_fence_before_sync();
     __syncwarp();

@@ -236,8 +236,12 @@ struct NwOwner {
         float v[16];
         blk_to_row(c ? g1 : g0, v);
         if (p.zero_aggr) blk_zero(p.aggr, p.aggr_ld, tile_of(c, t));  // behind the loads of BOTH contexts
+        uint32_t hi[16], lo[16];
+        split16(v, hi, lo);  // in front of the wait: only the two TMEM stores are left behind it
         wait_d(c, t, 0);
-        to_a(c, v);
+        tmem_st16(tm_lane(c) + NW_A_HI + 16 * qd, hi);
+        tmem_st16(tm_lane(c) + NW_A_LO + 16 * qd, lo);
+        a_done(c);
       }
     }
   }

@@ -345,6 +345,23 @@ __device__ __forceinline__ void split_store16(uint32_t taddr_hi, uint32_t taddr_
   tmem_st16(taddr_lo, lo);
 }
 
+// the same in two steps -- split into registers, store later -- for stages that may compute in front of a barrier
+// wait and only have to store behind it
+__device__ __forceinline__ void split16(const float (&v)[16], uint32_t (&hi)[16], uint32_t (&lo)[16]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    f32x2 h, l;
+    split_tf32_act2(pack2(v[2 * j], v[2 * j + 1]), h, l);
+    float a, b;
+    unpack2(h, a, b);
+    hi[2 * j] = __float_as_uint(a);
+    hi[2 * j + 1] = __float_as_uint(b);
+    unpack2(l, a, b);
+    lo[2 * j] = __float_as_uint(a);
+    lo[2 * j + 1] = __float_as_uint(b);
+  }
+}
+
 // v[j] += x[j] on 16 values as 8 packed adds
 __device__ __forceinline__ void add16(float (&v)[16], const float4& x0, const float4& x1, const float4& x2, const float4& x3) {
   const float4 xs[4] = {x0, x1, x2, x3};
