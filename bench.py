@@ -377,9 +377,9 @@ def run_ours(args) -> None:
 
     # The step as ONE CUDA graph launch (graphs.CapturedForward: plan build + forward recorded over static input
     # buffers, replayed per step; same kernels, same work, no per-launch host time).  GTB_BENCH_NO_GRAPH=1: eager.
-    # N > 1: the NCCL exchanges would have to be captured too -- eager unless GTB_BENCH_GRAPH_MULTI=1.
+    # N > 1: the NCCL halo exchanges are recorded inside the graph as well (GTB_BENCH_GRAPH_MULTI=0: eager there).
     cap = None
-    if not os.environ.get("GTB_BENCH_NO_GRAPH") and (world == 1 or os.environ.get("GTB_BENCH_GRAPH_MULTI")):
+    if not os.environ.get("GTB_BENCH_NO_GRAPH") and (world == 1 or os.environ.get("GTB_BENCH_GRAPH_MULTI", "1") != "0"):
         from gnn_tracking_b200.graphs import CapturedForward
         try:
             cap = CapturedForward(model, x, ei, ea, halo=halo)
@@ -503,9 +503,23 @@ def run_ours(args) -> None:
         dist.all_reduce(hf, op=dist.ReduceOp.MAX)
         halo_frac = float(hf.item())
 
+    def leave():
+        """Tear-down at N > 1.  With NCCL exchanges recorded inside a CUDA graph (GTB_BENCH_GRAPH_MULTI=1)
+        ``destroy_process_group`` was seen to hang behind the finished run: the graph is dropped first and the process
+        then leaves without the collective tear-down (everything measured has been synchronised and printed)."""
+        nonlocal cap
+        if world == 1:
+            return
+        if cap is not None:
+            cap = None
+            torch.cuda.synchronize()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
+        dist.destroy_process_group()
+
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        leave()
         return
 
     peaks_file = ROOT / "MEASURED_PEAKS.json"
@@ -580,8 +594,7 @@ def run_ours(args) -> None:
         line["parity"] = {"vs": "oracle/in_oracle.py on the same full graph and weights", "tol": 1e-5,
                           "max_err_over_scale": parity_report(step_resident(), ref, "full-size bench graph")}
     emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+    leave()
 
 
 _RESULT_FD = None
