@@ -41,6 +41,7 @@ class CapturedForward:
             clear_plan_cache()
             self.out = self._run()
         self.launches = ops.launch_count() - l0  # kernels of the library inside one replay
+        self._weights = self._weight_key()
         clear_plan_cache()       # the captured plan lives in the graph's memory pool: not for eager callers
         _drop_scratch(model)
 
@@ -60,7 +61,13 @@ class CapturedForward:
         self.edge_index.copy_(edge_index, non_blocking=True)
         self.edge_attr.copy_(edge_attr, non_blocking=True)
 
+    def _weight_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.model.parameters())
+
     def replay(self):
+        if self._weight_key() != self._weights:  # the graph holds the PACKED weights of the capture
+            raise RuntimeError("the model's weights changed since the capture (optimizer step, load_state_dict, .to()): "
+                               "capture again")
         ops._count(self.launches)
         self.graph.replay()
         return self.out

@@ -36,3 +36,17 @@ def test_captured_forward_matches_eager(kw):
     # the eager path still works after a capture (no scratch shared with the graph's memory pool)
     with torch.no_grad():
         m.forward_tensors(*_graph(500, 6000, 5))
+
+
+def test_captured_forward_refuses_stale_weights():
+    from gnn_tracking_b200.graphs import CapturedForward
+    from gnn_tracking_b200.models.edge_classifier import ECForGraphTCN
+    torch.manual_seed(0)
+    m = ECForGraphTCN(node_indim=14, edge_indim=4, hidden_dim=64, L_ec=1).cuda()
+    g = _graph(500, 6000, 0)
+    fwd = CapturedForward(m, *g)
+    fwd(*g)
+    with torch.no_grad():
+        m.W.layers[0].weight.add_(1.0)  # bumps the version counter, as an optimizer step does
+    with pytest.raises(RuntimeError, match="capture again"):
+        fwd(*g)
