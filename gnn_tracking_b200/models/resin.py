@@ -176,12 +176,14 @@ class Skip2ResidualNetwork(ResidualNetwork):
     def __init__(self, layers: list[nn.Module], *, node_dim: int, edge_dim: int, add_bn: bool = False, **kwargs):
         if len(layers) % 2 != 0:
             raise ValueError("Only even number of layers allowed at the moment")
-        if add_bn:
-            raise NotImplementedError("Skip2ResidualNetwork(add_bn=True): batch norm is not on the B200 path")
         super().__init__(layers=layers, **kwargs)
-        # parameter-free placeholders keep the reference's module tree
-        self._node_batch_norms = nn.ModuleList([nn.Identity() for _ in layers])
-        self._edge_batch_norms = nn.ModuleList([nn.Identity() for _ in layers])
+        # the reference's module tree (resin.py:141-151): BatchNorm1d per layer input with ``add_bn``, else
+        # parameter-free placeholders.  The normalisation itself is the library's (torch.nn.BatchNorm1d: a
+        # column-wise affine map of an N x D / E x D table in front of a layer, batch statistics in training);
+        # it is row-permutation invariant, so it applies to destination-sorted edge tables unchanged.
+        self._add_bn = bool(add_bn)
+        self._node_batch_norms = nn.ModuleList([nn.BatchNorm1d(node_dim) if add_bn else nn.Identity() for _ in layers])
+        self._edge_batch_norms = nn.ModuleList([nn.BatchNorm1d(edge_dim) if add_bn else nn.Identity() for _ in layers])
 
     def _n_layer_calls(self) -> int:
         return 2 * max(len(self.layers) - 1, 0)
@@ -189,11 +191,23 @@ class Skip2ResidualNetwork(ResidualNetwork):
     def _call_sequence(self) -> list[int]:
         return [i for pair in pairwise(range(len(self.layers))) for i in pair]
 
+    def fused_ok(self, x, edge_attr, halo=None) -> bool:
+        return not self._add_bn and super().fused_ok(x, edge_attr, halo)  # the node launch hands x on un-normalised
+
+    def _bn(self, norms, i: int, t: Tensor) -> Tensor:
+        if not self._add_bn:
+            return t
+        out = norms[i](t)
+        return mark_sorted_edges(out) if has_sorted_edges(t) else out
+
     def _forward(self, x, plan, edge_attr):
         edge_attrs = [edge_attr] if self._collect_hidden_edge_embeds else None
         for i0, i1 in pairwise(range(len(self.layers))):
-            hx, he = self._layer(i0, x, plan, edge_attr, first=i0 == 0, residue=None)
-            x, edge_attr = self._layer(i1, hx, plan, he, first=False, residue=x)
+            # resin.py:157-168: act(bn(.)) in front of both layers; the residue is the un-normalised x
+            hx, he = self._layer(i0, self._bn(self._node_batch_norms, i0, x), plan, self._bn(self._edge_batch_norms, i0, edge_attr),
+                                 first=i0 == 0, residue=None)
+            x, edge_attr = self._layer(i1, self._bn(self._node_batch_norms, i1, hx), plan, self._bn(self._edge_batch_norms, i1, he),
+                                       first=False, residue=x)
             if edge_attrs is not None:
                 edge_attrs.append(edge_attr)
         return x, edge_attr, edge_attrs

@@ -95,7 +95,7 @@ def _n_layers(sd, prefix):
 
 
 def resin(x, edge_index, edge_attr, sd, prefix, *, alpha=0.5, residual_type="skip1", collect=False,
-          connect_to=1, add_bn=False):
+          connect_to=1, add_bn=False, bn_training=False):
     """``ResIN.forward`` models/resin.py:292-295 dispatching to the residual
     networks :99-114 (skip1), :153-175 (skip2, overlapping ``pairwise`` pairs
     reproduced literally), :197-216 (skip_top).  ``prefix`` points at
@@ -110,11 +110,18 @@ def resin(x, edge_index, edge_attr, sd, prefix, *, alpha=0.5, residual_type="ski
             if collect:
                 edge_attrs.append(edge_attr)
     elif residual_type == "skip2":
-        assert not add_bn, "oracle restates skip2 without batch norm"
+        def bn(kind, i, t):  # nn.BatchNorm1d of resin.py:141-151 (eps 1e-5; batch statistics when `training`)
+            if not add_bn:
+                return t
+            pre = f"{prefix}_{kind}_batch_norms.{i}."
+            return torch.nn.functional.batch_norm(t, sd[pre + "running_mean"].clone(), sd[pre + "running_var"].clone(),
+                                                  sd[pre + "weight"], sd[pre + "bias"], training=bn_training, momentum=0.1, eps=1e-5)
         for i0, i1 in pairwise(range(L)):
-            xin, ein = (x, edge_attr) if i0 == 0 else (torch.relu(x), torch.relu(edge_attr))
+            xn, en = bn("node", i0, x), bn("edge", i0, edge_attr)
+            xin, ein = (xn, en) if i0 == 0 else (torch.relu(xn), torch.relu(en))
             hx, he = interaction_network(xin, edge_index, ein, sd, f"{prefix}layers.{i0}.")
-            dx, edge_attr = interaction_network(torch.relu(hx), edge_index, torch.relu(he), sd, f"{prefix}layers.{i1}.")
+            dx, edge_attr = interaction_network(torch.relu(bn("node", i1, hx)), edge_index, torch.relu(bn("edge", i1, he)), sd,
+                                                f"{prefix}layers.{i1}.")
             x = sqconvex(dx, x, alpha)
             if collect:
                 edge_attrs.append(edge_attr)

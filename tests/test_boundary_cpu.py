@@ -188,3 +188,15 @@ def test_perfect_edge_classification():
     assert (w == torch.Tensor([False, False, True, False])).all()
     torch.manual_seed(0)
     assert 35 < PerfectEdgeClassification(tpr=0.5).forward(MockData(torch.full((100,), True)))["W"].sum() < 65
+
+
+def test_skip2_batch_norm_state_dict_contract():
+    """``add_bn=True`` keeps the reference's module tree: its state_dict (weights, running statistics,
+    num_batches_tracked of every BatchNorm1d) loads with ``strict=True``."""
+    from gnn_tracking_b200.models.resin import ResIN
+    from tests.golden.common import load
+    for case in load("resin_bn").values():
+        kw = {k: (dict(v) if isinstance(v, dict) else v) for k, v in case["kwargs"].items()}
+        m = ResIN(**kw)
+        m.load_state_dict(case["state_dict"], strict=True)
+        assert sorted(m.state_dict().keys()) == sorted(case["state_dict"].keys())

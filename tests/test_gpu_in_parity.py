@@ -198,3 +198,30 @@ def test_cpu_tensors_are_refused():
     m = InteractionNetwork(node_indim=2, edge_indim=2, node_outdim=2, edge_outdim=2)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(torch.zeros(3, 2), torch.zeros(2, 1, dtype=torch.long), torch.zeros(1, 2))
+
+
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_resin_skip2_batch_norm_vs_reference_golden(mode):
+    """``Skip2ResidualNetwork(add_bn=True)`` (resin.py:117-175) against outputs of the reference's own classes:
+    training mode (batch statistics) and eval mode (running statistics); a narrow and a 64-wide, 4-layer stack."""
+    from gnn_tracking_b200.models.resin import ResIN
+    from tests.golden.common import load, widen
+    graphs = load("graphs")
+    for name, case in load("resin_bn").items():
+        gd = widen(graphs[case["graph"]], *case["widen"])
+        kw = {k: (dict(v) if isinstance(v, dict) else v) for k, v in case["kwargs"].items()}
+        m = ResIN(**kw)
+        m.load_state_dict(case["state_dict"], strict=True)
+        m = m.cuda().train(mode == "train")
+        with torch.no_grad():
+            x, e, es = m(gd["x"].cuda(), gd["edge_index"].cuda(), gd["edge_attr"].cuda())
+        want = case["outputs"][mode]
+        close(x, want["x"], what=f"{name} {mode} x")
+        close(e, want["edge_attr"], what=f"{name} {mode} edge_attr")
+        for got, ref in zip(es, want.get("edge_attrs", [])):
+            close(got, ref, what=f"{name} {mode} edge_attrs")
+    # and it trains: gradients reach the batch-norm parameters through the fused layers
+    m.train()
+    x, e, _ = m(gd["x"].cuda(), gd["edge_index"].cuda(), gd["edge_attr"].cuda())
+    (x.sum() + e.sum()).backward()
+    assert all(p.grad is not None for p in m.parameters())

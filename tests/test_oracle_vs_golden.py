@@ -133,3 +133,24 @@ def test_oracle_graph_tcn_bf16_autocast_vs_reference_golden():
             err = float((out[k].float().reshape(r.shape) - r).abs().max())
             tol = 2 ** -7 if gname == "sector0" else 2.5e-2
             assert err <= tol * max(1.0, float(r.abs().max())), (gname, k, err)
+
+
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_oracle_skip2_batch_norm_vs_reference(mode):
+    """``Skip2ResidualNetwork(add_bn=True)`` (resin.py:117-175): the oracle's restatement against outputs of the
+    reference's own classes in training (batch statistics) and eval (running statistics) mode."""
+    from oracle import in_oracle as O
+    from tests.golden.common import load, widen
+    graphs = load("graphs")
+    for name, case in load("resin_bn").items():
+        gd = widen(graphs[case["graph"]], *case["widen"])
+        assert abs(float(gd["x"].double().sum()) - case["input_checksum"]) < 1e-6
+        kw = case["kwargs"]
+        with torch.no_grad():
+            x, e, es = O.resin(gd["x"], gd["edge_index"], gd["edge_attr"], case["state_dict"], "network.", alpha=kw["alpha"],
+                               residual_type="skip2", collect=True, add_bn=True, bn_training=mode == "train")
+        want = case["outputs"][mode]
+        for got, ref, what in ((x, want["x"], "x"), (e, want["edge_attr"], "edge_attr")):
+            assert float((got - ref).abs().max()) <= 1e-5 * max(1.0, float(ref.abs().max())), (name, mode, what)
+        for got, ref in zip(es, want.get("edge_attrs", [])):
+            assert float((got - ref).abs().max()) <= 1e-5 * max(1.0, float(ref.abs().max())), (name, mode)
