@@ -61,6 +61,9 @@ int edge_dist_pow_sum(const float*, int, const int64_t*, int64_t, const unsigned
 int radius_graph_count(const float*, int, int64_t, const int64_t*, float, int, int, int32_t*, cudaStream_t);
 int radius_graph_fill(const float*, int, int64_t, const int64_t*, float, int, int, const int64_t*, int64_t*, int64_t,
                       cudaStream_t);
+int radius_graph_grid_count(const float*, int, int64_t, const int64_t*, float, int, int, int32_t*, void*, size_t, cudaStream_t);
+int radius_graph_grid_fill(const float*, int, int64_t, const int64_t*, float, int, int, const int64_t*, int64_t*, int64_t, void*,
+                           size_t, cudaStream_t);
 int radius_pair_sum_grad(const float*, int, int64_t, const int64_t*, const int64_t*, const unsigned char*, const float*, float,
                          float, float, float, int, int, const float*, float*, float*, cudaStream_t);
 int edge_dist_pow_grad(const float*, int, const int64_t*, int64_t, const unsigned char*, float, const float*, float*,
@@ -375,6 +378,22 @@ int gtb_radius_graph_fill_f32(const float* x, int32_t d, int64_t n, const int64_
                               int32_t loop, const int64_t* offsets, int64_t* edge_index, int64_t n_edges, void* stream) {
   return radius_graph_fill(x, d, n, batch, r, max_num_neighbors, loop, offsets, edge_index, n_edges,
                            static_cast<cudaStream_t>(stream));
+}
+
+size_t gtb_radius_graph_grid_workspace_bytes(int64_t n) { return dbscan_grid_workspace_bytes(n); }
+
+int gtb_radius_graph_grid_count_f32(const float* x, int32_t d, int64_t n, const int64_t* batch, float r,
+                                    int32_t max_num_neighbors, int32_t loop, int32_t* counts, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  return radius_graph_grid_count(x, d, n, batch, r, max_num_neighbors, loop, counts, workspace, workspace_bytes,
+                                 static_cast<cudaStream_t>(stream));
+}
+
+int gtb_radius_graph_grid_fill_f32(const float* x, int32_t d, int64_t n, const int64_t* batch, float r,
+                                   int32_t max_num_neighbors, int32_t loop, const int64_t* offsets, int64_t* edge_index,
+                                   int64_t n_edges, void* workspace, size_t workspace_bytes, void* stream) {
+  return radius_graph_grid_fill(x, d, n, batch, r, max_num_neighbors, loop, offsets, edge_index, n_edges, workspace,
+                                workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int gtb_radius_pair_sum_grad_f32(const float* x, int32_t d, int64_t n, const int64_t* batch, const int64_t* pid,

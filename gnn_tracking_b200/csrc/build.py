@@ -13,7 +13,7 @@ from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
 LIB = HERE / "libgtb200.so"
-SOURCES = ["api.cu", "plan.cu", "mlp_ffma.cu", "mlp_tc.cu", "edge_ws.cu", "node_ws.cu", "enc_ws.cu", "head_ws.cu", "losses.cu", "oc.cu", "grad.cu", "atb_tc.cu", "radius.cu", "dbscan.cu", "dbscan_grid.cu"]
+SOURCES = ["api.cu", "plan.cu", "mlp_ffma.cu", "mlp_tc.cu", "edge_ws.cu", "node_ws.cu", "enc_ws.cu", "head_ws.cu", "losses.cu", "oc.cu", "grad.cu", "atb_tc.cu", "radius.cu", "dbscan.cu", "cell_list.cu"]
 HEADERS = [HERE / "common.cuh", HERE.parents[1] / "include" / "gtb200.h"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

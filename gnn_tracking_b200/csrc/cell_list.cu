@@ -1,17 +1,22 @@
-// DBSCAN over a uniform cell list (the neighbour search SURVEY 2a K6 / 8f-2 names): same results as
-// dbscan.cu -- labels identical to sklearn's -- without the N^2 candidate walk.
+// Uniform cell list over a low-dimensional latent space (the neighbour search SURVEY 2a K6 / 8f-2 / 8f-3 names), and
+// the two fixed-radius searches built on it: the DBSCAN trial (same results as dbscan.cu -- labels identical to
+// sklearn's) and the materialised radius graph (same edge list as radius.cu's all-pairs walk), without the N^2
+// candidate walk.
 //
 // The points are binned on their first min(d, 3) coordinates into cells at least eps wide, so every
 // neighbour (dist <= eps) of a point lies in the 3^k cells around its own; the full-dimensional distance
-// test is the one of dbscan.cu (fp32 screen, float64 decision on the rim).  Per call (= one trial of the
-// hyper-parameter scan, postprocessing/dbscanscanner.py:146-187; eps changes from trial to trial, so the
-// grid is rebuilt -- a 21-bit radix sort of the cell ids):
+// tests are the ones of dbscan.cu (fp32 screen, float64 decision on the rim) and radius.cu (fp32, strict).
+// Per build (DBSCAN: one trial of the hyper-parameter scan, postprocessing/dbscanscanner.py:146-187; eps changes
+// from trial to trial, so the grid is rebuilt -- a 21-bit radix sort of the cell ids):
 //   bounding box -> cell ids -> sort (cell id, point) -> cell_begin[] -> coordinates in cell order
+// DBSCAN passes:
 //   pass 0: neighbour counts -> core flags        pass 1: union-find of the core samples
 //   pass 2: roots (core: own component, border: smallest adjacent root, noise: -1)
 // Everything visible to the caller (core, parent, root) is indexed by the ORIGINAL point index, and the
 // outcome does not depend on the order in which neighbours are visited (components are rooted at their
 // lowest index, a border point takes the smallest adjacent root), so the numbering equals dbscan_inner's.
+// Radius-graph passes: count (neighbours per centre, capped), fill (sorted insertion into the centre's segment
+// of the edge list: ascending neighbours, the lowest indices kept under the cap -- radius.cu's order).
 #include <cub/cub.cuh>
 
 #include "common.cuh"
@@ -249,40 +254,63 @@ size_t dbscan_grid_workspace_bytes(int64_t n) {
          dg_align((size_t)n * DG_MAXD * 4) + dg_align(dg_cub_bytes(n));
 }
 
-template <int D>
-static int dg_run(const float* x, int d, int64_t n, double eps, int min_pts, unsigned char* core, int* parent, int* root,
-                  char* ws, cudaStream_t st) {
-  unsigned* mm = reinterpret_cast<unsigned*>(ws);
-  DgGrid* grid = reinterpret_cast<DgGrid*>(ws + 256);
+struct DgWs {  // the workspace, carved
+  unsigned* mm;
+  DgGrid* grid;
+  int32_t *keys, *vals, *keys_s, *idx_s, *cell_begin;
+  float* xs;
+  char* cub;
+};
+
+static DgWs dg_carve(char* ws, int64_t n) {
+  DgWs w;
+  w.mm = reinterpret_cast<unsigned*>(ws);
+  w.grid = reinterpret_cast<DgGrid*>(ws + 256);
   char* p = ws + 512;
-  int32_t* keys = reinterpret_cast<int32_t*>(p); p += dg_align((size_t)n * 4);
-  int32_t* vals = reinterpret_cast<int32_t*>(p); p += dg_align((size_t)n * 4);
-  int32_t* keys_s = reinterpret_cast<int32_t*>(p); p += dg_align((size_t)n * 4);
-  int32_t* idx_s = reinterpret_cast<int32_t*>(p); p += dg_align((size_t)n * 4);
-  int32_t* cell_begin = reinterpret_cast<int32_t*>(p); p += dg_align(((size_t)1 << DG_CELL_BITS) * 4 + 8);
-  float* xs = reinterpret_cast<float*>(p); p += dg_align((size_t)n * DG_MAXD * 4);
+  w.keys = reinterpret_cast<int32_t*>(p); p += dg_align((size_t)n * 4);
+  w.vals = reinterpret_cast<int32_t*>(p); p += dg_align((size_t)n * 4);
+  w.keys_s = reinterpret_cast<int32_t*>(p); p += dg_align((size_t)n * 4);
+  w.idx_s = reinterpret_cast<int32_t*>(p); p += dg_align((size_t)n * 4);
+  w.cell_begin = reinterpret_cast<int32_t*>(p); p += dg_align(((size_t)1 << DG_CELL_BITS) * 4 + 8);
+  w.xs = reinterpret_cast<float*>(p); p += dg_align((size_t)n * DG_MAXD * 4);
+  w.cub = p;
+  return w;
+}
+
+// the cell list of x for search radius eps, into the workspace
+template <int D>
+static int dg_build(const float* x, int d, int64_t n, double eps, const DgWs& w, cudaStream_t st) {
   size_t cub_bytes = dg_cub_bytes(n);
   const int k = d < 3 ? d : 3;
   const int threads = 256;
   const int blocks = (int)imin64((n + threads - 1) / threads, (int64_t)kNumSMs * 8);
-  int rc = check_cuda(cudaMemsetAsync(mm, 0xff, 12, st), "dbscan grid: init");  // running minima
-  if (rc == GTB_OK) rc = check_cuda(cudaMemsetAsync(mm + 3, 0, 12, st), "dbscan grid: init");  // running maxima
+  int rc = check_cuda(cudaMemsetAsync(w.mm, 0xff, 12, st), "cell list: init");  // running minima
+  if (rc == GTB_OK) rc = check_cuda(cudaMemsetAsync(w.mm + 3, 0, 12, st), "cell list: init");  // running maxima
   if (rc) return rc;
-  dg_bbox_kernel<<<blocks, threads, 0, st>>>(x, d, n, k, mm);
+  dg_bbox_kernel<<<blocks, threads, 0, st>>>(x, d, n, k, w.mm);
   GTB_CHECK_LAUNCH("dg_bbox_kernel");
-  dg_setup_kernel<<<1, 32, 0, st>>>(mm, k, eps, grid);
+  dg_setup_kernel<<<1, 32, 0, st>>>(w.mm, k, eps, w.grid);
   GTB_CHECK_LAUNCH("dg_setup_kernel");
-  dg_keys_kernel<<<blocks, threads, 0, st>>>(x, d, n, grid, keys, vals);
+  dg_keys_kernel<<<blocks, threads, 0, st>>>(x, d, n, w.grid, w.keys, w.vals);
   GTB_CHECK_LAUNCH("dg_keys_kernel");
-  rc = check_cuda(cub::DeviceRadixSort::SortPairs(p, cub_bytes, keys, keys_s, vals, idx_s, (int)n, 0, DG_CELL_BITS, st),
-                  "dbscan grid: SortPairs");
+  rc = check_cuda(cub::DeviceRadixSort::SortPairs(w.cub, cub_bytes, w.keys, w.keys_s, w.vals, w.idx_s, (int)n, 0, DG_CELL_BITS, st),
+                  "cell list: SortPairs");
   if (rc) return rc;
-  dg_layout_kernel<D><<<blocks, threads, 0, st>>>(x, d, n, grid, keys_s, idx_s, cell_begin, xs);
+  dg_layout_kernel<D><<<blocks, threads, 0, st>>>(x, d, n, w.grid, w.keys_s, w.idx_s, w.cell_begin, w.xs);
   GTB_CHECK_LAUNCH("dg_layout_kernel");
+  return GTB_OK;
+}
+
+template <int D>
+static int dg_run(const float* x, int d, int64_t n, double eps, int min_pts, unsigned char* core, int* parent, int* root,
+                  char* ws, cudaStream_t st) {
+  const DgWs w = dg_carve(ws, n);
+  int rc = dg_build<D>(x, d, n, eps, w, st);
+  if (rc) return rc;
   const double eps2 = eps * eps;
   const int pb = (int)((n + DG_T - 1) / DG_T);
   for (int phase = 0; phase < 3; ++phase) {
-    dg_pass_kernel<D><<<pb, DG_T, 0, st>>>(xs, n, grid, keys_s, idx_s, cell_begin, eps2, min_pts, phase, core, parent, root);
+    dg_pass_kernel<D><<<pb, DG_T, 0, st>>>(w.xs, n, w.grid, w.keys_s, w.idx_s, w.cell_begin, eps2, min_pts, phase, core, parent, root);
     GTB_CHECK_LAUNCH("dg_pass_kernel");
   }
   return GTB_OK;
@@ -300,6 +328,137 @@ int dbscan_grid(const float* x, int d, int64_t n, double eps, int min_pts, unsig
   if (d <= 4) return dg_run<4>(x, d, n, eps, min_pts, core, parent, root, ws, st);
   if (d <= 8) return dg_run<8>(x, d, n, eps, min_pts, core, parent, root, ws, st);
   return dg_run<16>(x, d, n, eps, min_pts, core, parent, root, ws, st);
+}
+
+// ---------------------------------------------------------------- radius graph over the cell list
+// torch_cluster.radius_graph semantics as in radius.cu (strict fp32 ||x_i - x_j||^2 < r^2 accumulated over the
+// coordinates in order, same batch entry, at most max_nb neighbours per centre: the lowest indices, ascending).
+// The zero padding of the coordinates to D adds exact zeros to the sum, so the fp32 distance -- and with it
+// the edge list -- is bit-identical to the all-pairs walk.  The cells are 1e-5 wider than r: a pair two cells
+// apart differs by more than the cell width in one coordinate, which fp32 rounding (6e-8 relative per
+// operation) cannot bring back below r^2.
+// One thread per centre (in cell order).  FILL: the centre's segment of the edge list is kept sorted while
+// the candidates arrive cell by cell (ascending inside a cell: the radix sort is stable), so most insertions
+// are appends; over the cap a smaller index displaces the largest one.
+template <int D, bool FILL>
+__global__ void __launch_bounds__(DG_T) rg_pass_kernel(const float* __restrict__ xs, int64_t n, const DgGrid* __restrict__ grid,
+                                                       const int32_t* __restrict__ keys_sorted,
+                                                       const int32_t* __restrict__ idx_sorted,
+                                                       const int32_t* __restrict__ cell_begin,
+                                                       const int64_t* __restrict__ batch, float r2, int max_nb, int loop,
+                                                       int32_t* __restrict__ counts, const int64_t* __restrict__ offsets,
+                                                       int64_t* __restrict__ edge_index, int64_t n_edges) {
+  const DgGrid gr = *grid;
+  const int64_t p = (int64_t)blockIdx.x * DG_T + threadIdx.x;
+  if (p >= n) return;
+  const int i = idx_sorted[p];
+  float xi[D];
+#pragma unroll
+  for (int c = 0; c < D; ++c) xi[c] = xs[p * D + c];
+  const long long batch_i = batch ? batch[i] : 0;
+  int64_t* seg = FILL ? edge_index + offsets[i] : nullptr;
+  int cell = keys_sorted[p];
+  const int ic = cell % gr.g[2];
+  cell /= gr.g[2];
+  const int ib = cell % gr.g[1], ia = cell / gr.g[1];
+  const int c_lo = max(ic - 1, 0), c_hi = min(ic + 1, gr.g[2] - 1);
+  int kept = 0;
+  for (int a = max(ia - 1, 0); a <= min(ia + 1, gr.g[0] - 1); ++a)
+    for (int b = max(ib - 1, 0); b <= min(ib + 1, gr.g[1] - 1); ++b) {
+      const int base = (a * gr.g[1] + b) * gr.g[2];
+      const int q_end = cell_begin[base + c_hi + 1];
+      for (int q = cell_begin[base + c_lo]; q < q_end; ++q) {
+        const float* xj = xs + (int64_t)q * D;
+        float v[D];
+#pragma unroll
+        for (int w = 0; w < D / 4; ++w) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(xj) + w);
+          v[4 * w] = t.x; v[4 * w + 1] = t.y; v[4 * w + 2] = t.z; v[4 * w + 3] = t.w;
+        }
+        float d2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          const float t = xi[c] - v[c];
+          d2 = fmaf(t, t, d2);
+        }
+        if (!(d2 < r2)) continue;
+        const int j = idx_sorted[q];
+        if (!loop && j == i) continue;
+        if (batch && batch[j] != batch_i) continue;
+        if (!FILL) {
+          ++kept;
+        } else if (kept < max_nb || (long long)j < seg[kept - 1]) {
+          int pos = kept < max_nb ? kept++ : kept - 1;  // free slot at the end, or the largest kept index leaves
+          while (pos > 0 && seg[pos - 1] > (long long)j) {
+            seg[pos] = seg[pos - 1];
+            --pos;
+          }
+          seg[pos] = j;
+        }
+      }
+    }
+  if (!FILL) {
+    counts[i] = min(kept, max_nb);
+  } else {
+    int64_t* centre = seg + n_edges;
+    for (int k = 0; k < kept; ++k) centre[k] = i;
+  }
+}
+
+template <int D>
+static int rg_count(const float* x, int d, int64_t n, const int64_t* batch, float r, int max_nb, int loop, int32_t* counts,
+                    char* ws, cudaStream_t st) {
+  const DgWs w = dg_carve(ws, n);
+  int rc = dg_build<D>(x, d, n, fabs((double)r) * (1.0 + 1e-5), w, st);
+  if (rc) return rc;
+  rg_pass_kernel<D, false><<<(int)((n + DG_T - 1) / DG_T), DG_T, 0, st>>>(w.xs, n, w.grid, w.keys_s, w.idx_s, w.cell_begin, batch,
+                                                                         r * r, max_nb, loop, counts, nullptr, nullptr, 0);
+  GTB_CHECK_LAUNCH("rg_pass_kernel<count>");
+  return GTB_OK;
+}
+
+template <int D>
+static int rg_fill(int64_t n, const int64_t* batch, float r, int max_nb, int loop, const int64_t* offsets, int64_t* edge_index,
+                   int64_t n_edges, char* ws, cudaStream_t st) {
+  const DgWs w = dg_carve(ws, n);
+  rg_pass_kernel<D, true><<<(int)((n + DG_T - 1) / DG_T), DG_T, 0, st>>>(w.xs, n, w.grid, w.keys_s, w.idx_s, w.cell_begin, batch,
+                                                                        r * r, max_nb, loop, nullptr, offsets, edge_index, n_edges);
+  GTB_CHECK_LAUNCH("rg_pass_kernel<fill>");
+  return GTB_OK;
+}
+
+static int rg_check(const char* who, const void* x, int d, int64_t n, int max_nb, const void* workspace, size_t workspace_bytes) {
+  GTB_REQUIRE(x && d >= 1 && d <= DG_MAXD && n < (1ll << 31) - 1 && max_nb >= 1, GTB_ERR_BAD_ARG,
+              "%s: bad arguments (dimension must be in [1, %d])", who, DG_MAXD);
+  GTB_REQUIRE(workspace != nullptr && workspace_bytes >= dbscan_grid_workspace_bytes(n), GTB_ERR_WORKSPACE, "%s: workspace too small", who);
+  GTB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, GTB_ERR_BAD_ARG, "%s: workspace must be 256-byte aligned", who);
+  return GTB_OK;
+}
+
+// builds the cell list in the workspace and counts; radius_graph_grid_fill walks the SAME workspace
+int radius_graph_grid_count(const float* x, int d, int64_t n, const int64_t* batch, float r, int max_nb, int loop, int32_t* counts,
+                            void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  int rc = rg_check("gtb_radius_graph_grid_count_f32", x, d, n, max_nb, workspace, workspace_bytes);
+  if (rc) return rc;
+  GTB_REQUIRE(counts != nullptr || n == 0, GTB_ERR_BAD_ARG, "gtb_radius_graph_grid_count_f32: counts is null");
+  if (n == 0) return GTB_OK;
+  char* ws = static_cast<char*>(workspace);
+  if (d <= 4) return rg_count<4>(x, d, n, batch, r, max_nb, loop, counts, ws, st);
+  if (d <= 8) return rg_count<8>(x, d, n, batch, r, max_nb, loop, counts, ws, st);
+  return rg_count<16>(x, d, n, batch, r, max_nb, loop, counts, ws, st);
+}
+
+int radius_graph_grid_fill(const float* x, int d, int64_t n, const int64_t* batch, float r, int max_nb, int loop,
+                           const int64_t* offsets, int64_t* edge_index, int64_t n_edges, void* workspace, size_t workspace_bytes,
+                           cudaStream_t st) {
+  int rc = rg_check("gtb_radius_graph_grid_fill_f32", x, d, n, max_nb, workspace, workspace_bytes);
+  if (rc) return rc;
+  GTB_REQUIRE(offsets && (edge_index || n_edges == 0), GTB_ERR_BAD_ARG, "gtb_radius_graph_grid_fill_f32: bad arguments");
+  if (n == 0 || n_edges == 0) return GTB_OK;
+  char* ws = static_cast<char*>(workspace);
+  if (d <= 4) return rg_fill<4>(n, batch, r, max_nb, loop, offsets, edge_index, n_edges, ws, st);
+  if (d <= 8) return rg_fill<8>(n, batch, r, max_nb, loop, offsets, edge_index, n_edges, ws, st);
+  return rg_fill<16>(n, batch, r, max_nb, loop, offsets, edge_index, n_edges, ws, st);
 }
 
 }  // namespace gtb

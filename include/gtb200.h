@@ -359,6 +359,19 @@ int gtb_radius_graph_count_f32(const float* x, int32_t d, int64_t n, const int64
 int gtb_radius_graph_fill_f32(const float* x, int32_t d, int64_t n, const int64_t* batch, float r,
                               int32_t max_num_neighbors, int32_t loop, const int64_t* offsets,
                               int64_t* edge_index, int64_t n_edges, void* stream);
+/* The same edge list (bit-identical) over the uniform cell list of gtb_dbscan_grid_f32 instead of the
+ * all-pairs walk (the grid hash behind torch_cluster's radius search).  count builds the
+ * cell list (cells r wide on the first min(d, 3) coordinates) in the workspace and counts; fill must be
+ * given the SAME workspace, untouched in between, on the same stream.
+ * workspace: gtb_radius_graph_grid_workspace_bytes(n) bytes, 256-byte aligned. */
+size_t gtb_radius_graph_grid_workspace_bytes(int64_t n);
+int gtb_radius_graph_grid_count_f32(const float* x, int32_t d, int64_t n, const int64_t* batch, float r,
+                                    int32_t max_num_neighbors, int32_t loop, int32_t* counts, void* workspace,
+                                    size_t workspace_bytes, void* stream);
+int gtb_radius_graph_grid_fill_f32(const float* x, int32_t d, int64_t n, const int64_t* batch, float r,
+                                   int32_t max_num_neighbors, int32_t loop, const int64_t* offsets,
+                                   int64_t* edge_index, int64_t n_edges, void* workspace, size_t workspace_bytes,
+                                   void* stream);
 
 /* Gradients of the two sums above (what torch autograd derives for the reference's
  * norm / pow / relu chain over the radius-graph and true edges, metric_learning.py:14-54, oc.py:46-69;

@@ -188,11 +188,16 @@ def test_radius_loss_gradients(cap, p_attr, p_rep):
     check("rg beta", bc.grad, br.grad)
 
 
+@pytest.mark.parametrize("method", ["grid", "brute"])
 @pytest.mark.parametrize("cap,loop,with_batch", [(32, False, True), (4, False, False), (1000, True, True)])
-def test_radius_graph_edge_list(cap, loop, with_batch):
+def test_radius_graph_edge_list(cap, loop, with_batch, method):
     """The materialised radius graph against the oracle's restatement of torch_cluster.radius_graph:
-    identical edge list (integer output: bit-exact), including the neighbour cap and batch segments."""
-    from gnn_tracking_b200.cluster import radius_graph
+    identical edge list (integer output: bit-exact), including the neighbour cap and batch segments --
+    over the cell list (default) and by the all-pairs walk."""
+    from functools import partial
+
+    from gnn_tracking_b200 import cluster
+    radius_graph = partial(cluster.radius_graph, method=method)
     from oracle import losses_oracle as L
     gen = torch.Generator().manual_seed(5)
     n = 1500
@@ -209,3 +214,40 @@ def test_radius_graph_edge_list(cap, loop, with_batch):
     assert radius_graph(torch.zeros((0, 3), device="cuda"), 1.0).shape == (2, 0)
     flipped = radius_graph(x.cuda(), 0.5, max_num_neighbors=cap, flow="target_to_source")
     assert torch.equal(flipped.flip(0), radius_graph(x.cuda(), 0.5, max_num_neighbors=cap))
+
+
+@pytest.mark.parametrize("n,d,r,cap", [(20000, 3, 0.08, 64), (20000, 8, 0.9, 16), (5000, 1, 0.001, 8), (5000, 2, 0.05, 3),
+                                       (3000, 12, 2.5, 256), (700, 3, 50.0, 100), (4000, 4, -0.2, 32), (2000, 3, 0.0, 8)])
+def test_radius_graph_grid_equals_brute_force(n, d, r, cap):
+    """Cell list against the all-pairs walk at sizes the python oracle does not reach: the same fp32 distances
+    decide, so the edge lists are bit-identical -- clustered points (dense cells, the cap bites), duplicates,
+    a radius above the box (one cell), r <= 0 (r*r decides, as in the walk), batch segments."""
+    from gnn_tracking_b200.cluster import radius_graph
+    gen = torch.Generator().manual_seed(n + d)
+    centres = torch.randn(40, d, generator=gen) * 2
+    x = centres[torch.randint(0, 40, (n,), generator=gen)] + 0.1 * torch.randn(n, d, generator=gen)
+    x[n // 2: n // 2 + 50] = x[:50]                       # exact duplicates
+    x[-1] = 40.0                                          # an outlier stretches the box
+    batch = torch.sort(torch.randint(0, 3, (n,), generator=gen)).values
+    xc, bc = x.cuda(), batch.cuda()
+    for b in (None, bc):
+        for loop in (False, True):
+            grid = radius_graph(xc, r, batch=b, loop=loop, max_num_neighbors=cap, method="grid")
+            brute = radius_graph(xc, r, batch=b, loop=loop, max_num_neighbors=cap, method="brute")
+            assert grid.shape == brute.shape and torch.equal(grid, brute), (n, d, r, cap, loop)
+    if r > 0:
+        assert brute.size(1) > 0
+
+
+def test_radius_graph_grid_non_finite_coordinates():
+    """NaN / Inf coordinates match nothing in either search (the distance test fails), wherever they are binned."""
+    from gnn_tracking_b200.cluster import radius_graph
+    gen = torch.Generator().manual_seed(9)
+    x = torch.rand(3000, 3, generator=gen)
+    x[5, 0] = float("nan")
+    x[17, 2] = float("inf")
+    x[99, 1] = float("-inf")
+    xc = x.cuda()
+    grid, brute = radius_graph(xc, 0.1, method="grid"), radius_graph(xc, 0.1, method="brute")
+    assert torch.equal(grid, brute)
+    assert not torch.isin(grid, torch.tensor([5, 17, 99], device="cuda")).any()
