@@ -93,6 +93,9 @@ SIGNATURES = {
     "gtb_radius_graph_count_f32": (C.c_int, [_vp, _i32, _i64, _vp, _f32, _i32, _i32, _vp, _vp]),
     "gtb_radius_graph_fill_f32": (C.c_int, [_vp, _i32, _i64, _vp, _f32, _i32, _i32, _vp, _vp, _i64, _vp]),
     "gtb_radius_graph_grid_workspace_bytes": (_sz, [_i64]),
+    "gtb_radius_pair_sum_grid_f32": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _i32, _i32, _vp, _vp, _sz, _vp]),
+    "gtb_radius_pair_sum_grad_grid_f32": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _i32, _i32, _vp, _vp, _vp,
+                                                     _vp, _sz, _vp]),
     "gtb_radius_graph_grid_count_f32": (C.c_int, [_vp, _i32, _i64, _vp, _f32, _i32, _i32, _vp, _vp, _sz, _vp]),
     "gtb_radius_graph_grid_fill_f32": (C.c_int, [_vp, _i32, _i64, _vp, _f32, _i32, _i32, _vp, _vp, _i64, _vp, _sz, _vp]),
     "gtb_radius_pair_sum_grad_f32": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _i32, _i32, _vp, _vp, _vp, _vp]),

@@ -61,6 +61,8 @@ int edge_dist_pow_sum(const float*, int, const int64_t*, int64_t, const unsigned
 int radius_graph_count(const float*, int, int64_t, const int64_t*, float, int, int, int32_t*, cudaStream_t);
 int radius_graph_fill(const float*, int, int64_t, const int64_t*, float, int, int, const int64_t*, int64_t*, int64_t,
                       cudaStream_t);
+int radius_pair_sum_grid(const float*, int, int64_t, const int64_t*, const int64_t*, const unsigned char*, const float*, float, float,
+                         float, float, int, int, double*, const float*, float*, float*, void*, size_t, cudaStream_t);
 int radius_graph_grid_count(const float*, int, int64_t, const int64_t*, float, int, int, int32_t*, void*, size_t, cudaStream_t);
 int radius_graph_grid_fill(const float*, int, int64_t, const int64_t*, float, int, int, const int64_t*, int64_t*, int64_t, void*,
                            size_t, cudaStream_t);
@@ -381,6 +383,24 @@ int gtb_radius_graph_fill_f32(const float* x, int32_t d, int64_t n, const int64_
 }
 
 size_t gtb_radius_graph_grid_workspace_bytes(int64_t n) { return dbscan_grid_workspace_bytes(n); }
+
+int gtb_radius_pair_sum_grid_f32(const float* x, int32_t d, int64_t n, const int64_t* batch, const int64_t* pid,
+                                 const uint8_t* src_flag, const float* beta, float q_min, float r, float p, float eps,
+                                 int32_t max_num_neighbors, int32_t mode, double* out, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
+  GTB_REQUIRE(out != nullptr, GTB_ERR_BAD_ARG, "gtb_radius_pair_sum_grid_f32: out is null");
+  return radius_pair_sum_grid(x, d, n, batch, pid, src_flag, beta, q_min, r, p, eps, max_num_neighbors, mode, out, nullptr,
+                              nullptr, nullptr, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int gtb_radius_pair_sum_grad_grid_f32(const float* x, int32_t d, int64_t n, const int64_t* batch, const int64_t* pid,
+                                      const uint8_t* src_flag, const float* beta, float q_min, float r, float p, float eps,
+                                      int32_t max_num_neighbors, int32_t mode, const float* coef, float* gx, float* gq,
+                                      void* workspace, size_t workspace_bytes, void* stream) {
+  GTB_REQUIRE(coef != nullptr, GTB_ERR_BAD_ARG, "gtb_radius_pair_sum_grad_grid_f32: coef is null");
+  return radius_pair_sum_grid(x, d, n, batch, pid, src_flag, beta, q_min, r, p, eps, max_num_neighbors, mode, nullptr, coef, gx,
+                              gq, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
+}
 
 int gtb_radius_graph_grid_count_f32(const float* x, int32_t d, int64_t n, const int64_t* batch, float r,
                                     int32_t max_num_neighbors, int32_t loop, int32_t* counts, void* workspace,

@@ -461,4 +461,194 @@ int radius_graph_grid_fill(const float* x, int d, int64_t n, const int64_t* batc
   return rg_fill<16>(n, batch, r, max_nb, loop, offsets, edge_index, n_edges, ws, st);
 }
 
+// ---------------------------------------------------------------- fused pair sums over the cell list
+// radius.cu's radius_pair_sum_kernel (the repulsive terms of the hinge and condensation losses, fused with the
+// neighbour search: metric_learning.py:93-112, oc.py:46-69, 115-117) without the all-pairs walk.  Same edges
+// (same fp32 distance test, same cap: the max_nb lowest neighbour indices of a centre), same fp32 terms; the
+// float64 sums and the float atomics of the gradient add them in another order.
+// The candidates of a centre arrive cell by cell, not in index order, so the cap is applied through a
+// threshold: walk 1 counts the neighbours; only if they exceed the cap, a bisection over the index range
+// (log2 n more walks, for that centre alone) finds the max_nb-th smallest neighbour index; walk 2 takes the
+// neighbours up to it.
+template <int D, class F>
+__device__ __forceinline__ void rg_walk(const float* __restrict__ xs, const DgGrid& gr, const int32_t* __restrict__ cell_begin,
+                                        int ia, int ib, int ic, const float (&xi)[D], float r2, F f) {
+  const int c_lo = max(ic - 1, 0), c_hi = min(ic + 1, gr.g[2] - 1);
+  for (int a = max(ia - 1, 0); a <= min(ia + 1, gr.g[0] - 1); ++a)
+    for (int b = max(ib - 1, 0); b <= min(ib + 1, gr.g[1] - 1); ++b) {
+      const int base = (a * gr.g[1] + b) * gr.g[2];
+      const int q_end = cell_begin[base + c_hi + 1];
+      for (int q = cell_begin[base + c_lo]; q < q_end; ++q) {
+        const float* xj = xs + (int64_t)q * D;
+        float v[D];
+#pragma unroll
+        for (int w = 0; w < D / 4; ++w) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(xj) + w);
+          v[4 * w] = t.x; v[4 * w + 1] = t.y; v[4 * w + 2] = t.z; v[4 * w + 3] = t.w;
+        }
+        float d2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          const float t = xi[c] - v[c];
+          d2 = fmaf(t, t, d2);
+        }
+        if (d2 < r2) f(q, d2, v);
+      }
+    }
+}
+
+// modes, outputs and GRAD as radius_pair_sum_kernel (radius.cu)
+template <int D, bool GRAD>
+__global__ void __launch_bounds__(DG_T) rg_pair_sum_kernel(
+    const float* __restrict__ xs, int d, int64_t n, const DgGrid* __restrict__ grid, const int32_t* __restrict__ keys_sorted,
+    const int32_t* __restrict__ idx_sorted, const int32_t* __restrict__ cell_begin, const int64_t* __restrict__ batch,
+    const int64_t* __restrict__ pid, const unsigned char* __restrict__ src_flag, const float* __restrict__ beta, float q_min,
+    float r, float p, float eps, int max_nb, int mode, double* __restrict__ out, const float* __restrict__ coef,
+    float* __restrict__ gx, float* __restrict__ gq) {
+  __shared__ double red[4][DG_T / 32];
+  const DgGrid gr = *grid;
+  const int tid = threadIdx.x;
+  const float r2 = r * r;
+  const float c0 = GRAD ? __ldg(coef) : 0.f;
+  double acc = 0.0, cnt_e = 0.0, nsum = 0.0, ncnt = 0.0;
+  const int64_t pos = (int64_t)blockIdx.x * DG_T + tid;
+  if (pos < n) {
+    const int i = idx_sorted[pos];
+    float xi[D], gi[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      xi[c] = xs[pos * D + c];
+      gi[c] = 0.f;
+    }
+    float gqi = 0.f;
+    const long long pid_i = pid[i], batch_i = batch ? batch[i] : 0;
+    float q_i = 0.f;
+    if (beta) {
+      const float b = __ldg(beta + i), a = atanhf(b);
+      q_i = a * a + q_min;
+      if (pid_i == 0) {
+        nsum += (double)b;
+        ncnt += 1.0;
+      }
+    }
+    int cell = keys_sorted[pos];
+    const int ic = cell % gr.g[2];
+    cell /= gr.g[2];
+    const int ib = cell % gr.g[1], ia = cell / gr.g[1];
+    int n_nb = 0;
+    rg_walk<D>(xs, gr, cell_begin, ia, ib, ic, xi, r2, [&](int q, float, const float (&)[D]) {
+      const int j = idx_sorted[q];
+      if (j != i && (!batch || batch[j] == batch_i)) ++n_nb;
+    });
+    int thr = 0x7fffffff;
+    if (n_nb > max_nb) {  // smallest T with #{neighbours j <= T} >= max_nb
+      int lo = 0, hi = (int)n - 1;
+      while (lo < hi) {
+        const int mid = lo + (hi - lo) / 2;
+        int c = 0;
+        rg_walk<D>(xs, gr, cell_begin, ia, ib, ic, xi, r2, [&](int q, float, const float (&)[D]) {
+          const int j = idx_sorted[q];
+          if (j <= mid && j != i && (!batch || batch[j] == batch_i)) ++c;
+        });
+        if (c >= max_nb) hi = mid;
+        else lo = mid + 1;
+      }
+      thr = lo;
+    }
+    if (n_nb > 0)
+      rg_walk<D>(xs, gr, cell_begin, ia, ib, ic, xi, r2, [&](int q, float d2, const float (&v)[D]) {
+        const int j = idx_sorted[q];
+        if (j > thr || j == i || (batch && batch[j] != batch_i)) return;
+        if (!src_flag[j] || pid[j] == pid_i) return;
+        float q_j = 0.f;
+        if (beta) {
+          const float a = atanhf(__ldg(beta + j));
+          q_j = a * a + q_min;
+        }
+        if (!GRAD) {
+          float term;
+          if (mode == 0) term = fmaxf(r - powf(sqrtf(d2), p), 0.f);
+          else term = (r - sqrtf(eps + d2)) * q_j * q_i;
+          acc += (double)term;
+          cnt_e += 1.0;
+        } else {
+          float w = 0.f;
+          if (mode == 0) {
+            const float dist = sqrtf(d2);
+            if (dist > 0.f && r - powf(dist, p) > 0.f) w = -c0 * p * powf(dist, p - 2.f);
+          } else {
+            const float s = sqrtf(eps + d2), qq = q_j * q_i;
+            w = -c0 * qq / s;
+            gqi += c0 * (r - s) * q_j;
+            atomicAdd(gq + j, c0 * (r - s) * q_i);
+          }
+          if (w != 0.f) {
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+              if (c < d) {
+                const float g = w * (xi[c] - v[c]);
+                gi[c] += g;
+                atomicAdd(gx + (size_t)j * d + c, -g);
+              }
+            }
+          }
+        }
+      });
+    if (GRAD) {
+#pragma unroll
+      for (int c = 0; c < D; ++c)
+        if (c < d && gi[c] != 0.f) atomicAdd(gx + (size_t)i * d + c, gi[c]);
+      if (mode == 1 && gqi != 0.f) atomicAdd(gq + i, gqi);
+    }
+  }
+  if (GRAD) return;
+  double v[4] = {acc, cnt_e, nsum, ncnt};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    if ((tid & 31) == 0) red[k][tid >> 5] = v[k];
+  }
+  __syncthreads();
+  if (tid < 4) {
+    double s = 0.0;
+    for (int w = 0; w < DG_T / 32; ++w) s += red[tid][w];
+    if (s != 0.0) atomicAdd(out + tid, s);
+  }
+}
+
+template <int D>
+static int rg_pair(const float* x, int d, int64_t n, const int64_t* batch, const int64_t* pid, const unsigned char* src_flag,
+                   const float* beta, float q_min, float r, float p, float eps, int max_nb, int mode, double* out,
+                   const float* coef, float* gx, float* gq, char* ws, cudaStream_t st) {
+  const DgWs w = dg_carve(ws, n);
+  int rc = dg_build<D>(x, d, n, fabs((double)r) * (1.0 + 1e-5), w, st);
+  if (rc) return rc;
+  const int blocks = (int)((n + DG_T - 1) / DG_T);
+  if (coef == nullptr)
+    rg_pair_sum_kernel<D, false><<<blocks, DG_T, 0, st>>>(w.xs, d, n, w.grid, w.keys_s, w.idx_s, w.cell_begin, batch, pid, src_flag,
+                                                          beta, q_min, r, p, eps, max_nb, mode, out, nullptr, nullptr, nullptr);
+  else
+    rg_pair_sum_kernel<D, true><<<blocks, DG_T, 0, st>>>(w.xs, d, n, w.grid, w.keys_s, w.idx_s, w.cell_begin, batch, pid, src_flag,
+                                                         beta, q_min, r, p, eps, max_nb, mode, nullptr, coef, gx, gq);
+  GTB_CHECK_LAUNCH("rg_pair_sum_kernel");
+  return GTB_OK;
+}
+
+// forward (coef == nullptr: out += the four sums) or gradient (coef != nullptr: gx, gq += the gradient), see
+// radius_pair_sum / radius_pair_sum_grad in radius.cu
+int radius_pair_sum_grid(const float* x, int d, int64_t n, const int64_t* batch, const int64_t* pid, const unsigned char* src_flag,
+                         const float* beta, float q_min, float r, float p, float eps, int max_nb, int mode, double* out,
+                         const float* coef, float* gx, float* gq, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  const char* who = coef ? "gtb_radius_pair_sum_grad_grid_f32" : "gtb_radius_pair_sum_grid_f32";
+  int rc = rg_check(who, x, d, n, max_nb, workspace, workspace_bytes);
+  if (rc) return rc;
+  GTB_REQUIRE(pid && src_flag && (mode == 0 || (mode == 1 && beta != nullptr)) && (coef ? (gx && (mode == 0 || gq)) : out != nullptr),
+              GTB_ERR_BAD_ARG, "%s: bad arguments", who);
+  if (n == 0) return GTB_OK;
+  char* ws = static_cast<char*>(workspace);
+  if (d <= 4) return rg_pair<4>(x, d, n, batch, pid, src_flag, beta, q_min, r, p, eps, max_nb, mode, out, coef, gx, gq, ws, st);
+  if (d <= 8) return rg_pair<8>(x, d, n, batch, pid, src_flag, beta, q_min, r, p, eps, max_nb, mode, out, coef, gx, gq, ws, st);
+  return rg_pair<16>(x, d, n, batch, pid, src_flag, beta, q_min, r, p, eps, max_nb, mode, out, coef, gx, gq, ws, st);
+}
+
 }  // namespace gtb

@@ -5,6 +5,8 @@ particles.  The radius graph is never built: ``gtb_radius_pair_sum_f32`` walks t
 and sums the hinge terms in one pass (torch_cluster.radius_graph semantics, see include/gtb200.h)."""
 from __future__ import annotations
 
+import os
+
 import torch
 from torch import Tensor
 
@@ -15,9 +17,20 @@ from ...utils.graph_masks import get_good_node_mask_tensors
 from . import MultiLossFct, MultiLossFctReturn
 
 
+def _grid_workspace(n: int, dev) -> tuple[Tensor, int]:
+    ws_bytes = lib().gtb_radius_graph_grid_workspace_bytes(n)
+    return torch.empty(ws_bytes, dtype=torch.uint8, device=dev), ws_bytes
+
+
+def _use_grid() -> bool:
+    """Neighbour search of the pair sums: the uniform cell list (``gtb_radius_pair_sum_grid_f32``) unless
+    ``GTB_RADIUS_BRUTE=1`` asks for the all-pairs walk (``gtb_radius_pair_sum_f32``): same edges, same terms."""
+    return os.environ.get("GTB_RADIUS_BRUTE") != "1"
+
+
 class _RadiusPairSumFn(torch.autograd.Function):
-    """``gtb_radius_pair_sum_f32`` with the gradient of its first output (the sum of the pair terms)
-    w.r.t. ``x`` and, in mode 1, ``beta`` (``gtb_radius_pair_sum_grad_f32``); the third output (sum
+    """``gtb_radius_pair_sum[_grid]_f32`` with the gradient of its first output (the sum of the pair terms)
+    w.r.t. ``x`` and, in mode 1, ``beta`` (``gtb_radius_pair_sum_grad[_grid]_f32``); the third output (sum
     of ``beta`` over ``pid == 0``) is differentiated in place."""
 
     @staticmethod
@@ -26,10 +39,16 @@ class _RadiusPairSumFn(torch.autograd.Function):
         dev = x.device
         n, d = x.shape
         out = torch.zeros(4, dtype=torch.float64, device=dev)
-        check(lib().gtb_radius_pair_sum_f32(x.data_ptr(), d, n, None if b is None else b.data_ptr(), pid.data_ptr(), flag.data_ptr(),
-                                            None if bt is None else bt.data_ptr(), q_min, r, p, eps, max_nb, mode, out.data_ptr(),
-                                            ops.stream_ptr(dev)))
-        ops._count(1)
+        args = (x.data_ptr(), d, n, None if b is None else b.data_ptr(), pid.data_ptr(), flag.data_ptr(),
+                None if bt is None else bt.data_ptr(), q_min, r, p, eps, max_nb, mode, out.data_ptr())
+        if _use_grid() and n > 0:
+            ws, ws_bytes = _grid_workspace(n, dev)
+            with ops.on_device(dev):
+                check(lib().gtb_radius_pair_sum_grid_f32(*args, ws.data_ptr(), ws_bytes, ops.stream_ptr(dev)))
+            ops._count(6)  # cell list (bounding box, grid, keys, sort, layout) + the pair sums
+        else:
+            check(lib().gtb_radius_pair_sum_f32(*args, ops.stream_ptr(dev)))
+            ops._count(1)
         ctx.save_for_backward(x, pid, flag, *([bt] if bt is not None else []), *([b] if b is not None else []))
         ctx.cfg, ctx.has = cfg, (bt is not None, b is not None)
         return out
@@ -47,11 +66,17 @@ class _RadiusPairSumFn(torch.autograd.Function):
         coef = g[0:1].to(torch.float32).contiguous()
         gx = torch.zeros((n, d), dtype=torch.float32, device=dev)
         gq = torch.zeros(n, dtype=torch.float32, device=dev) if mode == 1 else None
-        check(lib().gtb_radius_pair_sum_grad_f32(x.data_ptr(), d, n, None if b is None else b.data_ptr(), pid.data_ptr(),
-                                                 flag.data_ptr(), None if bt is None else bt.data_ptr(), q_min, r, p, eps, max_nb,
-                                                 mode, coef.data_ptr(), gx.data_ptr(), None if gq is None else gq.data_ptr(),
-                                                 ops.stream_ptr(dev)))
-        ops._count(1)
+        args = (x.data_ptr(), d, n, None if b is None else b.data_ptr(), pid.data_ptr(), flag.data_ptr(),
+                None if bt is None else bt.data_ptr(), q_min, r, p, eps, max_nb, mode, coef.data_ptr(), gx.data_ptr(),
+                None if gq is None else gq.data_ptr())
+        if _use_grid() and n > 0:
+            ws, ws_bytes = _grid_workspace(n, dev)
+            with ops.on_device(dev):
+                check(lib().gtb_radius_pair_sum_grad_grid_f32(*args, ws.data_ptr(), ws_bytes, ops.stream_ptr(dev)))
+            ops._count(6)
+        else:
+            check(lib().gtb_radius_pair_sum_grad_f32(*args, ops.stream_ptr(dev)))
+            ops._count(1)
         gbeta = None
         if bt is not None:
             gbeta = (pid == 0).to(torch.float32) * g[2].to(torch.float32)

@@ -365,6 +365,17 @@ int gtb_radius_graph_fill_f32(const float* x, int32_t d, int64_t n, const int64_
  * given the SAME workspace, untouched in between, on the same stream.
  * workspace: gtb_radius_graph_grid_workspace_bytes(n) bytes, 256-byte aligned. */
 size_t gtb_radius_graph_grid_workspace_bytes(int64_t n);
+/* gtb_radius_pair_sum_f32 / gtb_radius_pair_sum_grad_f32 over the same cell list: same edges, same fp32
+ * terms (sums in another order).  Each call builds the cell list in the workspace (same size as above). */
+int gtb_radius_pair_sum_grid_f32(const float* x, int32_t d, int64_t n, const int64_t* batch, const int64_t* pid,
+                                 const uint8_t* src_flag, const float* beta, float q_min, float r, float p,
+                                 float eps, int32_t max_num_neighbors, int32_t mode, double* out, void* workspace,
+                                 size_t workspace_bytes, void* stream);
+int gtb_radius_pair_sum_grad_grid_f32(const float* x, int32_t d, int64_t n, const int64_t* batch,
+                                      const int64_t* pid, const uint8_t* src_flag, const float* beta, float q_min,
+                                      float r, float p, float eps, int32_t max_num_neighbors, int32_t mode,
+                                      const float* coef, float* gx, float* gq, void* workspace,
+                                      size_t workspace_bytes, void* stream);
 int gtb_radius_graph_grid_count_f32(const float* x, int32_t d, int64_t n, const int64_t* batch, float r,
                                     int32_t max_num_neighbors, int32_t loop, int32_t* counts, void* workspace,
                                     size_t workspace_bytes, void* stream);

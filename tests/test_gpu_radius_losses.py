@@ -11,6 +11,16 @@ pytestmark = pytest.mark.gpu
 RTOL = 2e-5
 
 
+@pytest.fixture(autouse=True, params=["grid", "brute"])
+def neighbour_search(request, monkeypatch):
+    """Every test of this file runs over the cell list (default) and over the all-pairs walk."""
+    if request.param == "brute":
+        monkeypatch.setenv("GTB_RADIUS_BRUTE", "1")
+    else:
+        monkeypatch.delenv("GTB_RADIUS_BRUTE", raising=False)
+    return request.param
+
+
 def _close(got, ref, what):
     g, r = float(got), float(ref)
     if r != r:
@@ -251,3 +261,42 @@ def test_radius_graph_grid_non_finite_coordinates():
     grid, brute = radius_graph(xc, 0.1, method="grid"), radius_graph(xc, 0.1, method="brute")
     assert torch.equal(grid, brute)
     assert not torch.isin(grid, torch.tensor([5, 17, 99], device="cuda")).any()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("n,d,r,cap", [(20000, 3, 0.1, 256), (20000, 3, 0.1, 5), (6000, 8, 0.9, 16), (3000, 2, 0.0, 4)])
+def test_pair_sum_grid_equals_brute_force(n, d, r, cap, mode, monkeypatch):
+    """gtb_radius_pair_sum[_grad]_grid_f32 against the all-pairs walk on clustered points: the same edges (count
+    exact, also where the neighbour cap truncates -- the threshold bisection), the same fp32 terms (float64 sums
+    to 1e-12), gradients to float-atomics accuracy."""
+    from gnn_tracking_b200.metrics.losses.metric_learning import radius_pair_sum
+    gen = torch.Generator().manual_seed(7 * n + d + mode)
+    centres = torch.randn(30, d, generator=gen) * 2
+    x = (centres[torch.randint(0, 30, (n,), generator=gen)] + 0.1 * torch.randn(n, d, generator=gen)).cuda()
+    pid = torch.randint(0, 300, (n,), generator=gen).cuda()
+    flag = (torch.rand(n, generator=gen) < (0.3 if mode == 1 else 0.8)).cuda()
+    batch = torch.sort(torch.randint(0, 2, (n,), generator=gen)).values.cuda()
+    beta = (torch.rand(n, generator=gen) * 0.98 + 0.01).cuda() if mode == 1 else None
+    res = {}
+    for method in ("grid", "brute"):
+        if method == "brute":
+            monkeypatch.setenv("GTB_RADIUS_BRUTE", "1")
+        else:
+            monkeypatch.delenv("GTB_RADIUS_BRUTE", raising=False)
+        xg = x.clone().requires_grad_(True)
+        bg = None if beta is None else beta.clone().requires_grad_(True)
+        out = radius_pair_sum(x=xg, particle_id=pid, src_flag=flag, r=r, mode=mode, batch=batch, beta=bg, q_min=0.01, p=1.0,
+                              max_num_neighbors=cap)
+        (out[0] * 0.5 + (out[2] if mode == 1 else 0.0)).backward()
+        res[method] = (out.detach(), xg.grad, None if bg is None else bg.grad)
+    (og, xg_g, bg_g), (ob, xg_b, bg_b) = res["grid"], res["brute"]
+    assert float(og[1]) == float(ob[1]) and float(og[3]) == float(ob[3])
+    if r > 0:
+        assert float(ob[1]) > 0
+    assert float(og[0]) == pytest.approx(float(ob[0]), rel=1e-12, abs=1e-12)
+    assert float(og[2]) == pytest.approx(float(ob[2]), rel=1e-12, abs=1e-12)
+    scale = float(xg_b.abs().max()) + 1e-20
+    assert float((xg_g - xg_b).abs().max()) <= 2e-5 * scale
+    if bg_b is not None:
+        scale = float(bg_b.abs().max()) + 1e-20
+        assert float((bg_g - bg_b).abs().max()) <= 2e-5 * scale
