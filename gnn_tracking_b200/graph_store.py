@@ -273,16 +273,80 @@ class DevicePrefetcher:
                 done.popleft().synchronize()
 
 
+def shard_paths(paths, rank: int, world_size: int) -> list:
+    """The files of one rank when ``world_size`` processes walk the same list, one graph per step each (the
+    reference trains through Lightning's DDP strategy, whose ``DistributedSampler(shuffle=False)`` this follows):
+    the list is padded by wrapping around to a multiple of ``world_size`` so that every rank takes the same number
+    of steps (the gradient all-reduce needs them in lockstep), then rank r takes entries r, r + W, r + 2W, ..."""
+    paths = list(paths)
+    if world_size < 1 or not 0 <= rank < world_size:
+        raise ValueError(f"rank {rank} outside a world of {world_size}")
+    if world_size == 1 or not paths:
+        return paths
+    total = -(-len(paths) // world_size) * world_size
+    padded = paths + [paths[i % len(paths)] for i in range(total - len(paths))]
+    return padded[rank::world_size]
+
+
+def gpu_local_cpus(device: torch.device | str | int) -> set[int]:
+    """CPUs on the NUMA node the GPU hangs off (NVML's ideal affinity), restricted to the ones this process may
+    use; empty if NVML cannot tell."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        index = torch.device(device).index if not isinstance(device, int) else device
+        if index is None:
+            index = torch.cuda.current_device()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if visible:  # NVML numbers the physical devices
+            entry = visible.split(",")[index].strip()
+            handle = pynvml.nvmlDeviceGetHandleByUUID(entry) if entry.startswith("GPU-") else \
+                pynvml.nvmlDeviceGetHandleByIndex(int(entry))
+        else:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_words = (os.cpu_count() + 63) // 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, n_words)
+    except Exception:  # noqa: BLE001 - no NVML, no affinity information, a container without the device node
+        return set()
+    cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+    return cpus & os.sched_getaffinity(0)
+
+
+def bind_thread_near_gpu(device: torch.device | str | int) -> bool:
+    """Pin the CALLING thread to the CPUs next to the GPU, so that the pinned staging buffers it allocates and
+    fills are first touched on that NUMA node and the host-to-device copies do not cross the socket link.
+    Returns False (and changes nothing) when the topology is unknown."""
+    import os
+    cpus = gpu_local_cpus(device)
+    if not cpus:
+        return False
+    os.sched_setaffinity(0, cpus)  # tid 0 = the calling thread on Linux
+    return True
+
+
 class GraphLoader:
     """Iterates over graph files one graph per step (the reference trains with ``batch_size=1``,
     ``utils/loading.py:235``): a reader thread fills pinned staging buffers ``prefetch`` files ahead
-    and a ``DevicePrefetcher`` keeps the copy of the next graph in flight under the current step."""
+    and a ``DevicePrefetcher`` keeps the copy of the next graph in flight under the current step.
 
-    def __init__(self, paths, device: torch.device | str = "cuda", *, prefetch: int = 2, pinned: bool | None = None):
-        self.paths = [Path(p) for p in paths]
+    One process per GPU: every rank builds the loader over the SAME file list and walks its own share
+    (``shard_paths``; ``rank`` / ``world_size`` default to the initialised process group, else one process).
+    ``numa_local=True`` runs the reader thread on the CPUs next to this rank's GPU (``bind_thread_near_gpu``)."""
+
+    def __init__(self, paths, device: torch.device | str = "cuda", *, prefetch: int = 2, pinned: bool | None = None,
+                 rank: int | None = None, world_size: int | None = None, numa_local: bool = False):
+        if rank is None or world_size is None:
+            import torch.distributed as dist
+            on = dist.is_available() and dist.is_initialized()
+            rank = (dist.get_rank() if on else 0) if rank is None else rank
+            world_size = (dist.get_world_size() if on else 1) if world_size is None else world_size
+        self.paths = [Path(p) for p in shard_paths(paths, rank, world_size)]
+        self.rank, self.world_size = rank, world_size
         self.device = torch.device(device)
         self.pinned = self.device.type == "cuda" if pinned is None else pinned
         self.prefetch = max(1, int(prefetch))
+        self.numa_local = bool(numa_local) and self.device.type == "cuda"
 
     def __len__(self) -> int:
         return len(self.paths)
@@ -296,6 +360,8 @@ class GraphLoader:
 
         def reader():
             try:
+                if self.numa_local:
+                    bind_thread_near_gpu(self.device)
                 for p in self.paths:
                     if stop.is_set():
                         return

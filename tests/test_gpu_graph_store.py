@@ -58,7 +58,8 @@ def test_prefetched_graphs_give_the_same_results(tmp_path):
         gs.write_graph(paths[-1], **g)
         with torch.no_grad():
             want.append(m(gs.GraphData(**{k: v.cuda() for k, v in g.items()}))["W"].clone())
-    for source in (gs.DevicePrefetcher(graphs), gs.GraphLoader(paths, prefetch=2)):
+    for source in (gs.DevicePrefetcher(graphs), gs.GraphLoader(paths, prefetch=2),
+                   gs.GraphLoader(paths, prefetch=2, numa_local=True)):  # reader thread on the GPU's NUMA node
         clear_plan_cache()
         got = []
         with torch.no_grad():
@@ -84,3 +85,28 @@ def test_result_reader_returns_every_step_result():
         del w
         reader.wait(host=True)
         assert float(host[0]) == k + 0.5 and float(host[-1]) == k + 0.5 and float(host.sum()) == (k + 0.5) * (1 << 20)
+
+
+def test_reader_thread_binds_next_to_the_gpu():
+    """``bind_thread_near_gpu`` narrows the calling thread to NVML's ideal CPUs for the device (or reports that
+    the topology is unknown and leaves the thread alone); the main thread is untouched."""
+    import os
+    import threading
+
+    from gnn_tracking_b200 import graph_store as gs
+    before = os.sched_getaffinity(0)
+    seen = {}
+
+    def work():
+        seen["bound"] = gs.bind_thread_near_gpu("cuda:0")
+        seen["cpus"] = os.sched_getaffinity(0)
+
+    th = threading.Thread(target=work)
+    th.start()
+    th.join()
+    assert os.sched_getaffinity(0) == before
+    local = gs.gpu_local_cpus("cuda:0")
+    if seen["bound"]:
+        assert seen["cpus"] == local and local <= before and local
+    else:
+        assert not local and seen["cpus"] == before

@@ -59,3 +59,36 @@ def test_graph_loader_prefetch(tmp_path):
             break
     with pytest.raises(FileNotFoundError):
         list(gs.GraphLoader([paths[0], tmp_path / "missing.gtb"], device="cpu"))
+
+
+def test_shard_paths_follows_distributed_sampler():
+    """One process per GPU: rank r walks entries r, r + W, ... of the list padded by wrap-around, the order of
+    torch's ``DistributedSampler(shuffle=False)`` (what Lightning's DDP strategy gives the reference's loaders)."""
+    import pytest
+    from torch.utils.data import DistributedSampler
+    for n_files in (1, 5, 8, 9):
+        files = [f"g{i}" for i in range(n_files)]
+        for world in (1, 2, 3, 8):
+            shares = [gs.shard_paths(files, r, world) for r in range(world)]
+            assert len({len(s) for s in shares}) == 1                      # every rank takes the same number of steps
+            assert set().union(*map(set, shares)) == set(files)            # every file is visited
+            for r in range(world):
+                want = list(DistributedSampler(files, num_replicas=world, rank=r, shuffle=False))
+                assert shares[r] == [files[i] for i in want]
+    assert gs.shard_paths([], 1, 2) == []
+    with pytest.raises(ValueError):
+        gs.shard_paths(["a"], 2, 2)
+
+
+def test_graph_loader_rank_share(tmp_path):
+    paths = []
+    for i in range(5):
+        paths.append(tmp_path / f"g{i}.gtb")
+        gs.write_graph(paths[-1], **_graph(n=100 + i, e=300, seed=i))
+    seen = [[d.num_nodes for d in gs.GraphLoader(paths, device="cpu", rank=r, world_size=2)] for r in range(2)]
+    assert seen == [[100, 102, 104], [101, 103, 100]]
+    assert len(gs.GraphLoader(paths, device="cpu", rank=1, world_size=2)) == 3
+    # without an initialised process group: one process, every file
+    assert len(gs.GraphLoader(paths, device="cpu")) == 5
+    # no GPU here: the topology is unknown, nothing is bound
+    assert gs.gpu_local_cpus(0) == set() or isinstance(gs.gpu_local_cpus(0), set)
